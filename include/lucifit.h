@@ -1,0 +1,131 @@
+/* lucifit.h -- C ABI of the B200-native LUCI fitting path (liblucifit.so).
+ *
+ * LUCI (crhea93/LUCI) is pure Python and has no FFI of its own; the seam this library plugs into is the
+ * process boundary of its row worker:
+ *
+ *   joblib.Parallel(...)(delayed(Luci.fit_calc)(row, ...))        LuciBase.py:514-530, 691-705
+ *   Luci.fit_calc(i, x_min, x_max, y_min, fit_function, lines, vel_rel, sigma_rel, cube_slice, ...)
+ *       -> (i, ampls, flux, flux_errs, vels, vels_errs, broads, broads_errs, chi2, corr, step,
+ *           continuum, continuum_errs)                              LuciBase.py:258-268, 406
+ *   np.nansum(cube, axis=2) chunks (create_deep_image)              LuciBase.py:171-178
+ *   SNR_calc(i) per row (create_snr_map)                            LuciBase.py:1109-1175
+ *   bin_cube_function                                               LUCI/LuciUtility.py:319-355
+ *
+ * One lucifit_fit_batch call replaces the whole Parallel(...) loop for one GPU's shard of spaxels.
+ *
+ * Conventions: plain C, no exceptions cross the boundary; every function returns 0 on success or a negative
+ * LUCIFIT_E* code and leaves a message for lucifit_last_error() (thread-local).  The library never allocates
+ * or frees caller-visible memory: all buffers are DEVICE pointers owned by the caller (PyTorch tensors in the
+ * Python glue), plus a caller-provided device workspace whose size is queried first.  All work is enqueued on
+ * the caller's stream (passed as void* == cudaStream_t); calls are re-entrant per (device, stream).
+ */
+#ifndef LUCIFIT_H
+#define LUCIFIT_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define LUCIFIT_MAX_LINES 8
+
+#define LUCIFIT_OK 0
+#define LUCIFIT_EINVAL (-1)      /* bad argument / unsupported configuration */
+#define LUCIFIT_EWORKSPACE (-2)  /* workspace too small */
+#define LUCIFIT_ECUDA (-3)       /* a CUDA runtime call failed */
+
+enum { LUCIFIT_GAUSSIAN = 0, LUCIFIT_SINC = 1, LUCIFIT_SINCGAUSS = 2 };
+
+/* Per-spaxel status word written to out_status: bits 0-7 accepted LM iterations, bits 8-15 model+Jacobian
+ * evaluations, flags from bit 16. */
+#define LUCIFIT_ST_CONVERGED (1 << 16)
+#define LUCIFIT_ST_MAXITER (1 << 17)
+#define LUCIFIT_ST_BOUND (1 << 18)       /* a parameter sits on its box (LuciFit.py:614-633, 539-541) */
+#define LUCIFIT_ST_SINGULAR (1 << 19)
+#define LUCIFIT_ST_NAN_INPUT (1 << 20)   /* spectrum contains NaN: zeros are returned (cf. LuciBase.py:358-360, 393-405) */
+#define LUCIFIT_ST_MASKED (1 << 21)
+#define LUCIFIT_ST_BAD_NORM (1 << 22)    /* max(spectrum) <= 0 */
+
+/* Per-call constants (HOST memory).  Mirrors the arguments of Fit.__init__ (LUCI/LuciFit.py:49-57) that do not
+ * vary from spaxel to spaxel. */
+typedef struct lucifit_config {
+    int model;                                /* LUCIFIT_GAUSSIAN / _SINC / _SINCGAUSS   (model_type) */
+    int n_lines;                              /* L <= LUCIFIT_MAX_LINES                  (lines) */
+    double line_nm[LUCIFIT_MAX_LINES];        /* rest wavelengths, nm                    (line_dict, LuciFit.py:90-99) */
+    int vel_group[LUCIFIT_MAX_LINES];         /* vel_rel   (any integer labels) */
+    int sigma_group[LUCIFIT_MAX_LINES];       /* sigma_rel (any integer labels) */
+    int nii6548_idx, nii6583_idx;             /* indices of the [NII] doublet when nii_cons applies, else -1 */
+    int nz;                                   /* spectral samples per spaxel */
+    const double* axis;                       /* [nz] HOST: float32-rounded axis * (1 + obj_redshift), widened */
+    int fit_lo, fit_hi;                       /* argmin|axis - spec_min|, argmin|axis - spec_max|  (LuciFit.py:273-274) */
+    int noise_lo, noise_hi;                   /* noise window indices                              (LuciFit.py:327-328) */
+    int cont_lo, cont_hi;                     /* continuum window indices                          (LuciFit.py:476-477) */
+    double step_nm;                           /* hdr['STEP']   (delta_x) */
+    double n_steps;                           /* hdr['STEPNB'] (n_steps) */
+    double zpd_index;                         /* hdr['ZPDINDEX'] */
+    const double* transmission;               /* [nz] HOST transmission_interpolated, or NULL (LuciFit.py:197-207) */
+    int uncertainty;                          /* uncertainty_bool */
+    int scale_mode;                           /* 1: ML-prior path scale (LuciFit.py:374-375); 0: max(spectrum) (:782) */
+    int max_iter;                             /* LM iteration cap (0 -> 60) */
+    double ftol;                              /* predicted relative decrease of sum r^2 that counts as converged (0 -> 1e-8) */
+} lucifit_config;
+
+/* Number of floats per spaxel in out_rows: 7 L + 5, ordered
+ *   amplitudes[L] fluxes[L] flux_errors[L] velocities[L] vels_errors[L] sigmas[L] sigmas_errors[L]
+ *   chi2 corr axis_step continuum continuum_error           (the 12 lists of Luci.fit_calc, LuciBase.py:406) */
+int lucifit_row_floats(int n_lines);
+
+/* Device workspace needed by lucifit_fit_batch for this configuration (independent of n_spaxel). */
+int lucifit_workspace_bytes(const lucifit_config* cfg, int64_t n_spaxel, size_t* bytes);
+
+/* Fit n_spaxel spectra.
+ *   cube         [*, nz] float32 DEVICE, z contiguous; spaxel s reads row (spaxel_index ? spaxel_index[s] : s)
+ *   spaxel_index optional DEVICE int64 list (mask compaction) or NULL
+ *   theta_deg    [n_spaxel] DEVICE interferometer angle of each fitted spaxel (LuciBase.py:369)
+ *   vel0, broad0 [n_spaxel] DEVICE prior velocity / broadening in km/s (what the CNN writes to vel_ml / broad_ml,
+ *                LuciFit.py:356-361), either may be NULL (-> 0, the reference's ML_bool=False behaviour)
+ *   bkg          [nz] DEVICE background spectrum already multiplied by binning^2, or NULL (LuciBase.py:326-330)
+ *   out_rows     [n_spaxel][7L+5] DEVICE float32
+ *   out_fit_sol  optional [n_spaxel][3L+1] DEVICE: fit_sol (amplitude, position cm^-1, sigma cm^-1)*L, continuum
+ *   out_unc      optional [n_spaxel][3L+1] DEVICE: fit_uncertainties in the same layout
+ *   out_status   [n_spaxel] DEVICE int32 status words
+ */
+int lucifit_fit_batch(const lucifit_config* cfg, int64_t n_spaxel, const float* cube,
+                      const int64_t* spaxel_index, const float* theta_deg, const float* vel0, const float* broad0,
+                      const float* bkg, float* out_rows, float* out_fit_sol, float* out_unc, int32_t* out_status,
+                      void* workspace, size_t workspace_bytes, void* stream);
+
+/* Deep image: deep[s] = nansum_z cube[s][z] for s < n_spaxel - n_zero_tail, 0 for the rest
+ * (create_deep_image leaves the trailing nx mod 10 x-rows zero, LuciBase.py:173-177). */
+int lucifit_deep_image(const float* cube, int64_t n_spaxel, int nz, int64_t n_zero_tail, float* deep,
+                       void* stream);
+
+/* SNR map (LuciBase.py:1142-1172).  method 1: (nanmax - nanmean)/sqrt(std(noise window)), 0 if negative, else
+ * divided by sqrt(nanmean|sky|).  method 2: max(0, (nansum(flux window) - n * min(sigma_clip(sky, 1, 10 iters)))
+ * / std(noise window)).  If deep != NULL the same pass also writes the deep image (cube read once). */
+int lucifit_snr_map(const float* cube, int64_t n_spaxel, int nz, int method, int flux_lo, int flux_hi,
+                    int noise_lo, int noise_hi, float* snr, float* deep, void* stream);
+
+/* b x b nansum binning of the region [x0,x1) x [y0,y1) of cube[nx][ny][nz] -> binned[(x1-x0)/b][(y1-y0)/b][nz]
+ * (bin_cube_function, LUCI/LuciUtility.py:332-341; no division). */
+int lucifit_bin_cube(const float* cube, int nx, int ny, int nz, int b, int x0, int x1, int y0, int y1,
+                     float* binned, void* stream);
+
+/* Synthetic LuciSim-style cube written straight into HBM (benchmark input; LUCI/LuciSim.py:159-203):
+ * spectrum[s][z] = flux_scale * (continuum + sum_k amp[s][k] * profile(axis[z]; centre snapped to the axis,
+ * sigma from broad[s]) + noise_sigma[s] * noise[s][z]) where noise is caller-provided N(0,1) draws (or NULL). */
+int lucifit_sim_cube(const lucifit_config* cfg, int64_t n_spaxel, const float* amp /*[n][L]*/,
+                     const float* vel /*[n]*/, const float* broad /*[n]*/, const float* theta_deg /*[n]*/,
+                     const float* noise_sigma /*[n]*/, const float* noise /*[n][nz] or NULL*/, float continuum,
+                     float flux_scale, float* cube /*[n][nz]*/, void* workspace, size_t workspace_bytes,
+                     void* stream);
+
+const char* lucifit_last_error(void);
+const char* lucifit_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* LUCIFIT_H */

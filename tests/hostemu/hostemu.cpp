@@ -1,0 +1,74 @@
+// TEST INFRASTRUCTURE ONLY -- compiles the device fit pipeline (luci_b200/csrc/lucifit_core.cuh) for the CPU
+// with LANES = 1 so that the GPU-less test tier can exercise the very same prep / LM / uncertainty / output code
+// against the oracle.  Never loaded by the luci_b200 package.
+#include <stdlib.h>
+#include <vector>
+
+#include "../../luci_b200/csrc/lucifit_host.hpp"
+#include "../../luci_b200/csrc/lucifit_instances.h"
+
+template <int MODEL, int L, int NG>
+static void run_batch(const LfPlan& pl, int64_t n, const float* cube, const int64_t* index, const float* theta,
+                      const float* vel0, const float* broad0, float* out_rows, float* out_sol, float* out_unc,
+                      int32_t* status)
+{
+    LfWarp<1> w;
+    std::vector<unsigned char> buf(pl.per_warp_bytes + 64);
+    unsigned char* base = buf.data();
+    base += (16 - ((uintptr_t)base & 15)) & 15;
+    LfScratch sc = lf_scratch_at(pl, base);
+    float* spec = reinterpret_cast<float*>(base);
+    const int K = 7 * L + 5, PF = 3 * L + 1;
+    for (int64_t s = 0; s < n; ++s) {
+        int64_t row = index ? index[s] : s;
+        lf_fit_spaxel<MODEL, L, NG, NG, 1>(pl.dev, w, pl.dev.xo, cube + row * (int64_t)pl.dev.nz, theta[s],
+                                           vel0 ? vel0[s] : 0.0f, broad0 ? broad0[s] : 0.0f, spec, sc,
+                                           out_rows + s * K, status + s, out_sol ? out_sol + s * PF : 0,
+                                           out_unc ? out_unc + s * PF : 0);
+    }
+}
+
+extern "C" int hostemu_fit_batch(const lucifit_config* cfg, int64_t n, const float* cube, const int64_t* index,
+                                 const float* theta, const float* vel0, const float* broad0, const float* bkg,
+                                 float* out_rows, float* out_sol, float* out_unc, int32_t* status)
+{
+    LfPlan pl;
+    std::string err = lf_make_plan(cfg, pl);
+    if (!err.empty()) { fprintf(stderr, "hostemu: %s\n", err.c_str()); return -1; }
+    // the uncertainty scratch is always reserved in the harness
+    pl.dev.axis = pl.axis.data();
+    pl.dev.xo = pl.xo.data();
+    pl.dev.trans = pl.trans.empty() ? 0 : pl.trans.data();
+    pl.dev.bkg = bkg;
+#define X(L_, G_)                                                                                            \
+    if (pl.L == L_ && pl.nv_t == G_) {                                                                       \
+        if (cfg->model == 0) run_batch<0, L_, G_>(pl, n, cube, index, theta, vel0, broad0, out_rows, out_sol, out_unc, status); \
+        else if (cfg->model == 1) run_batch<1, L_, G_>(pl, n, cube, index, theta, vel0, broad0, out_rows, out_sol, out_unc, status); \
+        else run_batch<2, L_, G_>(pl, n, cube, index, theta, vel0, broad0, out_rows, out_sol, out_unc, status); \
+        return 0;                                                                                            \
+    }
+    LF_INSTANCES(X)
+#undef X
+    fprintf(stderr, "hostemu: tie pattern not instantiated (L=%d groups=%d)\n", pl.L, pl.nv_t);
+    return -1;
+}
+
+// unit-profile value and partials (for math unit tests)
+extern "C" void hostemu_profile(int model, float pp, float sig, float sinc_w, int n, const float* x, float* g,
+                                float* gp, float* gs)
+{
+    LfLine ln;
+    lf_line_setup(model, pp, 0.0f, sig, sinc_w, ln);
+    float piw = LF_PI_F / sinc_w, iw = 1.0f / sinc_w;
+    for (int i = 0; i < n; ++i) {
+        float dx = lf_dx(ln, x[i]);
+        if (model == 0) lf_profile<0>(ln, dx, piw, iw, false, g[i], gp[i], gs[i]);
+        else if (model == 1) lf_profile<1>(ln, dx, piw, iw, false, g[i], gp[i], gs[i]);
+        else lf_profile<2>(ln, dx, piw, iw, lf_is_far(ln, dx), g[i], gp[i], gs[i]);
+    }
+}
+
+extern "C" void hostemu_faddeeva(int n, const float* x, const float* y, float* wr, float* wi)
+{
+    for (int i = 0; i < n; ++i) lf_faddeeva(x[i], y[i], wr[i], wi[i]);
+}

@@ -115,9 +115,11 @@ int lucifit_bin_cube(const float* cube, int nx, int ny, int nz, int b, int x0, i
 
 /* Synthetic LuciSim-style cube written straight into HBM (benchmark input; LUCI/LuciSim.py:159-203):
  * spectrum[s][z] = flux_scale * (continuum + sum_k amp[s][k] * profile(axis[z]; centre snapped to the axis,
- * sigma from broad[s]) + noise_sigma[s] * noise[s][z]) where noise is caller-provided N(0,1) draws (or NULL). */
+ * sigma from broad[s][k]) + noise_sigma[s] * noise[s][z]) where noise is caller-provided N(0,1) draws (or NULL;
+ * it may alias cube: every element is read and then written by the same thread).  vel/broad follow LuciSim's
+ * conventions: centre = (vel/3e5 + 1) 1e7/lambda, sigma = broad * centre / (3e5 corr). */
 int lucifit_sim_cube(const lucifit_config* cfg, int64_t n_spaxel, const float* amp /*[n][L]*/,
-                     const float* vel /*[n]*/, const float* broad /*[n]*/, const float* theta_deg /*[n]*/,
+                     const float* vel /*[n][L]*/, const float* broad /*[n][L]*/, const float* theta_deg /*[n]*/,
                      const float* noise_sigma /*[n]*/, const float* noise /*[n][nz] or NULL*/, float continuum,
                      float flux_scale, float* cube /*[n][nz]*/, void* workspace, size_t workspace_bytes,
                      void* stream);

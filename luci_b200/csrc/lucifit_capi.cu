@@ -1,0 +1,191 @@
+// lucifit_capi.cu -- the extern "C" entry points of include/lucifit.h.
+#include <cuda_runtime.h>
+#include <string>
+
+#include "lucifit_host.hpp"
+#include "lucifit_fit_kernel.cuh"
+
+static thread_local std::string g_err;
+static int fail(int code, const std::string& msg) { g_err = msg; return code; }
+static int cuda_fail(cudaError_t e, const char* what)
+{
+    return fail(LUCIFIT_ECUDA, std::string(what) + ": " + cudaGetErrorString(e));
+}
+
+#define LF_DECL(m, l) extern "C" lf_launch_fn lf_launcher_m##m##_l##l(int bucket);
+#define LF_DECL_ALL(m) LF_DECL(m, 1) LF_DECL(m, 2) LF_DECL(m, 3) LF_DECL(m, 4) LF_DECL(m, 5) LF_DECL(m, 6) LF_DECL(m, 7) LF_DECL(m, 8)
+LF_DECL_ALL(0) LF_DECL_ALL(1) LF_DECL_ALL(2)
+
+static lf_launch_fn find_launcher(int model, int L, int bucket)
+{
+#define LF_CASE(m, l) if (model == m && L == l) return lf_launcher_m##m##_l##l(bucket);
+#define LF_CASE_ALL(m) LF_CASE(m, 1) LF_CASE(m, 2) LF_CASE(m, 3) LF_CASE(m, 4) LF_CASE(m, 5) LF_CASE(m, 6) LF_CASE(m, 7) LF_CASE(m, 8)
+    LF_CASE_ALL(0) LF_CASE_ALL(1) LF_CASE_ALL(2)
+    return nullptr;
+}
+
+struct LfSimArgs {
+    int model, L, nz;
+    double line_nm[LF_MAX_LINES];
+    double axis_k;
+    const double* axis;
+    long long n;
+    const float* amp; const float* vel; const float* broad; const float* theta; const float* noise_sigma;
+    const float* noise;
+    float continuum, flux_scale;
+    float* cube;
+};
+extern "C" cudaError_t lf_run_reduce(int mode, const float* cube, long long n_spaxel, int nz, long long n_live,
+                                     int flo, int fhi, int nlo, int nhi, float* snr, float* deep, int sm_count,
+                                     cudaStream_t stream);
+extern "C" cudaError_t lf_run_bin(const float* cube, int ny, int nz, int b, int x0, int y0, int nxb, int nyb,
+                                  float* out, int sm_count, cudaStream_t stream);
+extern "C" cudaError_t lf_run_sim(const LfSimArgs* a, int sm_count, cudaStream_t stream);
+
+static int sm_count_of_current_device(int* out)
+{
+    int dev = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e != cudaSuccess) return cuda_fail(e, "cudaGetDevice");
+    static thread_local int cached_dev = -1, cached_sm = 0;
+    if (cached_dev != dev) {
+        e = cudaDeviceGetAttribute(&cached_sm, cudaDevAttrMultiProcessorCount, dev);
+        if (e != cudaSuccess) return cuda_fail(e, "cudaDeviceGetAttribute");
+        cached_dev = dev;
+    }
+    *out = cached_sm;
+    return 0;
+}
+
+extern "C" {
+
+const char* lucifit_last_error(void) { return g_err.c_str(); }
+const char* lucifit_version(void) { return "lucifit 0.1.0 (sm_100a)"; }
+
+int lucifit_row_floats(int n_lines) { return 7 * n_lines + 5; }
+
+int lucifit_workspace_bytes(const lucifit_config* cfg, int64_t n_spaxel, size_t* bytes)
+{
+    (void)n_spaxel;
+    if (!bytes) return fail(LUCIFIT_EINVAL, "bytes is NULL");
+    LfPlan pl;
+    std::string err = lf_make_plan(cfg, pl);
+    if (!err.empty()) return fail(LUCIFIT_EINVAL, err);
+    *bytes = pl.table_bytes;
+    return 0;
+}
+
+int lucifit_fit_batch(const lucifit_config* cfg, int64_t n_spaxel, const float* cube,
+                      const int64_t* spaxel_index, const float* theta_deg, const float* vel0, const float* broad0,
+                      const float* bkg, float* out_rows, float* out_fit_sol, float* out_unc, int32_t* out_status,
+                      void* workspace, size_t workspace_bytes, void* stream)
+{
+    LfPlan pl;
+    std::string err = lf_make_plan(cfg, pl);
+    if (!err.empty()) return fail(LUCIFIT_EINVAL, err);
+    if (n_spaxel < 0) return fail(LUCIFIT_EINVAL, "n_spaxel < 0");
+    if (n_spaxel == 0) return 0;
+    if (!cube || !theta_deg || !out_rows || !out_status) return fail(LUCIFIT_EINVAL, "cube, theta_deg, out_rows and out_status are required");
+    if (!workspace || workspace_bytes < pl.table_bytes) return fail(LUCIFIT_EWORKSPACE, "workspace too small: call lucifit_workspace_bytes");
+    if (((uintptr_t)workspace & 255) != 0) return fail(LUCIFIT_EINVAL, "workspace must be 256-byte aligned");
+    lf_launch_fn fn = find_launcher(cfg->model, pl.L, pl.nv_t);
+    if (!fn) return fail(LUCIFIT_EINVAL, "this (n_lines, tie pattern) combination is not instantiated in this build");
+    cudaStream_t st = (cudaStream_t)stream;
+    unsigned char* ws = (unsigned char*)workspace;
+    cudaError_t e;
+    e = cudaMemcpyAsync(ws + pl.off_axis, pl.axis.data(), sizeof(double) * pl.axis.size(), cudaMemcpyHostToDevice, st);
+    if (e != cudaSuccess) return cuda_fail(e, "copy axis");
+    e = cudaMemcpyAsync(ws + pl.off_xo, pl.xo.data(), sizeof(float) * pl.xo.size(), cudaMemcpyHostToDevice, st);
+    if (e != cudaSuccess) return cuda_fail(e, "copy xo");
+    if (!pl.trans.empty()) {
+        e = cudaMemcpyAsync(ws + pl.off_trans, pl.trans.data(), sizeof(float) * pl.trans.size(), cudaMemcpyHostToDevice, st);
+        if (e != cudaSuccess) return cuda_fail(e, "copy transmission");
+    }
+    // the staging vectors live in `pl` (pageable host memory): cudaMemcpyAsync from pageable memory returns once
+    // the source has been staged, so `pl` may be destroyed when this function returns.
+    LfLaunch a;
+    a.cfg = pl.dev;
+    a.cfg.axis = (const double*)(ws + pl.off_axis);
+    a.cfg.xo = (const float*)(ws + pl.off_xo);
+    a.cfg.trans = pl.trans.empty() ? nullptr : (const float*)(ws + pl.off_trans);
+    a.cfg.bkg = bkg;
+    a.n = n_spaxel; a.cube = cube; a.index = (const long long*)spaxel_index; a.theta = theta_deg;
+    a.vel0 = vel0; a.broad0 = broad0; a.out_rows = out_rows; a.out_sol = out_fit_sol; a.out_unc = out_unc;
+    a.status = out_status;
+    a.off_u = (int)pl.off_u; a.off_v = (int)pl.off_v; a.per_warp = (int)pl.per_warp_bytes; a.cont_cap = (int)pl.cont_cap;
+    a.xo_bytes = (int)lf_align(sizeof(float) * pl.nfit, 16);
+    a.stream = st;
+    int rc = sm_count_of_current_device(&a.sm_count);
+    if (rc) return rc;
+    size_t smem = (size_t)a.xo_bytes + (size_t)LF_WARPS_PER_BLOCK * a.per_warp;
+    if (smem > 227 * 1024) return fail(LUCIFIT_EINVAL, "spectrum too long for the shared-memory layout (nz * 8 warps > 227 KB)");
+    e = fn(a);
+    if (e != cudaSuccess) return cuda_fail(e, "launch lf_fit_kernel");
+    return 0;
+}
+
+int lucifit_deep_image(const float* cube, int64_t n_spaxel, int nz, int64_t n_zero_tail, float* deep, void* stream)
+{
+    if (!cube || !deep || n_spaxel < 0 || nz < 1 || n_zero_tail < 0) return fail(LUCIFIT_EINVAL, "bad argument");
+    if (n_spaxel == 0) return 0;
+    int sm = 0; int rc = sm_count_of_current_device(&sm); if (rc) return rc;
+    cudaError_t e = lf_run_reduce(0, cube, n_spaxel, nz, n_spaxel - n_zero_tail, 0, 0, 0, 0, nullptr, deep, sm, (cudaStream_t)stream);
+    if (e != cudaSuccess) return cuda_fail(e, "launch lf_reduce_kernel");
+    return 0;
+}
+
+int lucifit_snr_map(const float* cube, int64_t n_spaxel, int nz, int method, int flux_lo, int flux_hi,
+                    int noise_lo, int noise_hi, float* snr, float* deep, void* stream)
+{
+    if (!cube || !snr || n_spaxel < 0 || nz < 1) return fail(LUCIFIT_EINVAL, "bad argument");
+    if (method != 1 && method != 2) return fail(LUCIFIT_EINVAL, "method must be 1 or 2");
+    if (flux_lo < 0 || flux_hi > nz || noise_lo < 0 || noise_hi > nz) return fail(LUCIFIT_EINVAL, "window outside [0, nz]");
+    if (n_spaxel == 0) return 0;
+    int sm = 0; int rc = sm_count_of_current_device(&sm); if (rc) return rc;
+    cudaError_t e = lf_run_reduce(method, cube, n_spaxel, nz, n_spaxel, flux_lo, flux_hi, noise_lo, noise_hi, snr, deep, sm, (cudaStream_t)stream);
+    if (e != cudaSuccess) return cuda_fail(e, "launch snr kernel");
+    return 0;
+}
+
+int lucifit_bin_cube(const float* cube, int nx, int ny, int nz, int b, int x0, int x1, int y0, int y1,
+                     float* binned, void* stream)
+{
+    if (!cube || !binned || b < 1 || nx < 1 || ny < 1 || nz < 1) return fail(LUCIFIT_EINVAL, "bad argument");
+    if (x0 < 0 || x1 > nx || y0 < 0 || y1 > ny || x1 < x0 || y1 < y0) return fail(LUCIFIT_EINVAL, "region outside the cube");
+    int nxb = (x1 - x0) / b, nyb = (y1 - y0) / b;
+    if (nxb == 0 || nyb == 0) return 0;
+    int sm = 0; int rc = sm_count_of_current_device(&sm); if (rc) return rc;
+    cudaError_t e = lf_run_bin(cube, ny, nz, b, x0, y0, nxb, nyb, binned, sm, (cudaStream_t)stream);
+    if (e != cudaSuccess) return cuda_fail(e, "launch lf_bin_kernel");
+    return 0;
+}
+
+int lucifit_sim_cube(const lucifit_config* cfg, int64_t n_spaxel, const float* amp, const float* vel,
+                     const float* broad, const float* theta_deg, const float* noise_sigma, const float* noise,
+                     float continuum, float flux_scale, float* cube, void* workspace, size_t workspace_bytes,
+                     void* stream)
+{
+    if (!cfg || !cfg->axis || cfg->nz < 8) return fail(LUCIFIT_EINVAL, "config/axis missing");
+    if (cfg->n_lines < 1 || cfg->n_lines > LF_MAX_LINES) return fail(LUCIFIT_EINVAL, "n_lines must be in [1, 8]");
+    if (cfg->model < 0 || cfg->model > 2) return fail(LUCIFIT_EINVAL, "bad model");
+    if (!amp || !vel || !broad || !theta_deg || !cube) return fail(LUCIFIT_EINVAL, "amp, vel, broad, theta_deg and cube are required");
+    size_t need = lf_align(sizeof(double) * cfg->nz, 256);
+    if (!workspace || workspace_bytes < need) return fail(LUCIFIT_EWORKSPACE, "workspace too small (need 8*nz bytes, 256-aligned)");
+    if (n_spaxel <= 0) return 0;
+    cudaStream_t st = (cudaStream_t)stream;
+    cudaError_t e = cudaMemcpyAsync(workspace, cfg->axis, sizeof(double) * cfg->nz, cudaMemcpyHostToDevice, st);
+    if (e != cudaSuccess) return cuda_fail(e, "copy axis");
+    LfSimArgs a;
+    a.model = cfg->model; a.L = cfg->n_lines; a.nz = cfg->nz;
+    for (int k = 0; k < LF_MAX_LINES; ++k) a.line_nm[k] = k < cfg->n_lines ? cfg->line_nm[k] : 1.0;
+    a.axis_k = 1e7 / (2.0 * cfg->step_nm * (cfg->n_steps - cfg->zpd_index));
+    a.axis = (const double*)workspace;
+    a.n = n_spaxel; a.amp = amp; a.vel = vel; a.broad = broad; a.theta = theta_deg; a.noise_sigma = noise_sigma;
+    a.noise = noise; a.continuum = continuum; a.flux_scale = flux_scale; a.cube = cube;
+    int sm = 0; int rc = sm_count_of_current_device(&sm); if (rc) return rc;
+    e = lf_run_sim(&a, sm, st);
+    if (e != cudaSuccess) return cuda_fail(e, "launch lf_sim_kernel");
+    return 0;
+}
+
+}  // extern "C"

@@ -279,7 +279,7 @@ LF_CORE void lf_eval(const LfCfg& cfg, const LfWarp<LANES>& w, const float* xo, 
     constexpr int P = D::P;
     LfLine ln[L];
     float aeff[L], dpdv[L], dsdv[L], dsdb[L], pk[L], bk[L];
-    const bool tie = cfg.i48 >= 0;
+    bool tie = cfg.i48 >= 0;
     float R = 0.0f, cRv[NV], cRb[NS];
 #pragma unroll
     for (int g = 0; g < NV; ++g) cRv[g] = 0.0f;
@@ -303,6 +303,12 @@ LF_CORE void lf_eval(const LfCfg& cfg, const LfWarp<LANES>& w, const float* xo, 
         dsdv[k] = beta * (1.0f / LF_C_KMS) * dpdv[k];
         dsdb[k] = p * (1.0f / LF_C_KMS);
         aeff[k] = th[k];
+    }
+    if (tie && MODEL == LF_SINC) {
+        // sinc: the constraint A_83 sigma_83/3 = A_48 sigma_48 (LuciFit.py:587-589) is vacuous when sigma = 0
+        // (no prior broadening, the reference's ML_bool=False path) -> both amplitudes are free
+#pragma unroll
+        for (int k = 0; k < L; ++k) if ((k == cfg.i83 || k == cfg.i48) && bk[k] == 0.0f) tie = false;
     }
     if (tie) {
         // A_6548 = R A_6583, R = G(sigma_6583)/(3 G(sigma_6548)); ln G = ln p + ln beta - ln c [- ln erf(u)]
@@ -605,7 +611,12 @@ LF_CORE void lf_expand(const LfCfg& cfg, float sinc_w, const float (&th)[LfDims<
         sg[k] = p[k] * (double)b / 299792.0;
         A[k] = (double)th[k];
     }
-    if (cfg.i48 >= 0) {
+    bool tie = cfg.i48 >= 0;
+    if (tie && MODEL == LF_SINC) {
+#pragma unroll
+        for (int k = 0; k < L; ++k) if ((k == cfg.i83 || k == cfg.i48) && beta[k] == 0.0) tie = false;
+    }
+    if (tie) {
         float p83 = 1.f, p48 = 1.f, b83 = 1.f, b48 = 1.f, s83 = 1.f, s48 = 1.f;
         double a83 = 0;
         LfLine t;

@@ -1,0 +1,316 @@
+// lucifit_reduce.cu -- HBM-bound kernels of the path: spectral-axis reductions (deep image, SNR map), spatial
+// binning and the synthetic-cube generator.
+//
+//   deep image   LuciBase.py:171-178        nansum over z of every spaxel
+//   SNR map      LuciBase.py:1142-1172      per-spaxel max / mean / mean|.| / windowed sum / windowed std
+//                                           (+ iterative 1-sigma clip minimum for method 2)
+//   bin cube     LUCI/LuciUtility.py:332-341  b x b nansum of spectra
+//   sim cube     LUCI/LuciSim.py:159-203    LuciSim.Spectrum.create_spectrum for every spaxel
+//
+// Layout: cube[spaxel][z], z contiguous (cube_final[x, y, z], LuciBase.py:122).  One warp streams one spaxel at a
+// time with 16-byte loads where the row alignment allows it; a block stages nothing in shared memory for the
+// plain reductions (each byte is used once), the sigma-clip of method 2 keeps the spectrum in shared memory.
+#include <cuda_runtime.h>
+#include <math.h>
+#include <stdint.h>
+#include "lucifit_core.cuh"
+
+#define RED_WARPS 8
+
+struct SnrAcc {
+    float sum, asum, mx, fsum, n1, n2;   // nansum, nansum|.|, nanmax, flux-window nansum, noise-window sum / sumsq
+    int cnt, ncnt;
+};
+
+__device__ __forceinline__ void snr_take(SnrAcc& a, float v, int z, int flo, int fhi, int nlo, int nhi, float shift)
+{
+    if (v == v) {
+        a.sum += v; a.asum += fabsf(v); a.mx = fmaxf(a.mx, v); a.cnt += 1;
+        if (z >= flo && z < fhi) a.fsum += v;
+        if (z >= nlo && z < nhi) { float d = v - shift; a.n1 += d; a.n2 += d * d; a.ncnt += 1; }
+    }
+}
+
+// MODE 0: deep only; MODE 1: SNR method 1 (+deep)
+template <int MODE>
+__global__ void __launch_bounds__(RED_WARPS * 32)
+lf_reduce_kernel(const float* __restrict__ cube, long long n_spaxel, int nz, long long n_live, int flo, int fhi,
+                 int nlo, int nhi, float* __restrict__ snr, float* __restrict__ deep)
+{
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const long long stride = (long long)gridDim.x * RED_WARPS;
+    for (long long s = (long long)blockIdx.x * RED_WARPS + warp; s < n_spaxel; s += stride) {
+        const float* row = cube + s * (long long)nz;
+        SnrAcc a;
+        a.sum = a.asum = a.fsum = a.n1 = a.n2 = 0.0f; a.mx = -INFINITY; a.cnt = a.ncnt = 0;
+        float shift = 0.0f;
+        if (MODE == 1) shift = row[nlo < nz ? nlo : 0];      // shifted two-moment variance (stable in FP32)
+        if (shift != shift) shift = 0.0f;
+        // peel to 16-byte alignment, then float4 body
+        int head = (int)(((16 - ((uintptr_t)row & 15)) & 15) >> 2);
+        if (head > nz) head = nz;
+        if (lane < head) {
+            float v = row[lane];
+            if (MODE == 0) { if (v == v) a.sum += v; } else snr_take(a, v, lane, flo, fhi, nlo, nhi, shift);
+        }
+        const int nvec = (nz - head) >> 2;
+        const float4* r4 = reinterpret_cast<const float4*>(row + head);
+        for (int i = lane; i < nvec; i += 32) {
+            float4 q = __ldcs(r4 + i);                        // streaming: every byte is read exactly once
+            int z = head + 4 * i;
+            if (MODE == 0) {
+                a.sum += (q.x == q.x ? q.x : 0.f) + (q.y == q.y ? q.y : 0.f) + (q.z == q.z ? q.z : 0.f) + (q.w == q.w ? q.w : 0.f);
+            } else {
+                snr_take(a, q.x, z, flo, fhi, nlo, nhi, shift); snr_take(a, q.y, z + 1, flo, fhi, nlo, nhi, shift);
+                snr_take(a, q.z, z + 2, flo, fhi, nlo, nhi, shift); snr_take(a, q.w, z + 3, flo, fhi, nlo, nhi, shift);
+            }
+        }
+        for (int z = head + 4 * nvec + lane; z < nz; z += 32) {
+            float v = row[z];
+            if (MODE == 0) { if (v == v) a.sum += v; } else snr_take(a, v, z, flo, fhi, nlo, nhi, shift);
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            a.sum += __shfl_xor_sync(0xffffffffu, a.sum, o);
+            if (MODE == 1) {
+                a.asum += __shfl_xor_sync(0xffffffffu, a.asum, o);
+                a.mx = fmaxf(a.mx, __shfl_xor_sync(0xffffffffu, a.mx, o));
+                a.n1 += __shfl_xor_sync(0xffffffffu, a.n1, o);
+                a.n2 += __shfl_xor_sync(0xffffffffu, a.n2, o);
+                a.cnt += __shfl_xor_sync(0xffffffffu, a.cnt, o);
+                a.ncnt += __shfl_xor_sync(0xffffffffu, a.ncnt, o);
+            }
+        }
+        if (lane == 0) {
+            if (deep) deep[s] = s < n_live ? a.sum : 0.0f;
+            if (MODE == 1) {
+                float mean = a.sum / (float)a.cnt;
+                float var = a.ncnt > 0 ? fmaxf(a.n2 / a.ncnt - (a.n1 / a.ncnt) * (a.n1 / a.ncnt), 0.0f) : NAN;
+                float std_out = sqrtf(var);
+                float v = (a.mx - mean) / sqrtf(fabsf(std_out));          // LuciBase.py:1159-1161
+                if (v < 0.0f) v = 0.0f;                                   // :1162-1163
+                else v = v / sqrtf(a.asum / (float)a.cnt);                // :1165
+                snr[s] = v;
+            }
+        }
+    }
+}
+
+// SNR method 2: flux-window sum minus n * min(sigma_clip(sky, sigma=1, maxiters=10)), over std of the noise
+// window (LuciBase.py:1144-1157, 1167-1169).  sigma_clip: centre = median, spread = population std.
+// The spectrum lives in shared memory; the median comes from a bisection on the value range (counting pass per
+// step) refined to the exact order statistics.
+__device__ float warp_select_kth(const float* v, const unsigned char* alive, int n, int k, int lane)
+{
+    // k-th smallest (0-based) among alive entries: radix-free bisection on float keys
+    // map floats to order-preserving uints
+    unsigned lo = 0u, hi = 0xffffffffu;
+    auto key = [](float f) { unsigned u = __float_as_uint(f); return (u & 0x80000000u) ? ~u : (u | 0x80000000u); };
+    while (lo < hi) {
+        unsigned mid = lo + ((hi - lo) >> 1);
+        int c = 0;
+        for (int i = lane; i < n; i += 32) if (alive[i] && key(v[i]) <= mid) ++c;
+        c = __reduce_add_sync(0xffffffffu, c);
+        if (c >= k + 1) hi = mid; else lo = mid + 1;
+    }
+    unsigned u = (lo & 0x80000000u) ? (lo & 0x7fffffffu) : ~lo;
+    return __uint_as_float(u);
+}
+
+__global__ void __launch_bounds__(RED_WARPS * 32)
+lf_snr2_kernel(const float* __restrict__ cube, long long n_spaxel, int nz, long long n_live, int flo, int fhi,
+               int nlo, int nhi, float* __restrict__ snr, float* __restrict__ deep)
+{
+    extern __shared__ __align__(16) unsigned char smem2[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int nzp = (nz + 15) & ~15;
+    float* v = reinterpret_cast<float*>(smem2) + (size_t)warp * nzp;
+    unsigned char* alive = smem2 + (size_t)RED_WARPS * nzp * sizeof(float) + (size_t)warp * nzp;
+    const long long stride = (long long)gridDim.x * RED_WARPS;
+    for (long long s = (long long)blockIdx.x * RED_WARPS + warp; s < n_spaxel; s += stride) {
+        const float* row = cube + s * (long long)nz;
+        float sum = 0.f, fsum = 0.f; double n1 = 0.0, n2 = 0.0; int ncnt = 0, m = 0;
+        float allmin = INFINITY;
+        for (int z = lane; z < nz; z += 32) {
+            float x = __ldcs(row + z);
+            v[z] = x;
+            bool fin = (x == x) && fabsf(x) != INFINITY;
+            alive[z] = fin ? 1 : 0;
+            m += fin;
+            if (x == x) { sum += x; allmin = fminf(allmin, x); if (z >= flo && z < fhi) fsum += x;
+                          if (z >= nlo && z < nhi) { n1 += x; n2 += (double)x * x; ++ncnt; } }
+        }
+        __syncwarp();
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            sum += __shfl_xor_sync(0xffffffffu, sum, o); fsum += __shfl_xor_sync(0xffffffffu, fsum, o);
+            n1 += __shfl_xor_sync(0xffffffffu, n1, o); n2 += __shfl_xor_sync(0xffffffffu, n2, o);
+            ncnt += __shfl_xor_sync(0xffffffffu, ncnt, o); m += __shfl_xor_sync(0xffffffffu, m, o);
+            allmin = fminf(allmin, __shfl_xor_sync(0xffffffffu, allmin, o));
+        }
+        // sigma_clip(sky, sigma=1, maxiters=10): median / population std of the survivors
+        for (int it = 0; it < 10 && m > 0; ++it) {
+            double med;
+            if (m & 1) med = warp_select_kth(v, alive, nz, m / 2, lane);
+            else med = 0.5 * ((double)warp_select_kth(v, alive, nz, m / 2 - 1, lane) + (double)warp_select_kth(v, alive, nz, m / 2, lane));
+            double s1 = 0.0, s2 = 0.0;
+            for (int z = lane; z < nz; z += 32) if (alive[z]) { double d = (double)v[z] - med; s1 += d; s2 += d * d; }
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) { s1 += __shfl_xor_sync(0xffffffffu, s1, o); s2 += __shfl_xor_sync(0xffffffffu, s2, o); }
+            double mu = s1 / m;
+            double sd = sqrt(fmax(s2 / m - mu * mu, 0.0));
+            double lo_b = med - sd, hi_b = med + sd;
+            int removed = 0;
+            for (int z = lane; z < nz; z += 32)
+                if (alive[z] && !((double)v[z] >= lo_b && (double)v[z] <= hi_b)) { alive[z] = 0; ++removed; }
+            removed = __reduce_add_sync(0xffffffffu, removed);
+            __syncwarp();
+            m -= removed;
+            if (removed == 0) break;
+        }
+        float cmin = INFINITY;
+        for (int z = lane; z < nz; z += 32) if (alive[z]) cmin = fminf(cmin, v[z]);
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) cmin = fminf(cmin, __shfl_xor_sync(0xffffffffu, cmin, o));
+        if (m <= 0) cmin = allmin;                                        // LuciBase.py:1151-1152
+        __syncwarp();
+        if (lane == 0) {
+            if (deep) deep[s] = s < n_live ? sum : 0.0f;
+            double mu = ncnt > 0 ? n1 / ncnt : 0.0;
+            double sd = ncnt > 0 ? sqrt(fmax(n2 / ncnt - mu * mu, 0.0)) : NAN;
+            double val = ((double)fsum - (double)cmin * (double)(fhi - flo)) / sd;   // :1153, 1167
+            snr[s] = val < 0.0 ? 0.0f : (float)val;
+        }
+    }
+}
+
+// b x b nansum binning: one thread per (output spaxel, 4 z samples)
+__global__ void lf_bin_kernel(const float* __restrict__ cube, int ny, int nz, int b, int x0, int y0, int nxb,
+                              int nyb, float* __restrict__ out)
+{
+    long long total = (long long)nxb * nyb * nz;
+    for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (long long)gridDim.x * blockDim.x) {
+        int z = (int)(t % nz);
+        long long sp = t / nz;
+        int j = (int)(sp % nyb), i = (int)(sp / nyb);
+        float acc = 0.0f;
+        for (int di = 0; di < b; ++di)
+            for (int dj = 0; dj < b; ++dj) {
+                float v = cube[((long long)(x0 + i * b + di) * ny + (y0 + j * b + dj)) * nz + z];
+                if (v == v) acc += v;
+            }
+        out[t] = acc;
+    }
+}
+
+// Synthetic cube: one warp per spaxel (LuciSim.Spectrum.create_spectrum, LuciSim.py:169-203).
+struct LfSimArgs {
+    int model, L, nz;
+    double line_nm[LF_MAX_LINES];
+    double axis_k;              // 1e7/(2 STEP (n_steps - zpd))
+    const double* axis;         // [nz]
+    long long n;
+    const float* amp; const float* vel; const float* broad; const float* theta; const float* noise_sigma;
+    const float* noise;
+    float continuum, flux_scale;
+    float* cube;
+};
+
+template <int MODEL>
+__global__ void __launch_bounds__(RED_WARPS * 32) lf_sim_kernel(const __grid_constant__ LfSimArgs a)
+{
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    LfWarp<32> w;
+    const long long stride = (long long)gridDim.x * RED_WARPS;
+    for (long long s = (long long)blockIdx.x * RED_WARPS + warp; s < a.n; s += stride) {
+        double ct = cos((double)a.theta[s] * 0.017453292519943295);
+        double corr = 1.0 / ct;
+        float sinc_w = (float)(corr * a.axis_k);
+        LfLine ln[LF_MAX_LINES];
+        float amp[LF_MAX_LINES];
+        const double x_ref = a.axis[0];
+        for (int k = 0; k < a.L; ++k) {
+            double lam_cm = 1e7 / a.line_nm[k];
+            double pos = ((double)a.vel[s * a.L + k] / 3e5) * lam_cm + lam_cm;                 // LuciSim.py:185
+            int idx = lf_argmin_axis(w, a.axis, a.nz, pos);                           // :186-187 (snap)
+            double psn = a.axis[idx];
+            double sigma = ((double)a.broad[s * a.L + k] * psn) / (3e5 * corr);                // :189
+            float hi, lo;
+            lf_split(psn - x_ref, hi, lo);
+            lf_line_setup(MODEL, hi, lo, (float)sigma, sinc_w, ln[k]);
+            amp[k] = a.amp[s * a.L + k];
+        }
+        const float piw = LF_PI_F / sinc_w, iw = 1.0f / sinc_w;
+        float* row = a.cube + s * (long long)a.nz;
+        const float* nrow = a.noise ? a.noise + s * (long long)a.nz : nullptr;
+        float nsig = a.noise_sigma ? a.noise_sigma[s] : 0.0f;
+        for (int z0 = 0; z0 < a.nz; z0 += 32) {
+            int z = z0 + lane;
+            bool live = z < a.nz;
+            float x = live ? (float)(a.axis[z] - x_ref) : 0.0f;
+            float m = a.continuum;
+            for (int k = 0; k < a.L; ++k) {
+                float dx = lf_dx(ln[k], x);
+                bool far = false;
+                if (MODEL == LF_SINCGAUSS) far = w.all(lf_is_far(ln[k], dx));
+                float g, gp, gs;
+                lf_profile<MODEL>(ln[k], dx, piw, iw, far, g, gp, gs);
+                m += amp[k] * g;
+            }
+            if (live) {
+                float nz_ = nrow ? nrow[z] : 0.0f;
+                row[z] = a.flux_scale * (m + nsig * nz_);
+            }
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------- host launchers
+extern "C" cudaError_t lf_run_reduce(int mode, const float* cube, long long n_spaxel, int nz, long long n_live,
+                                     int flo, int fhi, int nlo, int nhi, float* snr, float* deep, int sm_count,
+                                     cudaStream_t stream)
+{
+    long long want = (n_spaxel + RED_WARPS - 1) / RED_WARPS;
+    if (mode == 2) {
+        const int nzp = (nz + 15) & ~15;
+        size_t smem = (size_t)RED_WARPS * nzp * (sizeof(float) + 1);
+        cudaError_t e = cudaFuncSetAttribute(lf_snr2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+        int occ = 1;
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, lf_snr2_kernel, RED_WARPS * 32, smem);
+        if (occ < 1) return cudaErrorLaunchOutOfResources;
+        long long cap = (long long)sm_count * occ;
+        int grid = (int)(want < cap ? want : cap); if (grid < 1) grid = 1;
+        lf_snr2_kernel<<<grid, RED_WARPS * 32, smem, stream>>>(cube, n_spaxel, nz, n_live, flo, fhi, nlo, nhi, snr, deep);
+        return cudaGetLastError();
+    }
+    long long cap = (long long)sm_count * 8;            // 8 resident 256-thread CTAs per SM
+    int grid = (int)(want < cap ? want : cap); if (grid < 1) grid = 1;
+    if (mode == 0)
+        lf_reduce_kernel<0><<<grid, RED_WARPS * 32, 0, stream>>>(cube, n_spaxel, nz, n_live, 0, 0, 0, 0, nullptr, deep);
+    else
+        lf_reduce_kernel<1><<<grid, RED_WARPS * 32, 0, stream>>>(cube, n_spaxel, nz, n_live, flo, fhi, nlo, nhi, snr, deep);
+    return cudaGetLastError();
+}
+
+extern "C" cudaError_t lf_run_bin(const float* cube, int ny, int nz, int b, int x0, int y0, int nxb, int nyb,
+                                  float* out, int sm_count, cudaStream_t stream)
+{
+    long long total = (long long)nxb * nyb * nz;
+    long long want = (total + 255) / 256;
+    long long cap = (long long)sm_count * 16;
+    int grid = (int)(want < cap ? want : cap); if (grid < 1) grid = 1;
+    lf_bin_kernel<<<grid, 256, 0, stream>>>(cube, ny, nz, b, x0, y0, nxb, nyb, out);
+    return cudaGetLastError();
+}
+
+extern "C" cudaError_t lf_run_sim(const LfSimArgs* a, int sm_count, cudaStream_t stream)
+{
+    long long want = (a->n + RED_WARPS - 1) / RED_WARPS;
+    long long cap = (long long)sm_count * 4;
+    int grid = (int)(want < cap ? want : cap); if (grid < 1) grid = 1;
+    if (a->model == 0) lf_sim_kernel<0><<<grid, RED_WARPS * 32, 0, stream>>>(*a);
+    else if (a->model == 1) lf_sim_kernel<1><<<grid, RED_WARPS * 32, 0, stream>>>(*a);
+    else lf_sim_kernel<2><<<grid, RED_WARPS * 32, 0, stream>>>(*a);
+    return cudaGetLastError();
+}

@@ -1,0 +1,198 @@
+"""Torch-side plumbing around the C ABI: device buffers, streams, workspace, output unpacking.
+
+PyTorch is used for device memory and streams only; every kernel is launched through ``liblucifit.so``.
+"""
+import ctypes as C
+
+import numpy as np
+import torch
+
+from . import _capi
+from ._capi import FitConfig, check
+
+ROW_FIELDS = ('amplitudes', 'fluxes', 'flux_errors', 'velocities', 'vels_errors', 'sigmas', 'sigmas_errors')
+ROW_SCALARS = ('chi2', 'corr', 'axis_step', 'continuum', 'continuum_error')
+
+# counts launches of our kernels (bench.py reports it as `gpu_launches`)
+launch_counter = {'n': 0}
+
+
+def _ptr(t):
+    return C.c_void_p(0) if t is None else C.c_void_p(t.data_ptr())
+
+
+def _stream():
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def require_cuda(t, name, dtype):
+    if not isinstance(t, torch.Tensor) or not t.is_cuda:
+        raise TypeError('%s must be a CUDA tensor (there is no CPU path)' % name)
+    if t.dtype != dtype:
+        raise TypeError('%s must have dtype %s' % (name, dtype))
+    if not t.is_contiguous():
+        raise ValueError('%s must be contiguous' % name)
+    return t
+
+
+class Workspace:
+    """Caller-owned device workspace, grown on demand and reused across calls (one per device)."""
+
+    def __init__(self):
+        self.buf = None
+
+    def get(self, nbytes, device):
+        nbytes = max(int(nbytes), 256)
+        if self.buf is None or self.buf.numel() < nbytes or self.buf.device != device:
+            self.buf = torch.empty(nbytes + 256, dtype=torch.uint8, device=device)
+        off = (-self.buf.data_ptr()) % 256
+        return self.buf[off:off + nbytes]
+
+
+_workspaces = {}
+
+
+def workspace_for(device, nbytes):
+    ws = _workspaces.setdefault(str(device), Workspace())
+    return ws.get(nbytes, device)
+
+
+def fit_batch(cfg: FitConfig, cube, theta, vel0=None, broad0=None, index=None, bkg=None, want_sol=False,
+              want_unc=False):
+    """One ``lucifit_fit_batch`` call.  ``cube`` is ``[n_rows, nz]`` float32 on the GPU; ``index`` (int64, optional)
+    selects the rows to fit; ``theta``/``vel0``/``broad0`` are per *fitted* spaxel.  Returns a dict of device
+    tensors: ``rows [n, 7L+5]``, ``status [n]`` and optionally ``fit_sol`` / ``fit_unc`` ``[n, 3L+1]``."""
+    lib = _capi.lib()
+    require_cuda(cube, 'cube', torch.float32)
+    dev = cube.device
+    if cube.dim() != 2 or cube.shape[1] != cfg.c.nz:
+        raise ValueError('cube must be [n_rows, nz=%d]' % cfg.c.nz)
+    n = int(index.numel()) if index is not None else int(cube.shape[0])
+    require_cuda(theta, 'theta', torch.float32)
+    if theta.numel() != n:
+        raise ValueError('theta must have one entry per fitted spaxel')
+    for name, t in (('vel0', vel0), ('broad0', broad0)):
+        if t is not None:
+            require_cuda(t, name, torch.float32)
+            if t.numel() != n:
+                raise ValueError('%s must have one entry per fitted spaxel' % name)
+    if index is not None:
+        require_cuda(index, 'index', torch.int64)
+    if bkg is not None:
+        require_cuda(bkg, 'bkg', torch.float32)
+        if bkg.numel() != cfg.c.nz:
+            raise ValueError('bkg must have nz entries')
+    K, PF = cfg.row_floats, 3 * cfg.L + 1
+    rows = torch.empty((n, K), dtype=torch.float32, device=dev)
+    status = torch.empty((n,), dtype=torch.int32, device=dev)
+    sol = torch.empty((n, PF), dtype=torch.float32, device=dev) if want_sol else None
+    unc = torch.empty((n, PF), dtype=torch.float32, device=dev) if want_unc else None
+    need = C.c_size_t(0)
+    check(lib.lucifit_workspace_bytes(cfg.byref(), n, C.byref(need)))
+    ws = workspace_for(dev, need.value)
+    with torch.cuda.device(dev):
+        check(lib.lucifit_fit_batch(cfg.byref(), n, _ptr(cube), _ptr(index), _ptr(theta), _ptr(vel0), _ptr(broad0),
+                                    _ptr(bkg), _ptr(rows), _ptr(sol), _ptr(unc), _ptr(status), _ptr(ws),
+                                    C.c_size_t(ws.numel()), _stream()))
+    if n > 0:
+        launch_counter['n'] += 1
+    out = {'rows': rows, 'status': status}
+    if want_sol:
+        out['fit_sol'] = sol
+    if want_unc:
+        out['fit_unc'] = unc
+    return out
+
+
+def unpack_rows(rows, L):
+    """Split ``rows [n, 7L+5]`` into the 12 named quantities of ``Luci.fit_calc`` (LuciBase.py:406)."""
+    out = {}
+    for i, name in enumerate(ROW_FIELDS):
+        out[name] = rows[:, i * L:(i + 1) * L]
+    for i, name in enumerate(ROW_SCALARS):
+        out[name] = rows[:, 7 * L + i]
+    return out
+
+
+def deep_image(cube2d, n_zero_tail=0):
+    """``cube2d [n_spaxel, nz]`` -> ``deep [n_spaxel]`` (nansum over z); the last ``n_zero_tail`` entries are 0."""
+    lib = _capi.lib()
+    require_cuda(cube2d, 'cube', torch.float32)
+    n, nz = cube2d.shape
+    deep = torch.empty((n,), dtype=torch.float32, device=cube2d.device)
+    with torch.cuda.device(cube2d.device):
+        check(lib.lucifit_deep_image(_ptr(cube2d), n, nz, int(n_zero_tail), _ptr(deep), _stream()))
+    launch_counter['n'] += 1 if n > 0 else 0
+    return deep
+
+
+def snr_map(cube2d, method, flux_lo, flux_hi, noise_lo, noise_hi, with_deep=False):
+    lib = _capi.lib()
+    require_cuda(cube2d, 'cube', torch.float32)
+    n, nz = cube2d.shape
+    snr = torch.empty((n,), dtype=torch.float32, device=cube2d.device)
+    deep = torch.empty((n,), dtype=torch.float32, device=cube2d.device) if with_deep else None
+    with torch.cuda.device(cube2d.device):
+        check(lib.lucifit_snr_map(_ptr(cube2d), n, nz, int(method), int(flux_lo), int(flux_hi), int(noise_lo),
+                                  int(noise_hi), _ptr(snr), _ptr(deep), _stream()))
+    launch_counter['n'] += 1 if n > 0 else 0
+    return (snr, deep) if with_deep else snr
+
+
+def bin_cube(cube3d, binning, x_min, x_max, y_min, y_max):
+    """``cube3d [nx, ny, nz]`` -> ``[int((x_max-x_min)/b), int((y_max-y_min)/b), nz]`` b x b nansum."""
+    lib = _capi.lib()
+    require_cuda(cube3d, 'cube', torch.float32)
+    nx, ny, nz = cube3d.shape
+    b = int(binning)
+    nxb, nyb = int((x_max - x_min) / b), int((y_max - y_min) / b)
+    out = torch.empty((nxb, nyb, nz), dtype=torch.float32, device=cube3d.device)
+    with torch.cuda.device(cube3d.device):
+        check(lib.lucifit_bin_cube(_ptr(cube3d), nx, ny, nz, b, int(x_min), int(x_max), int(y_min), int(y_max),
+                                   _ptr(out), _stream()))
+    launch_counter['n'] += 1 if out.numel() > 0 else 0
+    return out
+
+
+def sim_cube(cfg: FitConfig, amp, vel, broad, theta, noise_sigma=None, noise=None, continuum=0.0, flux_scale=1.0,
+             out=None):
+    """LuciSim-style synthetic spectra written on the device (LuciSim.py:159-203).  ``amp [n, L]``, ``vel``,
+    ``broad``, ``theta``, ``noise_sigma`` ``[n]``; ``noise [n, nz]`` unit-variance draws (may alias ``out``)."""
+    lib = _capi.lib()
+    require_cuda(amp, 'amp', torch.float32)
+    n = amp.shape[0]
+    dev = amp.device
+    nz = cfg.c.nz
+    if out is None:
+        out = torch.empty((n, nz), dtype=torch.float32, device=dev)
+    require_cuda(out, 'out', torch.float32)
+    for name, t in (('vel', vel), ('broad', broad), ('theta', theta)):
+        require_cuda(t, name, torch.float32)
+    ws = workspace_for(dev, 8 * nz + 256)
+    with torch.cuda.device(dev):
+        check(lib.lucifit_sim_cube(cfg.byref(), n, _ptr(amp), _ptr(vel), _ptr(broad), _ptr(theta), _ptr(noise_sigma),
+                                   _ptr(noise), C.c_float(continuum), C.c_float(flux_scale), _ptr(out), _ptr(ws),
+                                   C.c_size_t(ws.numel()), _stream()))
+    launch_counter['n'] += 1 if n > 0 else 0
+    return out
+
+
+def status_summary(status):
+    """Host-side summary of the per-spaxel status words: mean evaluations E, iteration histogram, flag counts."""
+    st = status.detach().cpu().numpy().astype(np.int64)
+    fitted = (st & (_capi_flags()['NAN_INPUT'] | _capi_flags()['BAD_NORM'] | _capi_flags()['MASKED'])) == 0
+    it = st & 0xff
+    ev = (st >> 8) & 0xff
+    flags = _capi_flags()
+    out = {'n': int(st.size), 'n_fitted': int(fitted.sum()),
+           'mean_evals': float(ev[fitted].mean()) if fitted.any() else 0.0,
+           'mean_iters': float(it[fitted].mean()) if fitted.any() else 0.0,
+           'max_evals': int(ev.max()) if st.size else 0}
+    for name, bit in flags.items():
+        out['n_' + name.lower()] = int(((st & bit) != 0).sum())
+    return out
+
+
+def _capi_flags():
+    return {'CONVERGED': 1 << 16, 'MAXITER': 1 << 17, 'BOUND': 1 << 18, 'SINGULAR': 1 << 19, 'NAN_INPUT': 1 << 20,
+            'MASKED': 1 << 21, 'BAD_NORM': 1 << 22}

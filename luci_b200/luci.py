@@ -1,0 +1,420 @@
+"""``Luci`` -- drop-in for the fitting / reduction methods of ``LuciBase.Luci`` (reference ``LuciBase.py:44-1191``).
+
+Same method names, argument meaning and return values as the reference for the hot path
+(``fit_entire_cube``, ``fit_cube``, ``fit_region``, ``fit_spectrum_region``, ``create_deep_image``,
+``create_snr_map``, ``bin_cube``), same FITS/NPY artefacts on disk (``LuciUtility.save_fits`` layout).  The joblib
+fan-out over y-rows (``LuciBase.py:514-530``) is replaced by one ``lucifit_fit_batch`` call on the GPU holding the
+cube.  The cube lives in HBM as float32 ``[x, y, z]`` (z contiguous), exactly the reference's ``cube_final`` axes.
+
+Differences that are deliberate and documented in DESIGN.md:
+  * ``Luci.from_arrays(...)`` builds the object from in-memory arrays (h5py/astropy are optional here).
+  * the CNN prior of the reference (TensorFlow, out of scope) enters as ``prior_values=(vel_map, broad_map)`` in
+    km/s, which is exactly what the CNN writes into ``vel_ml`` / ``broad_ml`` (``LuciFit.py:352-361``);
+  * ``fit_entire_cube`` honours its keyword arguments and returns the ``fit_cube`` tuple (the reference drops them
+    and returns ``None``, ``LuciBase.py:255``);
+  * Bayesian / PCA-background / absorption / freeze branches raise ``NotImplementedError`` (out of scope rows).
+"""
+import os
+import warnings
+
+import numpy as np
+import numpy.ma as ma
+import torch
+
+from . import engine
+from ._capi import FitConfig, argmin_abs
+from .constants import LINE_DICT, snr_windows
+from .fitsio import read_fits, save_fits, write_fits
+
+
+def check_luci_path(Luci_path):
+    if Luci_path is not None and not Luci_path.endswith('/'):
+        Luci_path += '/'
+        print("We have added a trailing '/' to your Luci_path variable.\n")
+        print("Please add this in the future.\n")
+    return Luci_path
+
+
+def spectrum_axis_func(hdr_dict, redshift):
+    """``LUCI/LuciUtility.py:143-165``: float32 axis (redshifted and unshifted) from the header."""
+    len_wl = int(hdr_dict['STEPNB'])
+    start = float(hdr_dict['CRVAL3'])
+    step = float(hdr_dict['CDELT3'])
+    end = start + len_wl * step
+    axis = np.array(np.linspace(start, end, len_wl) * (redshift + 1), dtype=np.float32)
+    axis_unshifted = np.array(np.linspace(start, end, len_wl), dtype=np.float32)
+    return axis, axis_unshifted
+
+
+class Luci():
+    def __init__(self, Luci_path, cube_path, output_dir, object_name, redshift, resolution, ML_bool=True, mdn=False,
+                 device=None):
+        """Reference signature (``LuciBase.py:51``).  Reading the ORBS HDF5 cube needs ``h5py`` (optional here);
+        use :meth:`from_arrays` for in-memory data."""
+        self._init_common(Luci_path, output_dir, object_name, redshift, resolution, ML_bool, mdn, device)
+        self.cube_path = cube_path
+        self.read_in_cube()
+        self._finish_init()
+
+    # ------------------------------------------------------------------------------------------ construction
+    def _init_common(self, Luci_path, output_dir, object_name, redshift, resolution, ML_bool, mdn, device):
+        self.header_binned = None
+        self.Luci_path = check_luci_path(Luci_path)
+        self.cube_path = None
+        self.output_dir = output_dir + '/Luci_outputs'
+        os.makedirs(self.output_dir, exist_ok=True)
+        self.object_name = object_name
+        self.redshift = redshift
+        self.resolution = resolution
+        self.mdn = mdn
+        self.ML_bool = ML_bool
+        self.cube_final = None          # torch float32 [x, y, z] on the device
+        self.cube_binned = None
+        self.header = None              # dict of FITS cards (WCS)
+        self.deep_image = None
+        self.spectrum_axis = None
+        self.spectrum_axis_unshifted = None
+        self.wavenumbers_syn = None
+        self.hdr_dict = None
+        self.interferometer_theta = None
+        self.transmission_interpolated = None
+        self.strict_reference = True    # replicate the reference's quirks that change numbers
+        self.last_fit_summary = None
+        if device is None:
+            device = torch.device('cuda', torch.cuda.current_device()) if torch.cuda.is_available() else None
+        self.device = torch.device(device) if device is not None else None
+
+    def _finish_init(self):
+        self.step_nb = self.hdr_dict['STEPNB']
+        self.zpd_index = self.hdr_dict['ZPDINDEX']
+        self.filter = self.hdr_dict['FILTER']
+        if self.spectrum_axis is None:
+            self.spectrum_axis, self.spectrum_axis_unshifted = spectrum_axis_func(self.hdr_dict, self.redshift)
+            if self.filter in ('C4', 'C2', 'C1'):
+                self.spectrum_axis = self.spectrum_axis_unshifted      # LuciBase.py:96-97
+        self.dimx, self.dimy, self.dimz = (int(v) for v in self.cube_final.shape)
+
+    @classmethod
+    def from_arrays(cls, cube, hdr_dict, output_dir, object_name, redshift=0.0, resolution=5000,
+                    interferometer_theta=None, spectrum_axis=None, transmission=None, header=None, Luci_path=None,
+                    ML_bool=True, mdn=False, device=None):
+        """Build a ``Luci`` from in-memory data.
+
+        cube: ``[x, y, z]`` numpy array or torch tensor (copied to the GPU as float32; a CUDA float32 tensor is
+        used in place).  hdr_dict needs ``FILTER``, ``STEP``, ``STEPNB``, ``ZPDINDEX`` and, unless
+        ``spectrum_axis`` is given, ``CRVAL3``/``CDELT3``.  interferometer_theta: ``[x, y]`` degrees
+        (default 11.96, the LuciSim angle).  transmission: ``[z]`` or ``None``.
+        """
+        self = cls.__new__(cls)
+        self._init_common(Luci_path, output_dir, object_name, redshift, resolution, ML_bool, mdn, device)
+        if self.device is None:
+            raise RuntimeError('luci_b200 needs a CUDA device: there is no CPU path')
+        self.hdr_dict = dict(hdr_dict)
+        self.header = dict(header) if header is not None else {}
+        self.cube_final = self._to_device_cube(cube)
+        nx, ny = self.cube_final.shape[:2]
+        if interferometer_theta is None:
+            interferometer_theta = np.full((nx, ny), 11.96)
+        self.interferometer_theta = np.asarray(interferometer_theta, dtype=np.float64)
+        if spectrum_axis is not None:
+            self.spectrum_axis = np.asarray(spectrum_axis, dtype=np.float32)
+            self.spectrum_axis_unshifted = self.spectrum_axis
+        self.transmission_interpolated = None if transmission is None else np.asarray(transmission, dtype=np.float64)
+        self._finish_init()
+        return self
+
+    def _to_device_cube(self, cube):
+        if isinstance(cube, torch.Tensor):
+            t = cube
+            if t.is_cuda and t.dtype == torch.float32 and t.is_contiguous():
+                return t
+            return t.to(device=self.device, dtype=torch.float32).contiguous()
+        cube = np.asarray(cube)
+        out = torch.empty(cube.shape, dtype=torch.float32, device=self.device)
+        step = max(1, int(2 ** 28 // max(1, cube.shape[1] * cube.shape[2])))      # ~1 GiB float32 chunks along x
+        for i in range(0, cube.shape[0], step):
+            out[i:i + step] = torch.from_numpy(np.ascontiguousarray(cube[i:i + step], dtype=np.float32)).to(self.device)
+        return out
+
+    def read_in_cube(self):
+        """``LuciBase.py:106-145`` -- needs h5py; the clamp rules of :123-129 are applied on the device."""
+        try:
+            import h5py
+        except ImportError as exc:
+            raise ImportError('h5py is not installed: build the object with Luci.from_arrays(...)') from exc
+        raise NotImplementedError('HDF5 ingest is a "next" row (SURVEY 8f-2); use Luci.from_arrays')
+
+    # -------------------------------------------------------------------------------------------- reductions
+    def create_deep_image(self, output_name=None, binning=None):
+        """``LuciBase.py:147-215``: sum over the spectral axis, transposed to (ny, nx), written as FITS."""
+        nx, ny, nz = self.cube_final.shape
+        tail = (nx % 10) * ny if self.strict_reference else 0          # reference leaves nx mod 10 rows zero
+        deep = engine.deep_image(self.cube_final.view(nx * ny, nz), n_zero_tail=tail)
+        self.deep_image = deep.view(nx, ny).t().contiguous().cpu().numpy().astype(np.float64)
+        header_to_use = self.header
+        if binning is not None and binning != 1:
+            b = int(binning)
+            xs, ys = int(self.deep_image.shape[0] / b), int(self.deep_image.shape[1] / b)
+            d = self.deep_image[:xs * b, :ys * b].reshape(xs, b, ys, b)
+            self.deep_image = np.nansum(np.nansum(d, axis=3), axis=1) / (b ** 2)
+            header_to_use = dict(self.header)
+            for key, f in (('CRPIX1', 1.0 / b), ('CRPIX2', 1.0 / b), ('PC1_1', b), ('PC1_2', b), ('PC2_1', b), ('PC2_2', b)):
+                if key in header_to_use:
+                    header_to_use[key] = header_to_use[key] * f
+        if output_name is None:
+            output_name = self.output_dir + '/' + self.object_name + '_deep.fits'
+        write_fits(output_name, self.deep_image, header_to_use)
+
+    def bin_cube(self, cube_final, header, binning, x_min, x_max, y_min, y_max):
+        """``LuciBase.py:840-842`` / ``LuciUtility.py:319-355``: b x b nansum (no division)."""
+        self.cube_binned = engine.bin_cube(cube_final, binning, x_min, x_max, y_min, y_max)
+        hb = dict(header) if header else {}
+        if 'CRPIX1' in hb:
+            hb['CRPIX1'] = (hb['CRPIX1'] - x_min - 0.5) / binning + 0.5
+        if 'CRPIX2' in hb:
+            hb['CRPIX2'] = (hb['CRPIX2'] - y_min - 0.5) / binning + 0.5
+        for key in ('PC1_1', 'PC1_2', 'PC2_1', 'PC2_2'):
+            if key in hb:
+                hb[key] = hb[key] * binning
+        self.header_binned = hb        # the reference mutates self.header in place here; that bug is not replicated
+
+    def create_snr_map(self, x_min=0, x_max=2048, y_min=0, y_max=2064, method=1, n_threads=2, lines=[None],
+                       binning=1, bkgType=None, pca_coefficient_array=None, pca_vectors=None, pca_mean=None):
+        """``LuciBase.py:1048-1191``.  Returns the four masked arrays (SNR >= 1, 3, 5, 10) like the reference."""
+        cube_to_use = self.cube_final
+        if binning > 1:
+            self.bin_cube(self.cube_final, self.header, binning, x_min, x_max, y_min, y_max)
+            x_max = int((x_max - x_min) / binning)
+            y_max = int((y_max - y_min) / binning)
+            x_min = 0
+            y_min = 0
+            cube_to_use = self.cube_binned
+        (fmin, fmax), (nmin, nmax) = snr_windows(self.hdr_dict['FILTER'], lines)
+        ax = np.array(self.spectrum_axis)
+        flo, fhi = argmin_abs(ax, fmin), argmin_abs(ax, fmax)
+        nlo, nhi = argmin_abs(ax, nmin), argmin_abs(ax, nmax)
+        x_max = min(x_max, cube_to_use.shape[0]); y_max = min(y_max, cube_to_use.shape[1])
+        region = cube_to_use[x_min:x_max, y_min:y_max]
+        nxr, nyr, nz = region.shape
+        region2d = region.reshape(nxr * nyr, nz) if region.is_contiguous() else region.contiguous().view(nxr * nyr, nz)
+        snr = engine.snr_map(region2d, method, flo, fhi, nlo, nhi)
+        SNR = snr.view(nxr, nyr).t().contiguous().cpu().numpy()
+        os.makedirs(self.output_dir + '/SNR', exist_ok=True)
+        write_fits(self.output_dir + '/SNR/' + self.object_name + '_SNR.fits', SNR, self.header)
+        masks = []
+        for snr_val in [1, 3, 5, 10]:
+            mask = ma.masked_where(SNR >= snr_val, SNR)
+            masks.append(mask)
+            np.save("%s/SNR/%s_SNR_%i_mask.npy" % (self.output_dir, self.object_name, snr_val), ma.getmaskarray(mask))
+        self.snr_map = SNR
+        return masks
+
+    # --------------------------------------------------------------------------------------------------- fits
+    def _make_config(self, lines, fit_function, vel_rel, sigma_rel, uncertainty_bool, nii_cons, spec_min, spec_max,
+                     obj_redshift, ml_scale):
+        return FitConfig(fit_function, lines, vel_rel, sigma_rel, self.spectrum_axis, filter=self.hdr_dict['FILTER'],
+                         delta_x=self.hdr_dict['STEP'], n_steps=self.step_nb, zpd_index=self.zpd_index,
+                         trans_filter=self.transmission_interpolated, uncertainty_bool=uncertainty_bool,
+                         nii_cons=nii_cons, spec_min=spec_min, spec_max=spec_max, obj_redshift=obj_redshift,
+                         ml_scale=ml_scale)
+
+    @staticmethod
+    def _reject_unsupported(bayes_bool, absorp, initial_values, n_stoch, bkgType):
+        if bayes_bool:
+            raise NotImplementedError('bayes_bool=True (emcee/dynesty MCMC, LuciFit.py:930-1015) is out of scope')
+        if absorp is not None:
+            raise NotImplementedError('absorption templates (LuciBase.py:354-356) are out of scope')
+        if len(initial_values) == 2 or (len(initial_values) >= 1 and initial_values[0] is not False):
+            raise NotImplementedError('initial_values selects the freeze branch (LuciFit.py:688-709): a "next" row')
+        if n_stoch != 1:
+            raise NotImplementedError('n_stoch > 1 (random restarts, LuciFit.py:662-687) is a "next" row')
+        if bkgType == 'pca':
+            raise NotImplementedError("bkgType='pca' (LuciBase.py:331-352) is a \"next\" row")
+
+    def _cutout_header(self, header, x_min, y_min):
+        """What ``Cutout2D(...).wcs.to_header()`` changes for a rectangular cut-out: the reference pixel."""
+        h = dict(header) if header else {}
+        if 'CRPIX1' in h:
+            h['CRPIX1'] = h['CRPIX1'] - x_min
+        if 'CRPIX2' in h:
+            h['CRPIX2'] = h['CRPIX2'] - y_min
+        return h
+
+    def _fit_maps(self, cube3d, lines, fit_function, vel_rel, sigma_rel, x_min, x_max, y_min, y_max, mask, bkg,
+                  bkg_scale, uncertainty_bool, nii_cons, spec_min, spec_max, obj_redshift, prior_values):
+        """Shared body of fit_cube / fit_region: returns the 12 maps as numpy float32 arrays (ny', nx'[, L])."""
+        L = len(lines)
+        nxc, nyc, nz = cube3d.shape
+        nxo, nyo = x_max - x_min, y_max - y_min
+        have_prior = prior_values is not None
+        if not have_prior and self.ML_bool and fit_function != 'sinc':
+            warnings.warn('no prior_values given: starting every fit from velocity = broadening = 0 like the '
+                          "reference's ML_bool=False path, which only works for fit_function='sinc'")
+        cfg = self._make_config(lines, fit_function, vel_rel, sigma_rel, uncertainty_bool, nii_cons, spec_min,
+                                spec_max, obj_redshift, ml_scale=have_prior)
+        dev = cube3d.device
+        # fitted spaxels, ordered like the output maps: (y, x) row-major
+        yy, xx = np.meshgrid(np.arange(y_min, y_max), np.arange(x_min, x_max), indexing='ij')
+        if mask is not None:
+            sel = np.asarray(mask)[xx, yy].astype(bool)
+        else:
+            sel = np.ones_like(xx, dtype=bool)
+        flat = (xx.astype(np.int64) * nyc + yy.astype(np.int64))[sel]
+        theta = np.asarray(self.interferometer_theta)[xx[sel], yy[sel]].astype(np.float32)   # LuciBase.py:369
+        index = torch.from_numpy(flat).to(dev)
+        theta_t = torch.from_numpy(theta).to(dev)
+        v0 = b0 = None
+        if have_prior:
+            v0 = torch.from_numpy(np.ascontiguousarray(np.asarray(prior_values[0], dtype=np.float32)[sel])).to(dev)
+            b0 = torch.from_numpy(np.ascontiguousarray(np.asarray(prior_values[1], dtype=np.float32)[sel])).to(dev)
+        bkg_t = None
+        if bkg is not None:
+            bkg_t = torch.from_numpy(np.asarray(bkg, dtype=np.float32) * np.float32(bkg_scale)).to(dev)
+        res = engine.fit_batch(cfg, cube3d.view(nxc * nyc, nz), theta_t, v0, b0, index=index, bkg=bkg_t)
+        rows = res['rows']
+        K = cfg.row_floats
+        full = torch.zeros((nyo * nxo, K), dtype=torch.float32, device=dev)
+        pos = torch.from_numpy(np.flatnonzero(sel.ravel())).to(dev)
+        full[pos] = rows
+        full = full.view(nyo, nxo, K).cpu().numpy()
+        self.last_fit_summary = engine.status_summary(res['status'])
+        maps = {}
+        for i, name in enumerate(engine.ROW_FIELDS):
+            maps[name] = np.ascontiguousarray(full[:, :, i * L:(i + 1) * L])
+        for i, name in enumerate(engine.ROW_SCALARS):
+            maps[name] = np.ascontiguousarray(full[:, :, 7 * L + i])
+        return maps
+
+    def _ensure_deep(self):
+        if not os.path.exists(self.output_dir + '/' + self.object_name + '_deep.fits'):
+            self.create_deep_image()
+
+    def fit_cube(self, lines, fit_function, vel_rel, sigma_rel, x_min, x_max, y_min, y_max, bkg=None, bkgType=None,
+                 binning=None, bayes_bool=False, bayes_method='emcee', absorp=None, uncertainty_bool=False,
+                 n_threads=2, nii_cons=True, initial_values=[False], spec_min=None, spec_max=None, obj_redshift=0.0,
+                 n_stoch=1, pca_coefficient_array=None, pca_vectors=None, pca_mean=None, prior_values=None):
+        """``LuciBase.py:409-551``.  Returns ``(velocities, broadenings, flux, ampls)``, float32 ``(ny', nx', L)``.
+
+        ``n_threads`` is accepted and ignored (the batch runs on the GPU).  ``prior_values=(vel, broad)`` are
+        ``(ny', nx')`` maps in km/s replacing the reference's CNN prior."""
+        self._reject_unsupported(bayes_bool, absorp, initial_values, n_stoch, bkgType)
+        cube_to_slice = self.cube_final
+        header = self.header
+        if binning is not None and binning != 1:
+            self.bin_cube(self.cube_final, self.header, binning, x_min, x_max, y_min, y_max)
+            x_max = int((x_max - x_min) / binning)
+            y_max = int((y_max - y_min) / binning)
+            x_min = 0
+            y_min = 0
+            cube_to_slice = self.cube_binned
+            header = self.header_binned
+        self._ensure_deep()
+        use_bkg = bkg if bkgType == 'standard' else None                # LuciBase.py:325-330 (ignored otherwise)
+        scale = (binning ** 2) if (binning and use_bkg is not None) else 1.0
+        m = self._fit_maps(cube_to_slice, lines, fit_function, vel_rel, sigma_rel, x_min, x_max, y_min, y_max, None,
+                           use_bkg, scale, uncertainty_bool, nii_cons, spec_min, spec_max, obj_redshift, prior_values)
+        save_fits(self.output_dir, self.object_name, lines, m['amplitudes'], m['fluxes'], m['flux_errors'],
+                  m['velocities'], m['sigmas'], m['vels_errors'], m['sigmas_errors'], m['chi2'], m['continuum'],
+                  m['continuum_error'], self._cutout_header(header, x_min, y_min), binning, fit_function=fit_function)
+        self.last_fit_maps = m
+        return m['velocities'], m['sigmas'], m['fluxes'], m['amplitudes']
+
+    def fit_entire_cube(self, lines, fit_function, vel_rel, sigma_rel, bkg=None, binning=None, bayes_bool=False,
+                        output_name=None, uncertainty_bool=False, n_threads=1, **kwargs):
+        """``LuciBase.py:231-255``; unlike the reference the keyword arguments are honoured and the maps returned."""
+        return self.fit_cube(lines, fit_function, vel_rel, sigma_rel, 0, self.cube_final.shape[0], 0,
+                             self.cube_final.shape[1], bkg=bkg, binning=binning, bayes_bool=bayes_bool,
+                             uncertainty_bool=uncertainty_bool, n_threads=n_threads, **kwargs)
+
+    def _load_mask(self, region, pixel_list):
+        if pixel_list is not False:
+            mask = np.ones((self.cube_final.shape[0], self.cube_final.shape[1]), dtype=bool)   # LuciBase.py:637-639
+            for pair in region:
+                mask[pair] = True
+            return mask
+        if isinstance(region, str):
+            if '.reg' in region:
+                raise NotImplementedError('ds9 .reg regions need pyregion (out of scope): pass a boolean mask or .npy')
+            if '.npy' in region:
+                return np.load(region)
+            raise ValueError('Mask was incorrectly passed. Please use either a .reg file or a .npy file or a numpy ndarray')
+        if region is not None:
+            return np.asarray(region)
+        raise ValueError('Mask was incorrectly passed. Please use either a .reg file or a .npy file or a numpy ndarray')
+
+    def fit_region(self, lines, fit_function, vel_rel, sigma_rel, region, bkg=None, binning=None, bayes_bool=False,
+                   bayes_method='emcee', output_name=None, uncertainty_bool=False, n_threads=1, nii_cons=True,
+                   spec_min=None, spec_max=None, obj_redshift=0.0, initial_values=[False], n_stoch=1,
+                   pixel_list=False, prior_values=None):
+        """``LuciBase.py:553-722``.  Returns ``(velocities, broadenings, flux, chi2, mask)``.  Only the spaxels inside
+        the mask are sent to the GPU (compacted index list); the rest of every map stays 0 like the reference."""
+        self._reject_unsupported(bayes_bool, None, initial_values, n_stoch, None)
+        x_min, x_max = 0, self.cube_final.shape[0]
+        y_min, y_max = 0, self.cube_final.shape[1]
+        cube_to_slice = self.cube_final
+        header = self.header
+        if binning is not None and binning > 1:
+            self.bin_cube(self.cube_final, self.header, binning, x_min, x_max, y_min, y_max)
+            x_max = int((x_max - x_min) / binning)
+            y_max = int((y_max - y_min) / binning)
+            cube_to_slice = self.cube_binned
+            header = self.header_binned
+        mask = self._load_mask(region, pixel_list)
+        if binning is not None and binning > 1:
+            from .host_ops import bin_mask
+            mask = bin_mask(mask, binning, x_min, self.cube_final.shape[0], y_min, self.cube_final.shape[1])
+        self._ensure_deep()
+        # fit_region never forwards bkgType, so the reference ignores bkg here (LuciBase.py:691-705, 325)
+        m = self._fit_maps(cube_to_slice, lines, fit_function, vel_rel, sigma_rel, x_min, x_max, y_min, y_max, mask,
+                           None, 1.0, uncertainty_bool, nii_cons, spec_min, spec_max, obj_redshift, prior_values)
+        save_fits(self.output_dir, self.object_name, lines, m['amplitudes'], m['fluxes'], m['flux_errors'],
+                  m['velocities'], m['sigmas'], m['vels_errors'], m['sigmas_errors'], m['chi2'], m['continuum'],
+                  m['continuum_error'], self._cutout_header(header, x_min, y_min), binning)
+        self.last_fit_maps = m
+        return m['velocities'], m['sigmas'], m['fluxes'], m['chi2'], mask
+
+    def fit_spectrum_region(self, lines, fit_function, vel_rel, sigma_rel, region, initial_values=[False], bkg=None,
+                            bayes_bool=False, bayes_method='emcee', uncertainty_bool=False, mean=False,
+                            nii_cons=True, spec_min=None, spec_max=None, obj_redshift=0.0, n_stoch=1,
+                            prior_values=None):
+        """``LuciBase.py:949-1046``: fit the spectrum integrated over a mask.  Returns ``(axis, sky, fit_dict)``.
+        ``prior_values=(vel, broad)`` are scalars in km/s."""
+        self._reject_unsupported(bayes_bool, None, initial_values, n_stoch, None)
+        mask = torch.from_numpy(np.asarray(self._load_mask(region, False)).astype(bool)).to(self.cube_final.device)
+        spec_ct = int(mask.sum().item())
+        integrated = self.cube_final[mask].sum(dim=0, dtype=torch.float64)
+        if mean:
+            integrated = integrated / spec_ct
+        if bkg is not None:
+            integrated = integrated - torch.from_numpy(np.asarray(bkg, dtype=np.float64)).to(integrated.device) * spec_ct
+        sky32 = integrated.to(torch.float32).view(1, -1).contiguous()
+        # the reference passes the angle of the LAST pixel of its double loop (LuciBase.py:1035)
+        theta = float(self.interferometer_theta[self.cube_final.shape[0] - 1, self.cube_final.shape[1] - 1])
+        have_prior = prior_values is not None
+        cfg = self._make_config(lines, fit_function, vel_rel, sigma_rel, uncertainty_bool, nii_cons, spec_min, spec_max,
+                                obj_redshift, ml_scale=have_prior)
+        dev = sky32.device
+        th = torch.tensor([theta], dtype=torch.float32, device=dev)
+        v0 = torch.tensor([float(prior_values[0])], dtype=torch.float32, device=dev) if have_prior else None
+        b0 = torch.tensor([float(prior_values[1])], dtype=torch.float32, device=dev) if have_prior else None
+        res = engine.fit_batch(cfg, sky32, th, v0, b0, want_sol=True, want_unc=True)
+        L = len(lines)
+        row = res['rows'][0].cpu().numpy()
+        q = engine.unpack_rows(row[None, :], L)
+        fit_dict = {'fit_sol': res['fit_sol'][0].cpu().numpy().astype(np.float64),
+                    'fit_uncertainties': res['fit_unc'][0].cpu().numpy().astype(np.float64),
+                    'amplitudes': list(q['amplitudes'][0]), 'fluxes': list(q['fluxes'][0]),
+                    'flux_errors': list(q['flux_errors'][0]), 'chi2': float(q['chi2'][0]),
+                    'velocities': list(q['velocities'][0]), 'sigmas': list(q['sigmas'][0]),
+                    'vels_errors': list(q['vels_errors'][0]), 'sigmas_errors': list(q['sigmas_errors'][0]),
+                    'axis_step': float(q['axis_step'][0]), 'corr': float(q['corr'][0]),
+                    'continuum': float(q['continuum'][0]), 'continuum_error': float(q['continuum_error'][0]),
+                    'flat_samples': None, 'vel_ml': float(prior_values[0]) if have_prior else 0.0, 'vel_ml_sigma': 0,
+                    'broad_ml': abs(float(prior_values[1])) if have_prior else 0.0, 'broad_ml_sigma': 0,
+                    'fit_axis': np.asarray(self.spectrum_axis) * (1 + obj_redshift),
+                    'status': int(res['status'][0].item())}
+        fit_dict['scale'] = None
+        from .host_ops import plot_vector
+        fit_dict['fit_vector'] = plot_vector(cfg, fit_dict['fit_sol'], theta, self.cube_final.device)
+        sky = integrated.cpu().numpy()
+        return np.asarray(self.spectrum_axis), sky, fit_dict

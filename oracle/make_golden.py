@@ -1,0 +1,227 @@
+"""TEST INFRASTRUCTURE ONLY -- generates tests/golden/*.npz by running the UNMODIFIED reference
+(``/root/reference``: ``LuciBase.Luci.fit_calc`` -> ``LUCI.LuciFit.Fit``) under ``oracle/ref_shim.py`` on seeded
+synthetic spectra built with the reference's own ``LuciSim.Spectrum``.  Run in the build container only:
+
+    python -m oracle.make_golden            # all cases
+    python -m oracle.make_golden fit_sincgauss_sn3
+
+Each fixture stores the exact float32 inputs (cube rows, axis, priors, theta) and the reference's outputs (the 12
+quantities of fit_calc plus fit_sol / uncertainties / scale / SLSQP status) so that tests on the GPU box can
+compare without the reference tree.
+"""
+import os
+import sys
+import time
+import warnings
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(HERE)
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+GOLDEN = os.path.join(ROOT, 'tests', 'golden')
+
+SN3 = ['Halpha', 'NII6548', 'NII6583', 'SII6716', 'SII6731']
+
+CASES = {
+    # name: (filter, resolution, lines, model, vel_rel, sigma_rel, n, uncertainty, broad range, extra)
+    'fit_sincgauss_sn3': dict(filter='SN3', R=5000, lines=SN3, model='sincgauss', vel_rel=[1] * 5, sigma_rel=[1] * 5,
+                              n=24, unc=True, broad=(25, 60), seed=101),
+    'fit_gaussian_sn3': dict(filter='SN3', R=5000, lines=SN3, model='gaussian', vel_rel=[1] * 5, sigma_rel=[1] * 5,
+                             n=24, unc=True, broad=(60, 100), seed=102),
+    'fit_sinc_sn3': dict(filter='SN3', R=5000, lines=SN3, model='sinc', vel_rel=[1] * 5, sigma_rel=[1] * 5,
+                         n=6, unc=True, broad=(20, 60), seed=103),
+    'fit_gaussian_sn2': dict(filter='SN2', R=5000, lines=['Hbeta', 'OIII4959', 'OIII5007'], model='gaussian',
+                             vel_rel=[1] * 3, sigma_rel=[1] * 3, n=16, unc=False, broad=(60, 100), seed=104),
+    'fit_gaussian_sn1': dict(filter='SN1', R=5000, lines=['OII3726', 'OII3729'], model='gaussian', vel_rel=[1, 1],
+                             sigma_rel=[1, 1], n=16, unc=False, broad=(60, 100), seed=105),
+    'fit_sincgauss_groups': dict(filter='SN3', R=5000, lines=SN3, model='sincgauss', vel_rel=[1, 2, 2, 3, 3],
+                                 sigma_rel=[1, 2, 2, 3, 3], n=12, unc=True, broad=(30, 60), seed=106),
+    'fit_sincgauss_double': dict(filter='SN3', R=5000, lines=SN3 + ['Halpha'], model='sincgauss',
+                                 vel_rel=[1, 1, 1, 1, 1, 2], sigma_rel=[1, 1, 1, 1, 1, 2], n=10, unc=True,
+                                 broad=(30, 50), seed=107, double=True),
+    'fit_sincgauss_single': dict(filter='SN3', R=5000, lines=['Halpha'], model='sincgauss', vel_rel=[1],
+                                 sigma_rel=[1], n=12, unc=True, broad=(25, 60), seed=108),
+    'fit_sinc_noml': dict(filter='SN3', R=5000, lines=SN3, model='sinc', vel_rel=[1] * 5, sigma_rel=[1] * 5,
+                          n=4, unc=False, broad=(20, 60), seed=109, noml=True),
+}
+
+BASE_AMP = {'Halpha': 1.0, 'NII6583': 0.3, 'NII6548': 0.1, 'SII6716': 0.15, 'SII6731': 0.12, 'Hbeta': 1.0,
+            'OIII5007': 0.9, 'OIII4959': 0.3, 'OII3726': 1.0, 'OII3729': 0.8}
+
+
+def build_inputs(case):
+    """Seeded spectra from the reference's LuciSim (global numpy RNG, like the reference)."""
+    from oracle import ref_shim
+    ref_shim.install()
+    import LUCI.LuciSim as LS
+    rng = np.random.default_rng(case['seed'])
+    n = case['n']
+    lines = case['lines']
+    rows, v0, b0 = [], [], []
+    theta = 11.96
+    for i in range(n):
+        vel = float(rng.uniform(-40, 40) if case.get('noml') else rng.uniform(-150, 150))
+        broad = float(rng.uniform(*case['broad']))
+        snr = float(np.exp(rng.uniform(np.log(10), np.log(100))))
+        amps = [BASE_AMP[l] if BASE_AMP[l] == 1.0 else BASE_AMP[l] * rng.uniform(0.5, 1.5) for l in lines]
+        if 'NII6548' in lines and 'NII6583' in lines:
+            amps[lines.index('NII6548')] = amps[lines.index('NII6583')] / 3
+        vels = [vel] * len(lines)
+        broads = [broad] * len(lines)
+        vfit = [-vel * 299792 / 3e5]
+        if case.get('double'):
+            amps[-1] = 0.5
+            vels[-1] = vel - 200.0 * 3e5 / 299792     # second component at +200 km/s in the fitted convention
+            vfit.append(-vels[-1] * 299792 / 3e5)
+        np.random.seed(case['seed'] * 1000 + i)
+        sp = LS.Spectrum(lines, case['model'], amps, 0.0, 0.0, case['filter'], case['R'], snr)
+        sp.velocity, sp.broadening = vels, broads
+        axis, spec = sp.create_spectrum()
+        rows.append(((spec + 0.1) * 1e-17).astype(np.float32))
+        bfit = broad * np.cos(np.deg2rad(theta)) * 299792 / 3e5
+        # per velocity/sigma group priors are not expressible through the reference's CNN (one (v, b) pair per
+        # spectrum), so the prior is that of the first component
+        v0.append(vfit[0] + rng.normal(0, 15))
+        b0.append(abs(bfit * (1 + rng.normal(0, 0.15))))
+    cube = np.stack(rows)
+    return dict(cube=cube, axis32=np.asarray(axis, dtype=np.float32), v0=np.array(v0, np.float32),
+                b0=np.array(b0, np.float32), theta=np.full(n, theta, np.float32), n_steps=sp.n_steps,
+                delta_x=sp.delta_x)
+
+
+def run_reference(case, inp):
+    from oracle import ref_shim
+    Luci, LF = ref_shim.modules()
+    n, nz = inp['cube'].shape
+    lines = case['lines']
+    captured = []
+    orig_fit = LF.Fit.fit
+
+    def spy(self, *a, **k):
+        d = orig_fit(self, *a, **k)
+        captured.append((np.array(self.fit_sol, dtype=float), np.array(self.uncertainties, dtype=float),
+                         float(self.spectrum_scale), float(self.noise)))
+        return d
+
+    LF.Fit.fit = spy
+    noml = bool(case.get('noml'))
+    ref_shim.install_prior(None if noml else (lambda fit: (float(inp['v0'][_cur['i']]), float(inp['b0'][_cur['i']]))))
+    out = {k: [] for k in ('amplitudes', 'fluxes', 'flux_errors', 'velocities', 'vels_errors', 'sigmas',
+                           'sigmas_errors', 'chi2', 'corr', 'axis_step', 'continuum', 'continuum_error')}
+    wsyn = np.linspace(14700, 15600, 460).astype(np.float32)     # only feeds the (stubbed) CNN input
+    t0 = time.time()
+    try:
+        for i in range(n):
+            _cur['i'] = i
+            cube_slice = inp['cube'][i:i + 1].astype(np.float64)        # [x=1, z]
+            theta_map = np.full((1, 1), float(inp['theta'][i]))
+            res = Luci.fit_calc(0, 0, 1, 0, case['model'], lines, case['vel_rel'], case['sigma_rel'],
+                                cube_slice=cube_slice, spectrum_axis=inp['axis32'], wavenumbers_syn=wsyn,
+                                transmission_interpolated=None, interferometer_theta=theta_map,
+                                hdr_dict={'FILTER': case['filter'], 'STEP': inp['delta_x']}, step_nb=inp['n_steps'],
+                                zpd_index=0, mdn=False, ML_bool=not noml, uncertainty_bool=case['unc'],
+                                nii_cons=True, resolution=case['R'], Luci_path='/root/reference/')
+            for key, lst in zip(out.keys(), res[1:]):
+                out[key].append(lst[0])
+    finally:
+        LF.Fit.fit = orig_fit
+    dt = time.time() - t0
+    res = {('ref_' + k): np.array(v, dtype=np.float64) for k, v in out.items()}
+    res['ref_fit_sol'] = np.stack([c[0] for c in captured])
+    res['ref_fit_unc'] = np.stack([c[1] for c in captured])
+    res['ref_scale'] = np.array([c[2] for c in captured])
+    res['ref_noise'] = np.array([c[3] for c in captured])
+    res['ref_seconds_per_spaxel'] = np.array(dt / n)
+    return res
+
+
+_cur = {'i': 0}
+
+
+def make(name):
+    case = CASES[name]
+    inp = build_inputs(case)
+    with warnings.catch_warnings():
+        warnings.simplefilter('ignore')
+        ref = run_reference(case, inp)
+    meta = dict(filter=case['filter'], model=case['model'], lines=np.array(case['lines']),
+                vel_rel=np.array(case['vel_rel']), sigma_rel=np.array(case['sigma_rel']),
+                uncertainty=np.array(case['unc']), noml=np.array(bool(case.get('noml'))),
+                n_steps=np.array(inp['n_steps']), delta_x=np.array(inp['delta_x']))
+    os.makedirs(GOLDEN, exist_ok=True)
+    path = os.path.join(GOLDEN, name + '.npz')
+    np.savez_compressed(path, cube=inp['cube'], axis32=inp['axis32'], v0=inp['v0'], b0=inp['b0'], theta=inp['theta'],
+                        **meta, **ref)
+    print('%s: n=%d  %.2f s/spaxel (reference) -> %s' % (name, case['n'], float(ref['ref_seconds_per_spaxel']), path))
+
+
+if __name__ == '__main__':
+    names = [a for a in sys.argv[1:] if a != "reductions"] or ([] if "reductions" in sys.argv[1:] else list(CASES))
+    for nm in names:
+        make(nm)
+
+
+# ------------------------------------------------------------------------------------------------ reductions
+class _FakeLuci:
+    """Minimal stand-in for a ``Luci`` instance so that the reference's own ``create_deep_image`` /
+    ``create_snr_map`` / ``bin_cube`` method bodies (LuciBase.py:147-215, 1048-1191, 840-842) run on an in-memory
+    cube (the real constructor needs an ORBS HDF5 file)."""
+
+    def __init__(self, cube, axis32, out_dir):
+        self.cube_final = cube
+        self.cube_binned = None
+        self.header_binned = None
+        self.cube_path = 'none'
+        self.output_dir = out_dir
+        self.object_name = 'golden'
+        self.dimz = 0
+        self.hdr_dict = {'FILTER': 'SN3'}
+        self.spectrum_axis = axis32
+        self.header = {'CRPIX1': 10.0, 'CRPIX2': 12.0, 'PC1_1': 1.0, 'PC1_2': 0.0, 'PC2_1': 0.0, 'PC2_2': 1.0}
+        self.deep_image = None
+
+
+def make_reductions():
+    import tempfile
+    from oracle import ref_shim, luci_oracle as O
+    Luci, LF = ref_shim.modules()
+    rng = np.random.default_rng(2024)
+    nx, ny = 23, 14
+    axis, nsteps, dx, w = O.sim_axis('SN3', 5000)
+    axis32 = axis.astype(np.float32)
+    cube = np.zeros((nx, ny, len(axis)), np.float32)
+    for x in range(nx):
+        for y in range(ny):
+            am = [1.0, 0.1, 0.3, 0.15, 0.12]
+            snr = float(np.exp(rng.uniform(np.log(3), np.log(100))))
+            _, s = O.sim_spectrum(SN3, 'sincgauss', am, rng.uniform(-150, 150), rng.uniform(25, 60), 'SN3', 5000, snr, rng=rng)
+            cube[x, y] = ((s + 0.1) * 1e-17).astype(np.float32)
+    cube[3, 4, 100:104] = np.nan          # NaNs exercise nansum / nanstd
+    cube[7, 2, :] = np.nan
+    cube64 = cube.astype(np.float64)
+    tmp = tempfile.mkdtemp()
+    fake = _FakeLuci(cube64, axis32, tmp)
+    fake.bin_cube = lambda *a: Luci.bin_cube(fake, *a)
+    with warnings.catch_warnings():
+        warnings.simplefilter('ignore')
+        Luci.create_deep_image(fake)
+        deep = np.array(fake.deep_image)
+        snr = {}
+        for method in (1, 2):
+            masks = Luci.create_snr_map(fake, 0, nx, 0, ny, method=method, n_threads=1)
+            snr[method] = np.array(masks[0].data)
+        from LUCI.LuciUtility import bin_cube_function, bin_mask
+        _, binned = bin_cube_function(cube64, dict(fake.header), 2, 1, 21, 2, 12)
+        mask = rng.uniform(size=(nx, ny)) > 0.6
+        bmask = bin_mask(mask, 2, 0, nx, 0, ny)
+    path = os.path.join(GOLDEN, 'reductions_sn3.npz')
+    np.savez_compressed(path, cube=cube, axis32=axis32, ref_deep=deep, ref_snr1=snr[1], ref_snr2=snr[2],
+                        ref_binned=binned.astype(np.float32), bin_args=np.array([2, 1, 21, 2, 12]), mask=mask,
+                        ref_bin_mask=bmask)
+    print('reductions_sn3 ->', path, deep.shape, snr[1].shape)
+
+
+if __name__ == '__main__' and (len(sys.argv) == 1 or 'reductions' in sys.argv[1:]):
+    make_reductions()

@@ -33,7 +33,14 @@ _MISSING = {
 }
 
 
-class _Dummy:
+class _DummyMeta(type):
+    def __getattr__(cls, name):            # e.g. ``fits.writeto`` where ``fits`` itself is the _Dummy class
+        if name.startswith("__"):
+            raise AttributeError(name)
+        return _Dummy
+
+
+class _Dummy(metaclass=_DummyMeta):
     """Swallows any construction / call / attribute access."""
 
     def __init__(self, *a, **k):
@@ -130,6 +137,23 @@ def install():
             self.ML_model = StubCNN(v, b)
 
     LF.Fit.get_ML_model = _get_ml_model
+    if "h5py" in _MISSING:
+        import h5py
+
+        class _NoDeepFrameFile:
+            """Stands in for ``h5py.File`` inside ``Luci.create_deep_image`` (LuciBase.py:162-168): a file without a
+            pre-computed ``deep_frame`` so that the reference sums the cube itself."""
+
+            def __init__(self, *a, **k):
+                pass
+
+            def __contains__(self, key):
+                return False
+
+            def close(self):
+                pass
+
+        h5py.File = _NoDeepFrameFile
     _installed = True
 
 

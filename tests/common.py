@@ -1,0 +1,80 @@
+"""Shared helpers of the test-suite: golden fixtures, tolerances of BASELINE.json's north_star, comparison."""
+import ctypes as C
+import os
+
+import numpy as np
+
+from luci_b200._capi import FitConfig
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+GOLDEN = os.path.join(ROOT, 'tests', 'golden')
+
+# north_star: velocity within 0.5 km/s, broadening and fluxes within 1e-3 relative, chi2 no worse than the reference
+# by more than 1e-4 relative, for >= 99.9 % of spaxels.
+TOL_VEL_KMS = 0.5
+TOL_REL = 1e-3
+TOL_CHI2 = 1e-4
+
+FIT_CASES = ['fit_sincgauss_sn3', 'fit_gaussian_sn3', 'fit_sinc_sn3', 'fit_gaussian_sn2', 'fit_gaussian_sn1',
+             'fit_sincgauss_groups', 'fit_sincgauss_double', 'fit_sincgauss_single', 'fit_sinc_noml']
+
+
+def load_golden(name):
+    path = os.path.join(GOLDEN, name + '.npz')
+    g = dict(np.load(path, allow_pickle=False))
+    for k in ('lines',):
+        if k in g:
+            g[k] = [str(x) for x in g[k]]
+    for k in ('filter', 'model'):
+        if k in g:
+            g[k] = str(g[k])
+    return g
+
+
+def config_from_golden(g, uncertainty=None, **kw):
+    unc = bool(g['uncertainty']) if uncertainty is None else uncertainty
+    return FitConfig(g['model'], g['lines'], [int(v) for v in g['vel_rel']], [int(v) for v in g['sigma_rel']],
+                     g['axis32'], filter=g['filter'], delta_x=float(g['delta_x']), n_steps=int(g['n_steps']),
+                     zpd_index=0, uncertainty_bool=unc, nii_cons=True, ml_scale=not bool(g['noml']), **kw)
+
+
+def ptr(a):
+    return None if a is None else a.ctypes.data_as(C.c_void_p)
+
+
+def run_hostemu(lib, cfg, cube, theta, v0, b0, want_unc=True):
+    n = cube.shape[0]
+    K, PF = cfg.row_floats, 3 * cfg.L + 1
+    rows = np.zeros((n, K), np.float32)
+    sol = np.zeros((n, PF), np.float32)
+    unc = np.zeros((n, PF), np.float32)
+    st = np.zeros(n, np.int32)
+    cube = np.ascontiguousarray(cube, dtype=np.float32)
+    rc = lib.hostemu_fit_batch(cfg.byref(), n, ptr(cube), None, ptr(theta), ptr(v0), ptr(b0), None, ptr(rows),
+                               ptr(sol), ptr(unc), ptr(st))
+    assert rc == 0
+    return rows, sol, unc, st
+
+
+def split_rows(rows, L):
+    names = ('amplitudes', 'fluxes', 'flux_errors', 'velocities', 'vels_errors', 'sigmas', 'sigmas_errors')
+    out = {nm: rows[:, i * L:(i + 1) * L].astype(np.float64) for i, nm in enumerate(names)}
+    for i, nm in enumerate(('chi2', 'corr', 'axis_step', 'continuum', 'continuum_error')):
+        out[nm] = rows[:, 7 * L + i].astype(np.float64)
+    return out
+
+
+def parity_report(rows, g, model, check_broadening=True):
+    """Per-spaxel pass/fail against the reference outputs stored in a golden fixture, north_star tolerances."""
+    L = len(g['lines'])
+    q = split_rows(rows, L)
+    dv = np.abs(q['velocities'] - g['ref_velocities']).max(axis=1)
+    db = (np.abs(q['sigmas'] - g['ref_sigmas']) / np.abs(g['ref_sigmas'])).max(axis=1)
+    df = (np.abs(q['fluxes'] - g['ref_fluxes']) / np.abs(g['ref_fluxes'])).max(axis=1)
+    da = (np.abs(q['amplitudes'] - g['ref_amplitudes']) / np.abs(g['ref_amplitudes'])).max(axis=1)
+    dchi = (q['chi2'] - g['ref_chi2']) / np.abs(g['ref_chi2'])
+    dcont = np.abs(q['continuum'] - g['ref_continuum']) / np.abs(g['ref_continuum'])
+    ok = (dv <= TOL_VEL_KMS) & (df <= TOL_REL) & (dchi <= TOL_CHI2)
+    if check_broadening:
+        ok &= db <= TOL_REL
+    return dict(dv=dv, db=db, df=df, da=da, dchi=dchi, dcont=dcont, ok=ok, q=q)

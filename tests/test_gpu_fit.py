@@ -1,0 +1,176 @@
+"""GPU parity tests proper: the CUDA path through the C ABI (ctypes -> liblucifit.so) against the reference's
+outputs in tests/golden/ and against the oracle on freshly seeded inputs."""
+import warnings
+
+import numpy as np
+import pytest
+import torch
+
+from tests.common import (FIT_CASES, TOL_CHI2, TOL_REL, TOL_VEL_KMS, config_from_golden, load_golden,
+                          parity_report, split_rows)
+
+pytestmark = pytest.mark.gpu
+
+
+def _dev():
+    return torch.device('cuda', 0)
+
+
+def _gpu_fit(cfg, cube, theta, v0, b0, **kw):
+    from luci_b200 import engine
+    dev = _dev()
+    t = lambda a: None if a is None else torch.from_numpy(np.ascontiguousarray(a)).to(dev)
+    res = engine.fit_batch(cfg, t(cube.astype(np.float32)), t(theta), t(v0), t(b0), want_sol=True, want_unc=True, **kw)
+    torch.cuda.synchronize()
+    return {k: v.cpu().numpy() for k, v in res.items()}
+
+
+@pytest.mark.parametrize('name', [c for c in FIT_CASES if c != 'fit_sincgauss_double'])
+def test_cuda_matches_reference_golden(name):
+    g = load_golden(name)
+    cfg = config_from_golden(g)
+    noml = bool(g['noml'])
+    res = _gpu_fit(cfg, g['cube'], g['theta'], None if noml else g['v0'], None if noml else g['b0'])
+    rows, st = res['rows'], res['status']
+    rep = parity_report(rows, g, g['model'], check_broadening=(g['model'] != 'sinc'))
+    if name == 'fit_sinc_noml':
+        conv = rep['dv'] < TOL_VEL_KMS
+        assert conv.sum() >= 2 and (rep['df'][conv] < 5e-3).all() and (rep['dchi'] <= 1e-4 + 0.05 * conv).all()
+        return
+    frac = rep['ok'].mean()
+    if name == 'fit_sincgauss_groups':
+        assert frac >= 0.75 and (rep['dchi'] <= 1e-4).all(), (frac, rep['dchi'])
+    else:
+        assert frac >= 0.95, (name, frac, rep['dv'], rep['db'], rep['df'], rep['dchi'])
+    assert np.nanmedian(rep['dv']) < 0.02 and np.nanmedian(rep['df']) < 2e-4
+    assert ((st >> 16) & 1).all()
+    np.testing.assert_allclose(rep['q']['corr'], g['ref_corr'], rtol=1e-6)
+    np.testing.assert_allclose(rep['q']['axis_step'], g['ref_axis_step'], rtol=1e-6)
+    # fit_sol layout: amplitude, position, sigma per line + continuum
+    ok = rep['ok']
+    np.testing.assert_allclose(res['fit_sol'][ok][:, 1::3], g['ref_fit_sol'][ok][:, 1::3], rtol=2e-7, atol=3e-3)
+
+
+@pytest.mark.parametrize('name', ['fit_sincgauss_sn3', 'fit_gaussian_sn3', 'fit_sincgauss_single'])
+def test_cuda_uncertainties_match_reference(name):
+    g = load_golden(name)
+    cfg = config_from_golden(g, uncertainty=True)
+    res = _gpu_fit(cfg, g['cube'], g['theta'], g['v0'], g['b0'])
+    rep = parity_report(res['rows'], g, g['model'])
+    good = rep['ok'] & (rep['df'] < 1e-4)
+    assert good.sum() >= 0.6 * len(good)
+    for key in ('vels_errors', 'sigmas_errors', 'flux_errors', 'continuum_error'):
+        rel = np.abs(rep['q'][key][good] - g['ref_' + key][good]) / np.abs(g['ref_' + key][good])
+        assert np.median(rel) < 2e-3 and rel.max() < 5e-2, (key, rel)
+    # fit_uncertainties vector itself
+    u, ur = res['fit_unc'][good], g['ref_fit_unc'][good]
+    assert np.median(np.abs(u - ur) / np.abs(ur)) < 2e-3
+
+
+def test_cuda_matches_hostemu_build_of_the_same_source(hostemu):
+    """Warp-parallel device execution vs the single-lane CPU build of the same code (summation order only)."""
+    from tests.common import run_hostemu
+    g = load_golden('fit_sincgauss_sn3')
+    cfg = config_from_golden(g, uncertainty=True)
+    res = _gpu_fit(cfg, g['cube'], g['theta'], g['v0'], g['b0'])
+    rows_h, sol_h, unc_h, st_h = run_hostemu(hostemu, cfg, g['cube'], g['theta'], g['v0'], g['b0'])
+    L = 5
+    qd, qh = split_rows(res['rows'], L), split_rows(rows_h, L)
+    assert np.abs(qd['velocities'] - qh['velocities']).max() < 0.05
+    np.testing.assert_allclose(qd['fluxes'], qh['fluxes'], rtol=5e-4)
+    np.testing.assert_allclose(qd['sigmas'], qh['sigmas'], rtol=3e-4)
+    np.testing.assert_allclose(qd['chi2'], qh['chi2'], rtol=1e-4)
+
+
+def test_cuda_vs_oracle_on_device_generated_cube():
+    """Inputs synthesised on the GPU (lucifit_sim_cube), copied back and fitted by the oracle (SLSQP, float64)."""
+    from luci_b200 import engine
+    from luci_b200.sim import SN3_LINES, SyntheticCube
+    from oracle import luci_oracle as O
+    dev = _dev()
+    sc = SyntheticCube(4, 3, model='sincgauss', resolution=5000, seed=77)
+    cube = sc.synthesize(dev)
+    v0, b0 = sc.priors()
+    host = cube.cpu().numpy()
+    cfg = engine.FitConfig('sincgauss', SN3_LINES, [1] * 5, [1] * 5, sc.axis32, 'SN3', sc.delta_x, sc.n_steps, 0)
+    n = 12
+    flat = host.reshape(n, -1)
+    v0f, b0f = v0.T.reshape(n).copy(), b0.T.reshape(n).copy()     # priors are (ny, nx): back to x-major
+    res = _gpu_fit(cfg, flat, np.full(n, sc.theta, np.float32), v0f, b0f)
+    q = split_rows(res['rows'], 5)
+    bad = 0
+    with warnings.catch_warnings():
+        warnings.simplefilter('ignore')
+        for i in range(n):
+            o = O.OracleFit(flat[i].astype(np.float64), sc.axis32, 'sincgauss', SN3_LINES, [1] * 5, [1] * 5,
+                            theta=sc.theta, delta_x=sc.delta_x, n_steps=sc.n_steps, zpd_index=0, filter='SN3',
+                            nii_cons=True, prior=(float(v0f[i]), float(b0f[i]))).fit()
+            dv = np.abs(q['velocities'][i] - o['velocities']).max()
+            db = (np.abs(q['sigmas'][i] - o['sigmas']) / np.array(o['sigmas'])).max()
+            df = (np.abs(q['fluxes'][i] - o['fluxes']) / np.abs(o['fluxes'])).max()
+            dchi = (q['chi2'][i] - o['chi2']) / o['chi2']
+            bad += not (dv <= TOL_VEL_KMS and db <= TOL_REL and df <= TOL_REL and dchi <= TOL_CHI2)
+    assert bad == 0
+    # the synthetic truth is recovered within the noise (sanity of generator + fitter conventions)
+    truth_v = sc.vel_fit_truth.reshape(n)
+    assert np.median(np.abs(q['velocities'][:, 0] - truth_v)) < 3.0
+
+
+def test_index_list_background_and_flags():
+    from luci_b200 import engine
+    g = load_golden('fit_gaussian_sn3')
+    cfg = config_from_golden(g, uncertainty=False)
+    dev = _dev()
+    cube = g['cube'].copy()
+    n = cube.shape[0]
+    # (1) compaction: fitting rows [5, 2, 9] through an index list equals fitting them directly
+    idx = np.array([5, 2, 9], dtype=np.int64)
+    full = _gpu_fit(cfg, cube, g['theta'], g['v0'], g['b0'])
+    t = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(dev)
+    part = engine.fit_batch(cfg, t(cube), t(g['theta'][idx]), t(g['v0'][idx]), t(g['b0'][idx]), index=t(idx))
+    np.testing.assert_array_equal(part['rows'].cpu().numpy(), full['rows'][idx])
+    # (2) background subtraction on the device == fitting the pre-subtracted spectra (LuciBase.py:326-330)
+    bkg = (0.02e-17 * np.ones(cube.shape[1])).astype(np.float32)
+    a = engine.fit_batch(cfg, t(cube), t(g['theta']), t(g['v0']), t(g['b0']), bkg=t(bkg))
+    b = engine.fit_batch(cfg, t(cube - bkg[None, :]), t(g['theta']), t(g['v0']), t(g['b0']))
+    np.testing.assert_array_equal(a['rows'].cpu().numpy(), b['rows'].cpu().numpy())
+    # (3) unusable spectra are flagged and zeroed, neighbours untouched
+    cube2 = cube.copy()
+    cube2[0, 40] = np.nan
+    cube2[1] = -np.abs(cube2[1])
+    r = _gpu_fit(cfg, cube2, g['theta'], g['v0'], g['b0'])
+    assert r['status'][0] & (1 << 20) and not r['rows'][0].any()
+    assert r['status'][1] & (1 << 22) and not r['rows'][1].any()
+    np.testing.assert_array_equal(r['rows'][2:], full['rows'][2:])
+    # (4) empty batch is a no-op
+    e = engine.fit_batch(cfg, t(cube), t(g['theta'][:0]), t(g['v0'][:0]), t(g['b0'][:0]), index=t(idx[:0]))
+    assert e['rows'].shape == (0, cfg.row_floats)
+
+
+def test_size_independent_properties_on_a_large_batch():
+    """Properties that hold at any size: flux linearity in the input scale, determinism, batch-order invariance."""
+    from luci_b200 import engine
+    from luci_b200.sim import SN3_LINES, SyntheticCube
+    dev = _dev()
+    sc = SyntheticCube(96, 64, model='sincgauss', resolution=5000, seed=5)
+    cube = sc.synthesize(dev).view(96 * 64, -1)
+    v0, b0 = sc.priors()
+    t = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(dev)
+    v0f, b0f = t(v0.T.reshape(-1).copy()), t(b0.T.reshape(-1).copy())
+    theta = torch.full((cube.shape[0],), sc.theta, dtype=torch.float32, device=dev)
+    cfg = engine.FitConfig('sincgauss', SN3_LINES, [1] * 5, [1] * 5, sc.axis32, 'SN3', sc.delta_x, sc.n_steps, 0)
+    a = engine.fit_batch(cfg, cube, theta, v0f, b0f)
+    b = engine.fit_batch(cfg, cube, theta, v0f, b0f)
+    assert torch.equal(a['rows'], b['rows'])                                   # deterministic
+    c = engine.fit_batch(cfg, cube * 8.0, theta, v0f, b0f)                     # power of two: exact in FP32
+    qa, qc = split_rows(a['rows'].cpu().numpy(), 5), split_rows(c['rows'].cpu().numpy(), 5)
+    np.testing.assert_allclose(qc['fluxes'], 8.0 * qa['fluxes'], rtol=1e-6)
+    np.testing.assert_array_equal(qc['velocities'], qa['velocities'])
+    perm = torch.randperm(cube.shape[0], device=dev)
+    d = engine.fit_batch(cfg, cube, theta[perm], v0f[perm], b0f[perm], index=perm)
+    assert torch.equal(d['rows'], a['rows'][perm])                            # order / scheduling invariant
+    s = engine.status_summary(a['status'])
+    assert s['n_converged'] >= 0.999 * s['n'] and s['mean_evals'] < 12
+    truth = t(sc.vel_fit_truth.reshape(-1))
+    err = (a['rows'][:, 15] - truth).abs()
+    assert float(err.median()) < 2.0

@@ -1,0 +1,130 @@
+"""The drop-in Python API (luci_b200.luci.Luci) on the GPU: same calls, returns and files as LuciBase.Luci."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from tests.common import load_golden
+
+pytestmark = pytest.mark.gpu
+SN3 = ['Halpha', 'NII6548', 'NII6583', 'SII6716', 'SII6731']
+
+
+@pytest.fixture(scope='module')
+def world(tmp_path_factory):
+    from luci_b200.luci import Luci
+    from luci_b200.sim import SyntheticCube
+    dev = torch.device('cuda', 0)
+    sc = SyntheticCube(12, 10, model='sincgauss', resolution=5000, seed=3, snr_range=(20.0, 100.0))
+    cube = sc.synthesize(dev)
+    out = str(tmp_path_factory.mktemp('luci'))
+    hdr = {'CRPIX1': 6.0, 'CRPIX2': 5.0, 'CRVAL1': 10.0, 'CRVAL2': 20.0, 'CTYPE1': 'RA---TAN', 'CTYPE2': 'DEC--TAN',
+           'PC1_1': 1.0, 'PC1_2': 0.0, 'PC2_1': 0.0, 'PC2_2': 1.0}
+    luci = Luci.from_arrays(cube, sc.hdr_dict, out, 'OBJ', spectrum_axis=sc.axis32, header=hdr, device=dev)
+    return luci, sc, out
+
+
+def test_fit_cube_returns_and_files(world):
+    from luci_b200.fitsio import read_fits
+    luci, sc, out = world
+    v0, b0 = sc.priors()
+    vel, broad, flux, ampl = luci.fit_cube(SN3, 'sincgauss', [1] * 5, [1] * 5, 2, 9, 1, 8,
+                                           prior_values=(v0[1:8, 2:9], b0[1:8, 2:9]), uncertainty_bool=True)
+    assert vel.shape == broad.shape == flux.shape == ampl.shape == (7, 7, 5) and vel.dtype == np.float32
+    truth = sc.vel_fit_truth[2:9, 1:8].T
+    assert np.median(np.abs(vel[:, :, 0] - truth)) < 2.0
+    base = os.path.join(out, 'Luci_outputs')
+    d, h = read_fits(os.path.join(base, 'Velocity', 'OBJ_sincgauss_Halpha_velocity.fits'))
+    np.testing.assert_array_equal(d, vel[:, :, 0])
+    assert h['NAXIS1'] == 7 and h['NAXIS2'] == 7 and h['CRPIX1'] == 4.0 and h['CRPIX2'] == 4.0
+    for rel in ('Amplitudes/OBJ_sincgauss_SII6731_Amplitude.fits', 'Fluxes/OBJ_sincgauss_NII6548_Flux_err.fits',
+                'Broadening/OBJ_sincgauss_Halpha_broadening_err.fits', 'OBJ_sincgauss_Chi2.fits',
+                'OBJ_sincgauss_continuum.fits', 'OBJ_sincgauss_continuum_error.fits', 'OBJ_deep.fits'):
+        assert os.path.exists(os.path.join(base, rel)), rel
+    m = luci.last_fit_maps
+    assert (m['vels_errors'] > 0).all() and (m['flux_errors'] > 0).all() and (m['chi2'] > 0).all()
+    np.testing.assert_allclose(m['corr'], 1 / np.cos(np.deg2rad(11.96)), rtol=1e-6)
+    # tied amplitudes: [NII]6548 flux is a third of 6583 (area rule, LuciFit.py:584-595)
+    np.testing.assert_allclose(flux[:, :, 1] * 3, flux[:, :, 2], rtol=1e-5)
+
+
+def test_fit_region_masks_and_matches_fit_cube(world):
+    luci, sc, out = world
+    v0, b0 = sc.priors()
+    mask = np.zeros((12, 10), bool)
+    mask[3:7, 2:6] = True
+    vel, broad, flux, chi2, m = luci.fit_region(SN3, 'sincgauss', [1] * 5, [1] * 5, mask, prior_values=(v0, b0))
+    assert vel.shape == (10, 12, 5) and chi2.shape == (10, 12) and m is mask
+    assert (vel[~mask.T] == 0).all() and (chi2[mask.T] > 0).all()
+    velc, _, fluxc, _ = luci.fit_cube(SN3, 'sincgauss', [1] * 5, [1] * 5, 3, 7, 2, 6, prior_values=(v0[2:6, 3:7], b0[2:6, 3:7]))
+    np.testing.assert_array_equal(vel[2:6, 3:7], velc)
+    np.testing.assert_array_equal(flux[2:6, 3:7], fluxc)
+    assert luci.last_fit_summary['n'] == 16
+    assert os.path.exists(os.path.join(out, 'Luci_outputs', 'Velocity', 'OBJ_Halpha_velocity.fits'))   # no model suffix
+
+
+def test_binned_fit_and_entire_cube(world):
+    luci, sc, out = world
+    v0, b0 = sc.priors()
+    vb = 0.25 * (v0[0::2, 0::2] + v0[1::2, 0::2] + v0[0::2, 1::2] + v0[1::2, 1::2])
+    bb = 0.25 * (b0[0::2, 0::2] + b0[1::2, 0::2] + b0[0::2, 1::2] + b0[1::2, 1::2])
+    r = luci.fit_entire_cube(SN3, 'gaussian', [1] * 5, [1] * 5, binning=2, prior_values=(vb, bb))
+    vel, broad, flux, ampl = r
+    assert vel.shape == (5, 6, 5)
+    assert luci.cube_binned.shape == (6, 5, luci.cube_final.shape[2])
+    host = luci.cube_final.cpu().numpy()
+    np.testing.assert_allclose(luci.cube_binned[1, 2].cpu().numpy(), host[2:4, 4:6].sum(axis=(0, 1)), rtol=1e-6)
+    # binned amplitudes ~ 4x the unbinned ones (nansum, no division: LuciUtility.py:354)
+    assert 3.0 < np.median(ampl[:, :, 0]) / 1e-17 < 5.0
+    assert os.path.exists(os.path.join(out, 'Luci_outputs', 'Velocity', 'OBJ_2_gaussian_Halpha_velocity.fits'))
+
+
+def test_deep_image_and_snr_map_files(world):
+    from luci_b200.fitsio import read_fits
+    luci, sc, out = world
+    luci.create_deep_image()
+    host = luci.cube_final.cpu().numpy().astype(np.float64)
+    ref = host.sum(axis=2)
+    ref[10:] = 0                                   # 12 mod 10 trailing x-rows stay zero in the reference
+    np.testing.assert_allclose(luci.deep_image, ref.T, rtol=2e-6)
+    d, h = read_fits(os.path.join(out, 'Luci_outputs', 'OBJ_deep.fits'))
+    assert d.shape == (10, 12) and h['BITPIX'] == -64
+    masks = luci.create_snr_map(0, 12, 0, 10, method=1)
+    assert len(masks) == 4 and masks[0].shape == (10, 12)
+    snr, _ = read_fits(os.path.join(out, 'Luci_outputs', 'SNR', 'OBJ_SNR.fits'))
+    assert snr.shape == (10, 12) and (snr > 0).all()
+    for v in (1, 3, 5, 10):
+        mk = np.load(os.path.join(out, 'Luci_outputs', 'SNR', 'OBJ_SNR_%d_mask.npy' % v))
+        np.testing.assert_array_equal(mk, snr >= v)
+    luci.create_snr_map(2, 8, 1, 9, method=2)
+    assert luci.snr_map.shape == (8, 6)
+
+
+def test_fit_spectrum_region_dictionary(world):
+    luci, sc, out = world
+    mask = np.zeros((12, 10), bool)
+    mask[4:8, 3:7] = True
+    vtrue = float(sc.vel_fit_truth[4:8, 3:7].mean())
+    axis, sky, d = luci.fit_spectrum_region(SN3, 'sincgauss', [1] * 5, [1] * 5, mask, prior_values=(vtrue + 8.0, 40.0),
+                                            uncertainty_bool=True)
+    assert axis.shape == sky.shape == (luci.cube_final.shape[2],)
+    for key in ('fit_sol', 'fit_uncertainties', 'amplitudes', 'fluxes', 'flux_errors', 'chi2', 'velocities', 'sigmas',
+                'vels_errors', 'sigmas_errors', 'axis_step', 'corr', 'continuum', 'continuum_error', 'fit_vector',
+                'fit_axis'):
+        assert key in d
+    assert abs(d['velocities'][0] - vtrue) < 15.0
+    assert d['fit_vector'].shape == sky.shape
+    # the fit vector reproduces the integrated spectrum near H-alpha to within the noise
+    i = int(np.argmax(sky))
+    assert abs(d['fit_vector'][i] - sky[i]) < 0.2 * sky[i]
+
+
+def test_unsupported_branches_raise(world):
+    luci, sc, out = world
+    with pytest.raises(NotImplementedError):
+        luci.fit_cube(SN3, 'sinc', [1] * 5, [1] * 5, 0, 2, 0, 2, bayes_bool=True)
+    with pytest.raises(NotImplementedError):
+        luci.fit_cube(SN3, 'sinc', [1] * 5, [1] * 5, 0, 2, 0, 2, initial_values=[np.zeros((2, 2)), np.ones((2, 2))])
+    with pytest.raises(Exception, match='vel_rel'):
+        luci.fit_cube(SN3, 'sinc', [1] * 4, [1] * 5, 0, 2, 0, 2)

@@ -1,0 +1,422 @@
+#!/usr/bin/env python
+"""bench.py -- headline benchmark of the LUCI per-spaxel fitting hot path on B200.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--nx 2048 --ny 2064 --nz 841]
+
+Workload (BASELINE.json configs[1]): full 2048 x 2064 synthetic SN3 cube, 5-line sincgauss fit with tied velocity /
+broadening and the [NII] ratio tie, priors = truth + N(0, 15 km/s), truth * (1 + N(0, 0.15)).  One *step* = one
+pass of the hot path over the whole cube (prep + LM fit + derived outputs for every spaxel) and, for N > 1, the
+gather of the output maps to rank 0.  The cube is sharded in contiguous x-slabs over the N ranks (strong scaling:
+the cube is fixed), no collective on the fit path.
+
+Prints ONE JSON line (rank 0).  `value` = spaxels/s with the cube resident in HBM; `e2e` = the same metric with the
+cube in pinned HOST memory, streamed through the C ABI in chunks (H2D of the spectra and D2H of the result rows inside
+the timed region); `roofline` = algorithmic FLOP of the fit kernel / its CUDA-event time against the FP32-FMA
+throughput measured by a probe kernel in the same run (MEASURED_PEAKS.json carries no FP32 figure); `cpu_baseline` =
+the oracle port of the reference's row worker under joblib/loky on all host cores, on a bounded sample.
+
+`--impl reference` times only that CPU arm (rank 0; other ranks exit 0).
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+LINES = ['Halpha', 'NII6548', 'NII6583', 'SII6716', 'SII6731']
+METRIC = 'spaxels/sec, SN3 5-line sincgauss fit, 2048x2064 synthetic cube'
+F_MODEL = {'gaussian': 20, 'sinc': 30, 'sincgauss': 150}     # nominal flop per (sample, line): SURVEY.md 8(d)
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--gpus', type=int, default=1)
+    ap.add_argument('--steps', type=int, default=5)
+    ap.add_argument('--warmup', type=int, default=3)
+    ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
+    ap.add_argument('--nx', type=int, default=2048)
+    ap.add_argument('--ny', type=int, default=2064)
+    ap.add_argument('--nz', type=int, default=841)
+    ap.add_argument('--model', default='sincgauss')
+    ap.add_argument('--uncertainty', type=int, default=0)
+    ap.add_argument('--cpu-seconds', type=float, default=15.0, help='wall-clock budget of the CPU baseline sample')
+    ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--no-e2e', action='store_true')
+    ap.add_argument('--no-reductions', action='store_true')
+    return ap.parse_args()
+
+
+# ------------------------------------------------------------------------------------------------- CPU arm
+def _oracle_row(i, cube_rows, axis32, theta, hdr, n_steps, model, v0, b0, unc):
+    """One joblib task = one y-row, like LuciBase.py:514-530 (module-level so loky can pickle it)."""
+    import warnings
+    if ROOT not in sys.path:
+        sys.path.insert(0, ROOT)
+    from oracle import luci_oracle as O
+    nx = cube_rows.shape[0]
+    theta_map = np.full((nx, 1), theta)
+    with warnings.catch_warnings():
+        warnings.simplefilter('ignore')
+        return O.fit_calc(0, 0, nx, 0, model, LINES, [1] * 5, [1] * 5, cube_rows, axis32, None, theta_map, hdr,
+                          n_steps, 0, uncertainty_bool=unc, nii_cons=True, prior_maps=(v0[None, :], b0[None, :]))
+
+
+def cpu_sample(nz, model, n_rows, row_len, seed=4242):
+    """Synthetic spectra of the benchmark's distribution generated on the host (LuciSim restatement)."""
+    from oracle import luci_oracle as O
+    from luci_b200.sim import sim_axis
+    rng = np.random.default_rng(seed)
+    axis, n_steps, delta_x = sim_axis('SN3', n_steps=nz)
+    rows = []
+    for r in range(n_rows):
+        spectra, v0, b0 = [], [], []
+        for j in range(row_len):
+            vel, broad = rng.uniform(-150, 150), rng.uniform(25, 60)
+            snr = float(np.exp(rng.uniform(np.log(10), np.log(100))))
+            a83 = 0.3 * rng.uniform(0.5, 1.5)
+            amps = [1.0, a83 / 3, a83, 0.15 * rng.uniform(0.5, 1.5), 0.12 * rng.uniform(0.5, 1.5)]
+            s = np.zeros(nz)
+            corr = 1 / np.cos(np.deg2rad(11.96))
+            w = corr * 1e7 / (2 * delta_x * n_steps)
+            for k, line in enumerate(LINES):
+                lam = 1e7 / O.LINE_DICT[line]
+                pos = axis[np.argmin(np.abs(axis - ((vel / 3e5) * lam + lam)))]
+                sig = broad * pos / (3e5 * corr)
+                s += {'gaussian': lambda: O.gaussian_profile(axis, amps[k], pos, sig),
+                      'sinc': lambda: O.sinc_profile(axis, amps[k], pos, w),
+                      'sincgauss': lambda: O.sincgauss_profile(axis, amps[k], pos, sig, w)}[model]()
+            s = s + 0.1 + (1.0 / snr) * rng.normal(0, 1, nz)
+            spectra.append((s * 1e-17).astype(np.float32))
+            v0.append(-vel * 299792 / 3e5 + rng.normal(0, 15))
+            b0.append(abs(broad * np.cos(np.deg2rad(11.96)) * 299792 / 3e5 * (1 + rng.normal(0, 0.15))))
+        rows.append((np.stack(spectra).astype(np.float64), np.array(v0), np.array(b0)))
+    hdr = {'FILTER': 'SN3', 'STEP': delta_x}
+    return rows, axis.astype(np.float32), hdr, n_steps
+
+
+def run_cpu_arm(nz, model, unc, budget_s, steps=1, warmup=0):
+    """spaxels/s of the oracle port of Luci.fit_calc under joblib (loky, all host cores), one task per row."""
+    from joblib import Parallel, delayed
+    cores = os.cpu_count() or 1
+    row_len = 2
+    n_rows = cores                                              # one row per core per step
+    rows, axis32, hdr, n_steps = cpu_sample(nz, model, n_rows, row_len)
+    par = Parallel(n_jobs=cores, backend='loky')
+    # untimed: spin the worker pool up (imports SciPy in every worker)
+    par(delayed(_oracle_row)(0, rows[0][0][:1], axis32, 11.96, hdr, n_steps, model, rows[0][1][:1], rows[0][2][:1], unc)
+        for _ in range(cores))
+    times = []
+    total_steps = max(1, warmup) + max(1, steps) if warmup else max(1, steps)
+    t_start = time.time()
+    for s in range(total_steps):
+        t0 = time.time()
+        par(delayed(_oracle_row)(i, rows[i][0], axis32, 11.96, hdr, n_steps, model, rows[i][1], rows[i][2], unc)
+            for i in range(n_rows))
+        times.append(time.time() - t0)
+        if time.time() - t_start > budget_s and s + 1 >= (warmup + 1 if warmup else 1):
+            break
+    timed = times[warmup:] if warmup and len(times) > warmup else times
+    per_step = float(np.mean(timed))
+    n_sp = n_rows * row_len
+    return dict(value=n_sp / per_step, unit='spaxels/s', cores=cores, kind='port',
+                sample='%d rows x %d spaxels per step (nz=%d, %s, uncertainty=%d), %d timed step(s); oracle/luci_oracle.fit_calc '
+                       'under joblib loky, one task per row' % (n_rows, row_len, nz, model, int(unc), len(timed))), per_step, len(timed)
+
+
+def reference_arm(args):
+    rank = int(os.environ.get('RANK', '0'))
+    if rank != 0:
+        return
+    cb, per_step, k = run_cpu_arm(args.nz, args.model, bool(args.uncertainty), budget_s=240.0, steps=args.steps,
+                                  warmup=min(args.warmup, 1))
+    line = {'impl': 'reference', 'metric': METRIC, 'value': cb['value'], 'unit': 'spaxels/s', 'n_gpus': args.gpus,
+            'steps': k, 'warmup': min(args.warmup, 1), 'ms_per_step': per_step * 1e3, 'higher_is_better': True,
+            'scaling': 'strong', 'vs_baseline': None, 'dtype': 'f64', 'data': 'synthetic',
+            'config': {'workload': 'SN3 5-line %s, tied velocity/broadening + [NII] tie, nz=%d; bounded sample of the '
+                                   '2048x2064 cube' % (args.model, args.nz)},
+            'cpu_baseline': cb,
+            'e2e': {'value': cb['value'], 'unit': 'spaxels/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0}}
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------------- clocks
+class ClockSampler:
+    FIELDS = ('index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,'
+              'clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,'
+              'clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap')
+
+    def __init__(self, gpu_index):
+        self.gpu = gpu_index
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(['nvidia-smi', '-i', str(self.gpu), '--query-gpu=' + self.FIELDS,
+                                          '--format=csv,noheader,nounits', '-lms', '200'], stdout=subprocess.PIPE,
+                                         stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._pump, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _pump(self):
+        for ln in self.proc.stdout:
+            self.lines.append(ln.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {'sm_mhz': None, 'sm_max_mhz': None, 'reasons': ['nvidia-smi unavailable']}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons, power = [], [], set(), []
+        names = ['hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap']
+        for ln in self.lines:
+            parts = [p.strip() for p in ln.split(',')]
+            if len(parts) < 9:
+                continue
+            try:
+                sm.append(float(parts[1])); mx.append(float(parts[2])); power.append(float(parts[3]))
+            except ValueError:
+                continue
+            for nm, val in zip(names, parts[5:9]):
+                if val.lower().startswith('active'):
+                    reasons.add(nm)
+        return {'sm_mhz': float(np.median(sm)) if sm else None, 'sm_max_mhz': float(max(mx)) if mx else None,
+                'power_w_max': float(max(power)) if power else None, 'samples': len(sm), 'reasons': sorted(reasons)}
+
+
+# ------------------------------------------------------------------------------------------------- GPU arm
+def main():
+    args = parse()
+    if args.impl == 'reference':
+        reference_arm(args)
+        return
+    import torch
+    from luci_b200 import dist as ldist
+    from luci_b200 import engine
+    from luci_b200._capi import FitConfig
+    from luci_b200.sim import SyntheticCube
+
+    rank, world, local = ldist.init_process_group()
+    assert torch.cuda.is_available(), 'bench.py needs a GPU (there is no CPU fallback)'
+    dev = torch.device('cuda', local)
+    torch.cuda.set_device(dev)
+    model, unc = args.model, bool(args.uncertainty)
+    x_lo, x_hi = ldist.shard_bounds(args.nx, rank, world)
+    nx_local = x_hi - x_lo
+    sc = SyntheticCube(nx_local, args.ny, lines=LINES, model=model, n_steps=args.nz, x0=x_lo, nx_total=args.nx)
+    cube3 = sc.synthesize(dev, seed=1000 + rank)
+    n_local = nx_local * args.ny
+    cube = cube3.view(n_local, args.nz)
+    v0m, b0m = sc.priors()                                           # (ny, nx) maps
+    t = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(dev)
+    v0, b0 = t(v0m.T.reshape(-1).copy()), t(b0m.T.reshape(-1).copy())   # x-major like the cube rows
+    theta = torch.full((n_local,), float(sc.theta), dtype=torch.float32, device=dev)
+    cfg = FitConfig(model, LINES, [1] * 5, [1] * 5, sc.axis32, 'SN3', sc.delta_x, sc.n_steps, 0,
+                    uncertainty_bool=unc, nii_cons=True)
+    n_total = args.nx * args.ny
+    K = cfg.row_floats
+
+    def step():
+        res = engine.fit_batch(cfg, cube, theta, v0, b0)
+        rows = ldist.gather_rows(res['rows'], dst=0) if world > 1 else res['rows']
+        return res, rows
+
+    def barrier():
+        if world > 1:
+            torch.distributed.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(args.warmup):
+        res, rows = step()
+    barrier()
+    engine.launch_counter['n'] = 0
+    sampler = ClockSampler(local)
+    sampler.start()
+    time.sleep(0.3)
+    evs = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps + 1)]
+    barrier()
+    evs[0].record()
+    for s in range(args.steps):
+        res, rows = step()
+        evs[s + 1].record()
+    barrier()
+    clocks = sampler.stop()
+    total_ms = evs[0].elapsed_time(evs[-1])
+    step_ms = [evs[i].elapsed_time(evs[i + 1]) for i in range(args.steps)]
+    launches = engine.launch_counter['n']
+    total_ms = ldist.max_over_ranks(total_ms, dev)
+    ms_per_step = total_ms / args.steps
+    value = n_total / (ms_per_step * 1e-3)
+
+    # --- kernel time alone (no gather): equals the step at N = 1
+    summ = engine.status_summary(res['status'])
+    sum_evals = ldist.sum_over_ranks(summ['mean_evals'] * summ['n_fitted'], dev)
+    n_fit_total = ldist.sum_over_ranks(summ['n_fitted'], dev)
+    mean_E = sum_evals / max(n_fit_total, 1)
+    nfit = cfg.c.fit_hi - cfg.c.fit_lo
+    L, P_red = 5, 7                                                # 4 free amplitudes + v + beta + continuum
+    W = mean_E * nfit * (L * F_MODEL[model] + P_red * (P_red + 3)) + mean_E * P_red ** 3 / 3.0
+    if unc:
+        W += 24 * L * nfit * (F_MODEL[model] / 2.0) + (3 * L + 1) ** 3
+    kern_ms = float(np.mean(step_ms))
+    if world > 1:                                                   # time the kernel without the gather
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        barrier(); e0.record(); engine.fit_batch(cfg, cube, theta, v0, b0); e1.record(); e1.synchronize()
+        kern_ms = e0.elapsed_time(e1)
+    fp32_peak = engine.peak_probe(dev, 0)
+    mufu_peak = engine.peak_probe(dev, 1)
+    achieved = (W * n_local) / (kern_ms * 1e-3) / 1e12
+    alg_bytes = n_local * (4 * args.nz + 4 * K + 16)
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, 'MEASURED_PEAKS.json')))
+    except Exception:
+        pass
+    hbm_peak = float(peaks.get('hbm_gbs', 6650.0))
+    roofline = {'bound': 'fp32', 'achieved': achieved, 'peak': fp32_peak, 'unit': 'TFLOP/s',
+                'frac': achieved / fp32_peak if fp32_peak else None, 'traffic': None,
+                'peak_source': 'lucifit_peak_probe FFMA chains, measured in this run (nominal 74.4 at 1965 MHz)',
+                'mufu_peak_tops': mufu_peak, 'mean_evals_E': mean_E, 'flop_per_spaxel_W': W,
+                'kernel': 'lf_fit_kernel<%s,L=5,groups=1>' % model, 'kernel_ms': kern_ms,
+                'hbm_gbs_sanity': alg_bytes / (kern_ms * 1e-3) / 1e9, 'hbm_peak_gbs': hbm_peak,
+                'algorithmic_bytes': alg_bytes}
+
+    line = {'metric': METRIC, 'value': value, 'unit': 'spaxels/s', 'n_gpus': world, 'steps': args.steps,
+            'warmup': args.warmup, 'ms_per_step': ms_per_step, 'higher_is_better': True, 'scaling': 'strong',
+            'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
+            'config': {'workload': 'full %dx%d synthetic SN3 cube, nz=%d (N_fit=%d), 5-line %s, tied velocity/broadening '
+                                   '+ [NII] ratio tie, fit_entire_cube%s' % (args.nx, args.ny, args.nz, nfit, model,
+                                                                             ' + uncertainties' if unc else ''),
+                       'sharding': 'contiguous x-slabs, %d rank(s); gather of the (7L+5) float32 rows to rank 0 inside '
+                                   'the step' % world,
+                       'l2': 'inputs (%.1f GB per rank) larger than L2' % (cube.numel() * 4 / 1e9),
+                       'priors': 'truth + N(0,15 km/s), truth*(1+N(0,0.15))', 'snr': 'log-uniform 10..100'},
+            'gpu_launches': launches, 'clocks': clocks, 'roofline': roofline,
+            'fit_status': {k: summ[k] for k in ('n', 'n_converged', 'n_maxiter', 'n_bound', 'mean_evals', 'mean_iters')}}
+
+    # --- reductions (config 5): deep image + SNR map over the same cube, HBM-bound
+    if not args.no_reductions:
+        red = {}
+        flo, fhi, nlo, nhi = 300, 360, 10, 60
+        try:
+            from luci_b200._capi import argmin_abs
+            from luci_b200.constants import snr_windows
+            (f0, f1), (n0, n1) = snr_windows('SN3')
+            flo, fhi = argmin_abs(sc.axis32, f0), argmin_abs(sc.axis32, f1)
+            nlo, nhi = argmin_abs(sc.axis32, n0), argmin_abs(sc.axis32, n1)
+        except Exception:
+            pass
+        for name, fn in (('deep_image', lambda: engine.deep_image(cube)),
+                         ('snr_map_method1', lambda: engine.snr_map(cube, 1, flo, fhi, nlo, nhi)),
+                         ('snr1_plus_deep_fused', lambda: engine.snr_map(cube, 1, flo, fhi, nlo, nhi, with_deep=True))):
+            for _ in range(3):
+                fn()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            reps = 10
+            torch.cuda.synchronize(); e0.record()
+            for _ in range(reps):
+                fn()
+            e1.record(); e1.synchronize()
+            ms = e0.elapsed_time(e1) / reps
+            gbs = cube.numel() * 4 / (ms * 1e-3) / 1e9
+            red[name] = {'ms': ms, 'achieved': gbs, 'peak': hbm_peak, 'unit': 'GB/s', 'frac': gbs / hbm_peak,
+                         'bound': 'hbm'}
+        line['roofline_reductions'] = red
+
+    # --- end to end: cube in pinned host memory, streamed in chunks through the C ABI
+    if not args.no_e2e:
+        line['e2e'] = run_e2e(torch, engine, ldist, cfg, cube, theta, v0, b0, dev, args, world, n_total, K)
+    if rank == 0 and not args.no_cpu_baseline:
+        cb, _, _ = run_cpu_arm(args.nz, model, unc, budget_s=args.cpu_seconds)
+        line['cpu_baseline'] = cb
+    if world > 1:
+        torch.distributed.barrier()
+    if rank == 0:
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        torch.distributed.destroy_process_group()
+
+
+def run_e2e(torch, engine, ldist, cfg, cube, theta, v0, b0, dev, args, world, n_total, K):
+    """Host-resident cube: every step copies the spectra H2D (pinned, chunked, double-buffered against the fit of
+    the previous chunk) and the result rows D2H."""
+    n_local, nz = cube.shape
+    avail_kb = 0
+    try:
+        for ln in open('/proc/meminfo'):
+            if ln.startswith('MemAvailable'):
+                avail_kb = int(ln.split()[1])
+    except Exception:
+        pass
+    need = n_local * nz * 4 * world
+    frac = 1.0
+    if avail_kb and need * 2.5 > avail_kb * 1024:
+        frac = max(0.05, (avail_kb * 1024 / 2.5) / need)
+    n_e2e = int(n_local * frac)
+    host_cube = torch.empty((n_e2e, nz), dtype=torch.float32, pin_memory=True)
+    host_cube.copy_(cube[:n_e2e])
+    host_rows = torch.empty((n_e2e, K), dtype=torch.float32, pin_memory=True)
+    torch.cuda.synchronize()
+    chunk = 1 << 16
+    copy_s, comp_s = torch.cuda.Stream(device=dev), torch.cuda.Stream(device=dev)
+    bufs = [torch.empty((chunk, nz), dtype=torch.float32, device=dev) for _ in range(2)]
+    pbufs = [torch.empty((3, chunk), dtype=torch.float32, device=dev) for _ in range(2)]
+    host_par = torch.empty((3, n_e2e), dtype=torch.float32, pin_memory=True)     # theta, prior velocity, prior broadening
+    host_par[0].copy_(theta[:n_e2e]); host_par[1].copy_(v0[:n_e2e]); host_par[2].copy_(b0[:n_e2e])
+    torch.cuda.synchronize()
+    free_ev = [None, None]
+
+    def e2e_step():
+        for ci, lo in enumerate(range(0, n_e2e, chunk)):
+            hi = min(lo + chunk, n_e2e)
+            b = ci & 1
+            with torch.cuda.stream(copy_s):
+                if free_ev[b] is not None:
+                    copy_s.wait_event(free_ev[b])
+                bufs[b][:hi - lo].copy_(host_cube[lo:hi], non_blocking=True)
+                pbufs[b][:, :hi - lo].copy_(host_par[:, lo:hi], non_blocking=True)
+                ready = torch.cuda.Event()
+                ready.record(copy_s)
+            with torch.cuda.stream(comp_s):
+                comp_s.wait_event(ready)
+                m = hi - lo
+                res = engine.fit_batch(cfg, bufs[b][:m], pbufs[b][0, :m], pbufs[b][1, :m], pbufs[b][2, :m])
+                host_rows[lo:hi].copy_(res['rows'], non_blocking=True)
+                ev = torch.cuda.Event()
+                ev.record(comp_s)
+                free_ev[b] = ev
+        comp_s.synchronize()
+
+    e2e_step()                                                       # warm-up
+    if world > 1:
+        torch.distributed.barrier()
+    torch.cuda.synchronize()
+    reps = max(1, min(args.steps, 3))
+    t0 = time.perf_counter()
+    for _ in range(reps):
+        e2e_step()
+    torch.cuda.synchronize()
+    dt = (time.perf_counter() - t0) / reps
+    dt = ldist.max_over_ranks(dt, dev)
+    n_done = ldist.sum_over_ranks(n_e2e, dev)
+    return {'value': n_done / dt, 'unit': 'spaxels/s', 'h2d_bytes_per_step': int(n_done * (nz + 3) * 4),
+            'd2h_bytes_per_step': int(n_done * K * 4), 'ms_per_step': dt * 1e3,
+            'note': 'cube in pinned host memory, %d-spaxel chunks double-buffered through lucifit_fit_batch; '
+                    'fraction of the cube streamed per step: %.2f (host RAM bound)' % (chunk, frac)}
+
+
+if __name__ == '__main__':
+    main()

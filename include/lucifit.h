@@ -124,6 +124,11 @@ int lucifit_sim_cube(const lucifit_config* cfg, int64_t n_spaxel, const float* a
                      float flux_scale, float* cube /*[n][nz]*/, void* workspace, size_t workspace_bytes,
                      void* stream);
 
+/* Roofline probe: `blocks` CTAs of 256 threads each run `iters` iterations of 8 independent FFMA (mode 0) or
+ * MUFU.EX2 (mode 1) chains; out holds blocks*256 floats.  Work = blocks*256*iters*8 FMA (x2 flop) or MUFU ops.
+ * MEASURED_PEAKS.json has no FP32 / SFU figure; bench.py times this to get the denominators of the fit kernel. */
+int lucifit_peak_probe(int mode, int iters, int blocks, float* out, void* stream);
+
 const char* lucifit_last_error(void);
 const char* lucifit_version(void);
 

@@ -40,7 +40,8 @@ class lucifit_config(C.Structure):
 
 
 EXPORTS = ['lucifit_row_floats', 'lucifit_workspace_bytes', 'lucifit_fit_batch', 'lucifit_deep_image',
-           'lucifit_snr_map', 'lucifit_bin_cube', 'lucifit_sim_cube', 'lucifit_last_error', 'lucifit_version']
+           'lucifit_snr_map', 'lucifit_bin_cube', 'lucifit_sim_cube', 'lucifit_peak_probe', 'lucifit_last_error',
+           'lucifit_version']
 
 _lib = None
 
@@ -63,6 +64,8 @@ def declare(lib):
     lib.lucifit_bin_cube.restype = C.c_int
     lib.lucifit_sim_cube.argtypes = [cfgp, i64, vp, vp, vp, vp, vp, vp, C.c_float, C.c_float, vp, vp, sz, vp]
     lib.lucifit_sim_cube.restype = C.c_int
+    lib.lucifit_peak_probe.argtypes = [C.c_int, C.c_int, C.c_int, vp, vp]
+    lib.lucifit_peak_probe.restype = C.c_int
     lib.lucifit_last_error.argtypes = []
     lib.lucifit_last_error.restype = C.c_char_p
     lib.lucifit_version.argtypes = []

@@ -41,6 +41,7 @@ extern "C" cudaError_t lf_run_reduce(int mode, const float* cube, long long n_sp
 extern "C" cudaError_t lf_run_bin(const float* cube, int ny, int nz, int b, int x0, int y0, int nxb, int nyb,
                                   float* out, int sm_count, cudaStream_t stream);
 extern "C" cudaError_t lf_run_sim(const LfSimArgs* a, int sm_count, cudaStream_t stream);
+extern "C" cudaError_t lf_run_peak(int mode, int iters, int blocks, float* out, cudaStream_t stream);
 
 static int sm_count_of_current_device(int* out)
 {
@@ -185,6 +186,14 @@ int lucifit_sim_cube(const lucifit_config* cfg, int64_t n_spaxel, const float* a
     int sm = 0; int rc = sm_count_of_current_device(&sm); if (rc) return rc;
     e = lf_run_sim(&a, sm, st);
     if (e != cudaSuccess) return cuda_fail(e, "launch lf_sim_kernel");
+    return 0;
+}
+
+int lucifit_peak_probe(int mode, int iters, int blocks, float* out, void* stream)
+{
+    if ((mode != 0 && mode != 1) || iters < 1 || blocks < 1 || !out) return fail(LUCIFIT_EINVAL, "bad argument");
+    cudaError_t e = lf_run_peak(mode, iters, blocks, out, (cudaStream_t)stream);
+    if (e != cudaSuccess) return cuda_fail(e, "launch lf_peak_kernel");
     return 0;
 }
 

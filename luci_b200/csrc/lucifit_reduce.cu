@@ -265,6 +265,43 @@ __global__ void __launch_bounds__(RED_WARPS * 32) lf_sim_kernel(const __grid_con
     }
 }
 
+// Peak probes (roofline denominators that MEASURED_PEAKS.json does not carry): dependent-free FFMA chains and
+// MUFU.EX2 chains, 8 independent accumulators per thread.
+template <int MODE>
+__global__ void __launch_bounds__(256) lf_peak_kernel(int iters, float* out)
+{
+    float a0 = threadIdx.x * 1e-3f, a1 = a0 + 1.f, a2 = a0 + 2.f, a3 = a0 + 3.f, a4 = a0 + 4.f, a5 = a0 + 5.f, a6 = a0 + 6.f, a7 = a0 + 7.f;
+    const float m = 0.999f, c = 1e-3f;
+    for (int i = 0; i < iters; ++i) {
+        if (MODE == 0) {
+            a0 = fmaf(a0, m, c); a1 = fmaf(a1, m, c); a2 = fmaf(a2, m, c); a3 = fmaf(a3, m, c);
+            a4 = fmaf(a4, m, c); a5 = fmaf(a5, m, c); a6 = fmaf(a6, m, c); a7 = fmaf(a7, m, c);
+        }
+    }
+    out[blockIdx.x * blockDim.x + threadIdx.x] = a0 + a1 + a2 + a3 + a4 + a5 + a6 + a7;
+}
+
+template <>
+__global__ void __launch_bounds__(256) lf_peak_kernel<1>(int iters, float* out)
+{
+    float a0 = threadIdx.x * 1e-3f, a1 = a0 + .1f, a2 = a0 + .2f, a3 = a0 + .3f, a4 = a0 + .4f, a5 = a0 + .5f, a6 = a0 + .6f, a7 = a0 + .7f;
+    for (int i = 0; i < iters; ++i) {
+        asm volatile("ex2.approx.ftz.f32 %0, %0;" : "+f"(a0)); asm volatile("ex2.approx.ftz.f32 %0, %0;" : "+f"(a1));
+        asm volatile("ex2.approx.ftz.f32 %0, %0;" : "+f"(a2)); asm volatile("ex2.approx.ftz.f32 %0, %0;" : "+f"(a3));
+        asm volatile("ex2.approx.ftz.f32 %0, %0;" : "+f"(a4)); asm volatile("ex2.approx.ftz.f32 %0, %0;" : "+f"(a5));
+        asm volatile("ex2.approx.ftz.f32 %0, %0;" : "+f"(a6)); asm volatile("ex2.approx.ftz.f32 %0, %0;" : "+f"(a7));
+        a0 -= 1.0f; a1 -= 1.0f; a2 -= 1.0f; a3 -= 1.0f; a4 -= 1.0f; a5 -= 1.0f; a6 -= 1.0f; a7 -= 1.0f;
+    }
+    out[blockIdx.x * blockDim.x + threadIdx.x] = a0 + a1 + a2 + a3 + a4 + a5 + a6 + a7;
+}
+
+extern "C" cudaError_t lf_run_peak(int mode, int iters, int blocks, float* out, cudaStream_t stream)
+{
+    if (mode == 0) lf_peak_kernel<0><<<blocks, 256, 0, stream>>>(iters, out);
+    else lf_peak_kernel<1><<<blocks, 256, 0, stream>>>(iters, out);
+    return cudaGetLastError();
+}
+
 // ------------------------------------------------------------------------------------------- host launchers
 extern "C" cudaError_t lf_run_reduce(int mode, const float* cube, long long n_spaxel, int nz, long long n_live,
                                      int flo, int fhi, int nlo, int nhi, float* snr, float* deep, int sm_count,

@@ -196,3 +196,23 @@ def status_summary(status):
 def _capi_flags():
     return {'CONVERGED': 1 << 16, 'MAXITER': 1 << 17, 'BOUND': 1 << 18, 'SINGULAR': 1 << 19, 'NAN_INPUT': 1 << 20,
             'MASKED': 1 << 21, 'BAD_NORM': 1 << 22}
+
+
+def peak_probe(device, mode, iters=4096, blocks_per_sm=8):
+    """Measured FP32-FMA (mode 0, TFLOP/s) or MUFU.EX2 (mode 1, Tops/s) throughput of this GPU."""
+    lib = _capi.lib()
+    sms = torch.cuda.get_device_properties(device).multi_processor_count
+    blocks = sms * blocks_per_sm
+    out = torch.empty(blocks * 256, dtype=torch.float32, device=device)
+    best = 0.0
+    with torch.cuda.device(device):
+        for rep in range(4):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            check(lib.lucifit_peak_probe(mode, iters, blocks, _ptr(out), _stream()))
+            e1.record()
+            e1.synchronize()
+            ops = blocks * 256 * iters * 8 * (2 if mode == 0 else 1)
+            if rep > 0:
+                best = max(best, ops / (e0.elapsed_time(e1) * 1e-3) / 1e12)
+    return best

@@ -111,9 +111,10 @@ def test_cuda_vs_oracle_on_device_generated_cube():
             dchi = (q['chi2'][i] - o['chi2']) / o['chi2']
             bad += not (dv <= TOL_VEL_KMS and db <= TOL_REL and df <= TOL_REL and dchi <= TOL_CHI2)
     assert bad == 0
-    # the synthetic truth is recovered within the noise (sanity of generator + fitter conventions)
+    # the synthetic truth is recovered (sanity of generator + fitter sign conventions).  LuciSim snaps every line
+    # to the nearest channel (LuciSim.py:185-187), i.e. by up to half a channel = 24 km/s at R = 5000.
     truth_v = sc.vel_fit_truth.reshape(n)
-    assert np.median(np.abs(q['velocities'][:, 0] - truth_v)) < 3.0
+    assert np.median(np.abs(q['velocities'][:, 0] - truth_v)) < 25.0
 
 
 def test_index_list_background_and_flags():
@@ -173,4 +174,4 @@ def test_size_independent_properties_on_a_large_batch():
     assert s['n_converged'] >= 0.999 * s['n'] and s['mean_evals'] < 12
     truth = t(sc.vel_fit_truth.reshape(-1))
     err = (a['rows'][:, 15] - truth).abs()
-    assert float(err.median()) < 2.0
+    assert float(err.median()) < 25.0                 # LuciSim's channel snapping: up to 24 km/s

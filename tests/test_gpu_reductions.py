@@ -49,7 +49,7 @@ def test_bin_cube_matches_reference():
     g = load_golden('reductions_sn3')
     b, x0, x1, y0, y1 = [int(v) for v in g['bin_args']]
     out = engine.bin_cube(_t(g['cube']), b, x0, x1, y0, y1).cpu().numpy()
-    np.testing.assert_allclose(out, g['ref_binned'], rtol=1e-6, atol=1e-26)
+    np.testing.assert_allclose(out, g['ref_binned'], rtol=1e-6, atol=2e-24)   # FP32 sums of ~4e-18 terms
     odd = engine.bin_cube(_t(g['cube']), 3, 0, 23, 0, 14).cpu().numpy()     # ragged: 23/3 -> 7, 14/3 -> 4
     assert odd.shape == (7, 4, g['cube'].shape[2])
 
@@ -92,7 +92,8 @@ def test_large_reduction_is_size_independent():
     torch.testing.assert_close(deep, cube.sum(dim=1), rtol=2e-6, atol=0)
     snr1 = engine.snr_map(cube, 1, 300, 360, 10, 60)
     perm = torch.randperm(cube.shape[0], device=dev)
-    torch.testing.assert_close(engine.snr_map(cube[perm].contiguous(), 1, 300, 360, 10, 60), snr1[perm], rtol=0, atol=0)
+    # row alignment (hence the float4 peel and the summation order) changes with the position in the cube
+    torch.testing.assert_close(engine.snr_map(cube[perm].contiguous(), 1, 300, 360, 10, 60), snr1[perm], rtol=3e-6, atol=0)
     mx, mean = cube.max(dim=1).values, cube.mean(dim=1)
     std = cube[:, 10:60].double().std(dim=1, unbiased=False).float()
     ref = (mx - mean) / std.sqrt() / cube.abs().mean(dim=1).sqrt()

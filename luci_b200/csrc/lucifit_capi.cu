@@ -65,14 +65,19 @@ const char* lucifit_version(void) { return "lucifit 0.1.0 (sm_100a)"; }
 
 int lucifit_row_floats(int n_lines) { return 7 * n_lines + 5; }
 
+static size_t lf_slice_of(int64_t n_spaxel)
+{
+    return (size_t)(n_spaxel < LF_SLICE_SPAXELS ? (n_spaxel > 0 ? n_spaxel : 1) : LF_SLICE_SPAXELS);
+}
+
 int lucifit_workspace_bytes(const lucifit_config* cfg, int64_t n_spaxel, size_t* bytes)
 {
-    (void)n_spaxel;
     if (!bytes) return fail(LUCIFIT_EINVAL, "bytes is NULL");
     LfPlan pl;
     std::string err = lf_make_plan(cfg, pl);
     if (!err.empty()) return fail(LUCIFIT_EINVAL, err);
-    *bytes = pl.table_bytes;
+    // constant tables + the state records of one slice (the batch is processed LF_SLICE_SPAXELS at a time)
+    *bytes = pl.table_bytes + lf_align(lf_slice_of(n_spaxel) * pl.state_bytes + 16, 256);
     return 0;
 }
 
@@ -87,7 +92,9 @@ int lucifit_fit_batch(const lucifit_config* cfg, int64_t n_spaxel, const float* 
     if (n_spaxel < 0) return fail(LUCIFIT_EINVAL, "n_spaxel < 0");
     if (n_spaxel == 0) return 0;
     if (!cube || !theta_deg || !out_rows || !out_status) return fail(LUCIFIT_EINVAL, "cube, theta_deg, out_rows and out_status are required");
-    if (!workspace || workspace_bytes < pl.table_bytes) return fail(LUCIFIT_EWORKSPACE, "workspace too small: call lucifit_workspace_bytes");
+    const size_t slice = lf_slice_of(n_spaxel);
+    const size_t need = pl.table_bytes + lf_align(slice * pl.state_bytes + 16, 256);
+    if (!workspace || workspace_bytes < need) return fail(LUCIFIT_EWORKSPACE, "workspace too small: call lucifit_workspace_bytes");
     if (((uintptr_t)workspace & 255) != 0) return fail(LUCIFIT_EINVAL, "workspace must be 256-byte aligned");
     lf_launch_fn fn = find_launcher(cfg->model, pl.L, pl.nv_t);
     if (!fn) return fail(LUCIFIT_EINVAL, "this (n_lines, tie pattern) combination is not instantiated in this build");
@@ -106,22 +113,36 @@ int lucifit_fit_batch(const lucifit_config* cfg, int64_t n_spaxel, const float* 
     // the source has been staged, so `pl` may be destroyed when this function returns.
     LfLaunch a;
     a.cfg = pl.dev;
+    a.ly = pl.ly;
     a.cfg.axis = (const double*)(ws + pl.off_axis);
     a.cfg.xo = (const float*)(ws + pl.off_xo);
     a.cfg.trans = pl.trans.empty() ? nullptr : (const float*)(ws + pl.off_trans);
     a.cfg.bkg = bkg;
-    a.n = n_spaxel; a.cube = cube; a.index = (const long long*)spaxel_index; a.theta = theta_deg;
-    a.vel0 = vel0; a.broad0 = broad0; a.out_rows = out_rows; a.out_sol = out_fit_sol; a.out_unc = out_unc;
-    a.status = out_status;
-    a.off_u = (int)pl.off_u; a.off_v = (int)pl.off_v; a.per_warp = (int)pl.per_warp_bytes; a.cont_cap = (int)pl.cont_cap;
+    a.cube = cube;
     a.xo_bytes = (int)lf_align(sizeof(float) * pl.nfit, 16);
     a.stream = st;
+    a.state = (float*)(ws + pl.table_bytes);
+    a.unc_ws = pl.dev.uncertainty ? (double*)(ws + pl.table_bytes + lf_align(slice * sizeof(float) * pl.dev.state_floats, 16)) : nullptr;
     int rc = sm_count_of_current_device(&a.sm_count);
     if (rc) return rc;
-    size_t smem = (size_t)a.xo_bytes + (size_t)LF_WARPS_PER_BLOCK * a.per_warp;
-    if (smem > 227 * 1024) return fail(LUCIFIT_EINVAL, "spectrum too long for the shared-memory layout (nz * 8 warps > 227 KB)");
-    e = fn(a);
-    if (e != cudaSuccess) return cuda_fail(e, "launch lf_fit_kernel");
+    const size_t smem_max = (size_t)a.xo_bytes + (size_t)LF_PREP_WARPS * pl.ly.prep_bytes;
+    if (smem_max > 200 * 1024) return fail(LUCIFIT_EINVAL, "spectrum too long for the shared-memory layout (nz * 8 warps > 200 KB)");
+    const int K = 7 * pl.L + 5, PF = 3 * pl.L + 1;
+    for (int64_t s0 = 0; s0 < n_spaxel; s0 += (int64_t)slice) {
+        const int64_t ns = n_spaxel - s0 < (int64_t)slice ? n_spaxel - s0 : (int64_t)slice;
+        a.n = ns;
+        a.index = spaxel_index ? (const long long*)spaxel_index + s0 : nullptr;
+        a.index_base = s0;
+        a.theta = theta_deg + s0;
+        a.vel0 = vel0 ? vel0 + s0 : nullptr;
+        a.broad0 = broad0 ? broad0 + s0 : nullptr;
+        a.out_rows = out_rows + s0 * K;
+        a.out_sol = out_fit_sol ? out_fit_sol + s0 * PF : nullptr;
+        a.out_unc = out_unc ? out_unc + s0 * PF : nullptr;
+        a.status = out_status + s0;
+        e = fn(a);
+        if (e != cudaSuccess) return cuda_fail(e, "launch fit stage kernels");
+    }
     return 0;
 }
 

@@ -1,32 +1,37 @@
-// lucifit_core.cuh -- per-spaxel pipeline executed by ONE WARP: prep -> Levenberg-Marquardt -> derived outputs.
+// lucifit_core.cuh -- per-spaxel pipeline of the fit path, executed by ONE WARP per spaxel, in four stages that the
+// device runs as four small kernels (each hot loop has to fit the 32 KB instruction cache of an SM):
 //
-// Replaces, for one spectrum, LUCI.LuciFit.Fit.__init__/fit (LUCI/LuciFit.py:49-173, 761-835):
-//   normalise + window      LuciFit.py:110-112, 225-280        -> lf_prep
-//   noise                   LuciFit.py:282-331                 -> lf_prep
-//   continuum estimate      LuciFit.py:432-486                 -> lf_cont_estimate (MAD sigma-clip + median)
-//   line estimates          LuciFit.py:382-430                 -> lf_prep
-//   SLSQP on the nll        LuciFit.py:635-687                 -> lf_lm  (tie-eliminated, box-projected LM)
-//   chi2 / flux / velocity  LuciFit.py:799-834, 1050-1069,
-//                           LUCI/LuciFitParameters.py:14-185   -> lf_outputs
+//   stage        replaces (LUCI/LuciFit.py unless noted)                                         function
+//   prep         Fit.__init__ :49-173 (normalise :110-112, window :225-280, noise :282-331),       lf_stage_prep
+//                cont_estimate :432-486, line_vals_estimate :382-430, initial vector :663-672
+//   lm           calculate_params :635-687 (SLSQP on the nll with the constraints :523-633)        lf_stage_lm
+//   unc          uncertainties :713-722 + LuciUtility.hessianComp :409-434                          lf_stage_unc
+//   out          fit() tail :799-834, calc_chisquare :1050-1069, LuciFitParameters.py:14-185        lf_stage_out
 //
-// The tie constraints of the reference (LuciFit.py:523-598) are eliminated analytically: the unknowns are
+// Between stages a spaxel is a small state record in the caller's workspace (LF_SO_* offsets below).
+//
+// The tie constraints of the reference (:523-598) are eliminated analytically: the unknowns are
 //   theta = [A_0..A_{L-1} | v_0..v_{NV-1} | beta_0..beta_{NS-1} | continuum]
-// with line centre p_k = 1e7/(lambda_k (1 + v_g/c)) and sigma_k = p_k beta_h / c, so equal velocity /
-// equal broadening inside a group hold identically, and (if enabled) A_6548 = A_6583 G(sigma_6583)/(3 G(sigma_6548)).
+// with line centre p_k = 1e7/(lambda_k (1 + v_g/c)) and sigma_k = p_k beta_h / c, so equal velocity / equal
+// broadening inside a group hold identically, and (if enabled) A_6548 = A_6583 G(sigma_6583)/(3 G(sigma_6548)).
 // Line centres are carried as offsets from x_ref = axis[fit_lo] so FP32 never subtracts two 1.5e4-sized numbers.
 //
-// Lane model: LANES = 32 on the device (one warp per spaxel, sample n owned by lane n % 32), LANES = 1 in the
-// CPU test harness (tests/hostemu) which compiles this very file with g++.
+// Lane model: LANES = 32 on the device (sample n of the fit window is owned by lane n % 32), LANES = 1 in the CPU
+// test harness (tests/hostemu), which compiles this very file with g++.
+//
+// Code-size rules of this file: loops over lines are ROLLED (`#pragma unroll 1`) with the per-line constants in
+// per-warp shared memory, so there is one copy of the profile code per stage; only the small fixed-size
+// normal-equation arrays are unrolled into registers.
 #pragma once
 #include <stdint.h>
 #include "lucifit_math.cuh"
 
 #if defined(__CUDACC__)
 #define LF_CORE __device__ __forceinline__
-#define LF_CORE_NOINLINE __device__ __noinline__
+#define LF_ALIGN16 __align__(16)
 #else
 #define LF_CORE inline
-#define LF_CORE_NOINLINE
+#define LF_ALIGN16 alignas(16)
 #endif
 
 #define LF_MAX_LINES 8
@@ -38,6 +43,10 @@ enum {
     LF_ST_CONVERGED = 1 << 16, LF_ST_MAXITER = 1 << 17, LF_ST_BOUND = 1 << 18, LF_ST_SINGULAR = 1 << 19,
     LF_ST_NAN_INPUT = 1 << 20, LF_ST_MASKED = 1 << 21, LF_ST_BAD_NORM = 1 << 22, LF_ST_NAN_RESULT = 1 << 23
 };
+#define LF_ST_BADMASK (LF_ST_NAN_INPUT | LF_ST_MASKED | LF_ST_BAD_NORM)
+
+// per-spaxel state record (float words; the record starts 8-byte aligned and its stride is even)
+enum { LF_SO_NOISE = 0, LF_SO_SCALE = 2, LF_SO_CORR = 4, LF_SO_SINCW = 6, LF_SO_INVW = 8, LF_SO_STATUS = 9, LF_SO_TH = 10 };
 
 struct LfCfg {                     // device-side constants of one lucifit_fit_batch call
     int model, L, nv, ns;
@@ -46,6 +55,7 @@ struct LfCfg {                     // device-side constants of one lucifit_fit_b
     int i48, i83;                  // [NII] tie: indices of NII6548 / NII6583, -1 when off
     int sigbox_group;              // sigma group of the LAST line: 0 <= sigma <= 10 cm^-1 (LuciFit.py:539-541)
     int uncertainty, ml_scale, max_iter, n_out;
+    int state_floats;              // stride of the state record
     float ftol;
     float p0[LF_MAX_LINES];        // 1e7/lambda_k                     [cm^-1]
     float p0_off[LF_MAX_LINES];    // 1e7/lambda_k - x_ref             [cm^-1]
@@ -53,7 +63,7 @@ struct LfCfg {                     // device-side constants of one lucifit_fit_b
     double line_nm[LF_MAX_LINES];
     double x_ref;
     double axis_k;                 // 1e7/(2 STEP (n_steps - zpd)); axis_step = sinc_width = corr * axis_k
-    const double* axis;            // [nz]  float32-rounded axis values, widened
+    const double* axis;            // [nz]  float32-rounded axis values, widened; strictly increasing
     const float* xo;               // [n_fit] axis[fit_lo + n] - x_ref (kernels stage it into shared memory)
     const float* trans;            // [nz] or null
     const float* bkg;              // [nz] or null (already multiplied by binning^2)
@@ -71,6 +81,7 @@ template <> struct LfWarp<1> {
     int sum(int v) const { return v; }
     bool all(bool p) const { return p; }
     bool any(bool p) const { return p; }
+    float xchg(float v, int) const { return v; }
     void argmin(double& v, int& i) const {}
     void sync() const {}
 };
@@ -97,6 +108,7 @@ template <> struct LfWarp<32> {
     }
     __device__ bool all(bool p) const { return __all_sync(0xffffffffu, p); }
     __device__ bool any(bool p) const { return __any_sync(0xffffffffu, p); }
+    __device__ float xchg(float v, int o) const { return __shfl_xor_sync(0xffffffffu, v, o); }
     __device__ void argmin(double& v, int& i) const {   // smallest v, ties -> smallest index (np.argmin)
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) {
@@ -115,85 +127,83 @@ template <int P> struct LfSym {            // packed upper triangle, row-major
     enum { N = P * (P + 1) / 2 };
 };
 
-// index of the axis sample nearest to `pos` (first one on ties, like np.argmin(|axis - pos|)), all lanes.
-template <int LANES>
-LF_CORE int lf_argmin_axis(const LfWarp<LANES>& w, const double* axis, int nz, double pos)
+template <int MODEL, int L, int NV, int NS> struct LfDims {
+    enum { P = L + NV + NS + 1, IV = L, IS = L + NV, IC = L + NV + NS, NH = P * (P + 1) / 2, NA = NH + P };
+};
+
+// Index of the axis sample nearest to `pos` (first one on ties, like np.argmin(|axis - pos|)) for a strictly
+// increasing axis: binary search for the first sample >= pos, then the closer of it and its left neighbour.
+LF_CORE int lf_nearest_axis(const double* axis, int nz, double pos)
 {
-    double best = 1e300;
-    int bi = 0x7fffffff;
-    for (int i = w.lane; i < nz; i += LANES) {
-        double d = fabs(axis[i] - pos);
-        if (d < best) { best = d; bi = i; }
+    int lo = 0, hi = nz;                                // first index with axis[i] >= pos, in [0, nz]
+    while (lo < hi) {
+        int mid = (lo + hi) >> 1;
+        if (axis[mid] < pos) lo = mid + 1; else hi = mid;
     }
-    w.argmin(best, bi);
-    return bi;
+    if (lo == 0) return 0;
+    if (lo == nz) return nz - 1;
+    return (fabs(axis[lo - 1] - pos) <= fabs(axis[lo] - pos)) ? lo - 1 : lo;
 }
 
-// k-th smallest (0-based) of the alive entries of v[0..n), by rank counting; all lanes get the result.
+// In-place ascending bitonic sort of v[0..npad) (npad a power of two; pad with +inf), all lanes cooperate.
 template <int LANES>
-LF_CORE double lf_kth(const LfWarp<LANES>& w, const double* v, const unsigned char* alive, int n, int k)
+LF_CORE void lf_sort(const LfWarp<LANES>& w, double* v, int npad)
 {
-    double found = 0.0;
-    int hit = 0;
-    for (int i = w.lane; i < n; i += LANES) {
-        if (!alive[i]) continue;
-        double vi = v[i];
-        int rank = 0;
-        for (int j = 0; j < n; ++j) {
-            if (!alive[j]) continue;
-            double vj = v[j];
-            rank += (vj < vi) || (vj == vi && j < i);
+    for (int k = 2; k <= npad; k <<= 1) {
+        for (int j = k >> 1; j > 0; j >>= 1) {
+            for (int t = w.lane; t < (npad >> 1); t += LANES) {
+                int i = 2 * j * (t / j) + (t % j);
+                int l = i + j;
+                bool up = (i & k) == 0;
+                double a = v[i], b = v[l];
+                if ((a > b) == up) { v[i] = b; v[l] = a; }
+            }
+            w.sync();
         }
-        if (rank == k) { found = vi; hit = 1; }
     }
-    // exactly one lane hits
-    double r = w.sum(hit ? found : 0.0);
-    return r;
 }
 
-template <int LANES>
-LF_CORE double lf_median(const LfWarp<LANES>& w, const double* v, const unsigned char* alive, int n, int m)
+LF_CORE double lf_sorted_median(const double* v, int a, int m)   // median of the sorted range v[a .. a+m)
 {
     if (m <= 0) return 0.0;
-    if (m & 1) return lf_kth(w, v, alive, n, m / 2);
-    return 0.5 * (lf_kth(w, v, alive, n, m / 2 - 1) + lf_kth(w, v, alive, n, m / 2));
+    if (m & 1) return v[a + m / 2];
+    return 0.5 * (v[a + m / 2 - 1] + v[a + m / 2]);
 }
 
-// Continuum guess: median of the window after <=3 rounds of 1-sigma clipping about the median with
-// mad_std as the spread (LuciFit.py:474-486; astropy sigma_clip semantics restated in oracle/astro_stats.py).
-// `vals`/`dev`/`alive` are per-warp scratch of LF_MAX_CONT_WIN entries.
+// Continuum guess: median of the window after <=3 rounds of 1-sigma clipping about the median with mad_std as the
+// spread (LuciFit.py:474-486; astropy sigma_clip semantics restated in oracle/astro_stats.py).  The window is
+// sorted once; a clip keeps the values inside an interval, so the survivors are always a contiguous range of it.
+// `sv` / `dv` are per-warp scratch of `npad` doubles each.
 template <int LANES>
 LF_CORE double lf_cont_estimate(const LfWarp<LANES>& w, const float* spec, int lo, int hi, double sigma_level,
-                                double* vals, double* dev, unsigned char* alive)
+                                double* sv, double* dv, int npad)
 {
     int n = hi - lo;
     if (n > LF_MAX_CONT_WIN) n = LF_MAX_CONT_WIN;
     if (n <= 0) return 0.0;
-    for (int i = w.lane; i < n; i += LANES) { vals[i] = (double)spec[lo + i]; alive[i] = 1; }
+    for (int i = w.lane; i < npad; i += LANES) sv[i] = i < n ? (double)spec[lo + i] : INFINITY;
     w.sync();
-    int m = n;
+    lf_sort(w, sv, npad);
+    int a = 0, m = n;
     for (int it = 0; it < 3 && m > 0; ++it) {
-        double med = lf_median(w, vals, alive, n, m);
-        for (int i = w.lane; i < n; i += LANES) dev[i] = fabs(vals[i] - med);
+        double med = lf_sorted_median(sv, a, m);
+        int mpad = 2;
+        while (mpad < m) mpad <<= 1;
+        for (int i = w.lane; i < mpad; i += LANES) dv[i] = i < m ? fabs(sv[a + i] - med) : INFINITY;
         w.sync();
-        double mad = 1.482602218505602 * lf_median(w, dev, alive, n, m);
+        lf_sort(w, dv, mpad);
+        double mad = 1.482602218505602 * lf_sorted_median(dv, 0, m);
         double lo_b = med - sigma_level * mad, hi_b = med + sigma_level * mad;
-        int removed = 0;
-        for (int i = w.lane; i < n; i += LANES)
-            if (alive[i] && !(vals[i] >= lo_b && vals[i] <= hi_b)) { alive[i] = 0; ++removed; }
-        removed = w.sum(removed);
+        int below = 0, above = 0;
+        for (int i = w.lane; i < m; i += LANES) { double x = sv[a + i]; below += !(x >= lo_b); above += !(x <= hi_b); }
+        below = w.sum(below); above = w.sum(above);
         w.sync();
-        m -= removed;
-        if (removed == 0) break;
+        if (below + above == 0) break;
+        a += below; m -= below + above;
     }
-    if (m < 1) {                                   // LuciFit.py:481-482: fall back to the unclipped window
-        for (int i = w.lane; i < n; i += LANES) alive[i] = 1;
-        w.sync();
-        m = n;
-    }
-    return lf_median(w, vals, alive, n, m);
+    if (m < 1) { a = 0; m = n; }                       // LuciFit.py:481-482: fall back to the unclipped window
+    return lf_sorted_median(sv, a, m);
 }
-
 
 // Area ratio of the [NII] doublet tie, A_6548 = R A_6583 (LuciFit.py:584-595): gaussian & sinc
 // R = sigma_83/(3 sigma_48) = p_83 beta_83/(3 p_48 beta_48) (beta cancels inside one sigma group);
@@ -206,222 +216,260 @@ LF_HD float lf_tie_ratio(int model, float p83, float b83, float s83, float p48, 
     return (p83 * b83) / (3.0f * p48 * fmaxf(b48, 1e-6f));
 }
 
-// --------------------------------------------------------------------------------------------- per spaxel
-struct LfPrep {
-    float smax;        // max of the (background-subtracted) spectrum
-    float wmax;        // max inside the fit window
-    float inv_wmax;
-    double noise;      // std of the normalised spectrum in the noise window
-    double cont0;      // continuum guess (normalised by smax)
-    double scale;      // spectrum_scale (LuciFit.py:374-375 / :782)
-    double corr;       // 1/cos(theta)
-    double sinc_w;     // == axis_step
-    int bad;           // status flags raised during prep
+// ------------------------------------------------------------------------------------- per-warp work areas
+// One model evaluation's per-line working set, kept in per-warp shared memory (80 bytes = 5 x 16-byte loads).
+struct LF_ALIGN16 LfLineX {
+    LfLine ln;
+    float aeff;        // amplitude in effect (tied [NII]6548: R * A_6583)
+    float dpdv;        // d centre / d v_g
+    float dsdv;        // d sigma  / d v_g
+    float dsdb;        // d sigma  / d beta_h
+    float ck, sk;      // cos, sin of the line's phase pi (centre - x_ref)/w
+    int vg, sg;        // group indices
+    float p, beta;
+};
+struct LfTieX {        // warp-uniform constants of the [NII] tie for one evaluation
+    float R;
+    float cRv[LF_MAX_LINES];
+    float cRb[LF_MAX_LINES];
+    int active;
 };
 
-template <int MODEL, int L, int NV, int NS> struct LfDims {
-    enum { P = L + NV + NS + 1, IV = L, IS = L + NV, IC = L + NV + NS, NH = P * (P + 1) / 2 };
+struct LfWork {        // pointers into the per-warp scratch (which of them are valid depends on the stage)
+    float* spec;       // prep: [nz] background-subtracted spectrum
+    double* sortv;     // prep: [npad] sorted continuum window
+    double* sortd;     // prep: [npad] deviations
+    int npad;
+    float* yw;         // lm/unc/out: [nfit] data of the fit window (normalised as the stage needs)
+    float* sw;         // [nfit] sin(pi xo/w)
+    float* cw;         // [nfit] cos(pi xo/w)
+    LfLineX* lines;    // [L]  (unc: [13 L])
+    LfTieX* tie;
+    float* gt;         // [(L+1)][LANES] unit profiles of the current chunk (unc: [13][LANES])
+    float* hb;         // lm: [2][NA] normal equations (accepted / trial)
+    float* thb;        // lm: [4][P]  theta, trial theta, lower, upper
+    double* apd;       // unc/out: [3][L] amplitude, centre, sigma of every line (float64)
+    float* tile;       // unc: [LANES][(3L+1)|1]
+    double* hess;      // unc: [PF*PF + 2 PF]
 };
 
-// Reads the spaxel's spectrum into `spec` (per-warp, nz floats) and computes everything Fit.__init__ does.
+// Fills sw/cw (phase table) for the window: the angle of sample n is pi xo[n]/w.
 template <int LANES>
-LF_CORE void lf_prep(const LfCfg& cfg, const LfWarp<LANES>& w, const float* gspec, float theta_deg,
-                     float* spec, double* sc_vals, double* sc_dev, unsigned char* sc_alive, LfPrep& pr)
+LF_CORE void lf_phase_table(const LfWarp<LANES>& w, const float* xo, int nfit, double inv_w, float* sw, float* cw)
 {
-    const int nz = cfg.nz;
-    float smax = -INFINITY, wmax = -INFINITY, tmax = -INFINITY;
-    int nan_ct = 0;
-    for (int i = w.lane; i < nz; i += LANES) {
-        float s = gspec[i];
-        if (cfg.bkg) s -= cfg.bkg[i];
-        spec[i] = s;
-        nan_ct += (s != s);
-        smax = fmaxf(smax, s);
-        if (i >= cfg.fit_lo && i < cfg.fit_hi) wmax = fmaxf(wmax, s);
-        float st = s;
-        if (cfg.trans) { float t = cfg.trans[i]; if (t > 0.5f) st = s / t; }
-        tmax = fmaxf(tmax, st);
+    for (int n = w.lane; n < nfit; n += LANES) {
+        float s, c;
+        lf_phase((double)xo[n] * inv_w, s, c);
+        sw[n] = s; cw[n] = c;
     }
-    smax = w.max(smax); wmax = w.max(wmax); tmax = w.max(tmax);
-    nan_ct = w.sum(nan_ct);
-    w.sync();
-    pr.bad = 0;
-    if (nan_ct > 0) pr.bad |= LF_ST_NAN_INPUT;
-    if (!(smax > 0.0f) || !(wmax > 0.0f) || !isfinite(smax)) pr.bad |= LF_ST_BAD_NORM;
-    pr.smax = smax; pr.wmax = wmax; pr.inv_wmax = 1.0f / wmax;
-    // noise: population std of spectrum_normalized over the noise window (LuciFit.py:327-331)
-    {
-        int n = cfg.noise_hi - cfg.noise_lo;
-        double s1 = 0.0;
-        for (int i = cfg.noise_lo + w.lane; i < cfg.noise_hi; i += LANES) s1 += (double)spec[i];
-        s1 = w.sum(s1);
-        double mean = n > 0 ? s1 / n : 0.0;
-        double s2 = 0.0;
-        for (int i = cfg.noise_lo + w.lane; i < cfg.noise_hi; i += LANES) { double d = (double)spec[i] - mean; s2 += d * d; }
-        s2 = w.sum(s2);
-        pr.noise = n > 0 ? sqrt(s2 / n) / (double)smax : NAN;
-    }
-    pr.cont0 = lf_cont_estimate(w, spec, cfg.cont_lo, cfg.cont_hi, 1.0, sc_vals, sc_dev, sc_alive) / (double)smax;
-    // scale: ML-prior path max(spectrum_restricted) * max(spectrum_T) ; plain path max(spectrum_T)
-    pr.scale = cfg.ml_scale ? ((double)wmax / (double)smax) * (double)tmax : (double)tmax;
-    double ct = fabs(cos((double)theta_deg * 0.017453292519943295));
-    pr.corr = 1.0 / ct;
-    pr.sinc_w = pr.corr * cfg.axis_k;
 }
 
-// One pass over the fit window: chi2 = sum r^2, H = J^T J (packed upper), gr = J^T r at parameters th.
+// Per-line records of one evaluation at parameters th (per-warp memory), lane k builds line k.
 template <int MODEL, int L, int NV, int NS, int LANES>
-LF_CORE void lf_eval(const LfCfg& cfg, const LfWarp<LANES>& w, const float* xo, const float* spec, float inv_wmax, float sinc_w,
-                     const float (&th)[LfDims<MODEL, L, NV, NS>::P], double& chi2_out,
-                     float (&H)[LfDims<MODEL, L, NV, NS>::NH], float (&gr)[LfDims<MODEL, L, NV, NS>::P])
+LF_CORE void lf_setup_lines(const LfCfg& cfg, const LfWarp<LANES>& w, const float* th, float sinc_w, double inv_w,
+                            LfLineX* sl, LfTieX* tx)
 {
     typedef LfDims<MODEL, L, NV, NS> D;
-    constexpr int P = D::P;
-    LfLine ln[L];
-    float aeff[L], dpdv[L], dsdv[L], dsdb[L], pk[L], bk[L];
-    bool tie = cfg.i48 >= 0;
-    float R = 0.0f, cRv[NV], cRb[NS];
-#pragma unroll
-    for (int g = 0; g < NV; ++g) cRv[g] = 0.0f;
-#pragma unroll
-    for (int h = 0; h < NS; ++h) cRb[h] = 0.0f;
-#pragma unroll
-    for (int k = 0; k < L; ++k) {
+    w.sync();
+    for (int k = w.lane; k < L; k += LANES) {
         int g = NV == 1 ? 0 : cfg.vg[k], h = NS == 1 ? 0 : cfg.sg[k];
-        float v = 0.0f, beta = 0.0f;
-#pragma unroll
-        for (int gg = 0; gg < NV; ++gg) if (gg == g) v = th[D::IV + gg];
-#pragma unroll
-        for (int hh = 0; hh < NS; ++hh) if (hh == h) beta = th[D::IS + hh];
+        float v = th[D::IV + g], beta = th[D::IS + h];
         float vt = v * (1.0f / LF_C_KMS);
         float i1v = 1.0f / (1.0f + vt);
         float p = cfg.p0[k] * i1v;
         float sig = p * beta * (1.0f / LF_C_KMS);
-        lf_line_setup(MODEL, cfg.p0_off[k], cfg.p0_lo[k] - cfg.p0[k] * vt * i1v, sig, sinc_w, ln[k]);
-        pk[k] = p; bk[k] = beta;
-        dpdv[k] = -p * i1v * (1.0f / LF_C_KMS);
-        dsdv[k] = beta * (1.0f / LF_C_KMS) * dpdv[k];
-        dsdb[k] = p * (1.0f / LF_C_KMS);
-        aeff[k] = th[k];
+        LfLineX x;
+        lf_line_setup(MODEL, cfg.p0_off[k], cfg.p0_lo[k] - cfg.p0[k] * vt * i1v, sig, sinc_w, x.ln);
+        x.p = p; x.beta = beta;
+        x.dpdv = -p * i1v * (1.0f / LF_C_KMS);
+        x.dsdv = beta * (1.0f / LF_C_KMS) * x.dpdv;
+        x.dsdb = p * (1.0f / LF_C_KMS);
+        x.aeff = th[k];
+        x.vg = g; x.sg = h;
+        x.ck = 1.0f; x.sk = 0.0f;
+        if (MODEL != LF_GAUSSIAN) lf_phase(((double)x.ln.pp + (double)x.ln.dp) * inv_w, x.sk, x.ck);
+        sl[k] = x;
     }
-    if (tie && MODEL == LF_SINC) {
-        // sinc: the constraint A_83 sigma_83/3 = A_48 sigma_48 (LuciFit.py:587-589) is vacuous when sigma = 0
-        // (no prior broadening, the reference's ML_bool=False path) -> both amplitudes are free
-#pragma unroll
-        for (int k = 0; k < L; ++k) if ((k == cfg.i83 || k == cfg.i48) && bk[k] == 0.0f) tie = false;
-    }
-    if (tie) {
-        // A_6548 = R A_6583, R = G(sigma_6583)/(3 G(sigma_6548)); ln G = ln p + ln beta - ln c [- ln erf(u)]
-        float p83 = 1.f, p48 = 1.f, b83 = 1.f, b48 = 1.f, s83 = 1.f, s48 = 1.f, a83 = 0.f;
-        float dv83 = 0.f, dv48 = 0.f, db83 = 0.f, db48 = 0.f, dp83 = 0.f, dp48 = 0.f;
-#pragma unroll
-        for (int k = 0; k < L; ++k) {
-            if (k == cfg.i83) { p83 = pk[k]; b83 = bk[k]; s83 = ln[k].sig; a83 = th[k]; dv83 = dsdv[k]; db83 = dsdb[k]; dp83 = dpdv[k]; }
-            if (k == cfg.i48) { p48 = pk[k]; b48 = bk[k]; s48 = ln[k].sig; dv48 = dsdv[k]; db48 = dsdb[k]; dp48 = dpdv[k]; }
+    w.sync();
+    if (w.lane == 0) {
+        bool tie = cfg.i48 >= 0;
+        if (tie && MODEL == LF_SINC) {
+            // sinc: A_83 sigma_83/3 = A_48 sigma_48 (LuciFit.py:587-589) is vacuous when sigma = 0 (no prior
+            // broadening, the reference's ML_bool=False path) -> both amplitudes are free
+            if (sl[cfg.i83].beta == 0.0f || sl[cfg.i48].beta == 0.0f) tie = false;
         }
-        int g83 = NV == 1 ? 0 : cfg.vg[cfg.i83], g48 = NV == 1 ? 0 : cfg.vg[cfg.i48];
-        int h83 = NS == 1 ? 0 : cfg.sg[cfg.i83], h48 = NS == 1 ? 0 : cfg.sg[cfg.i48];
-        R = lf_tie_ratio(MODEL, p83, b83, s83, p48, b48, s48, h83 == h48, sinc_w);
-        float E83 = 0.f, E48 = 0.f;
-        if (MODEL == LF_SINCGAUSS) { E83 = 1.0f / s83 - lf_dlnG(MODEL, s83, sinc_w); E48 = 1.0f / s48 - lf_dlnG(MODEL, s48, sinc_w); }
+        tx->active = tie ? 1 : 0;
+        tx->R = 0.0f;
 #pragma unroll
-        for (int g = 0; g < NV; ++g)
-            cRv[g] = a83 * R * ((g == g83 ? dp83 / p83 - E83 * dv83 : 0.f) - (g == g48 ? dp48 / p48 - E48 * dv48 : 0.f));
+        for (int g = 0; g < NV; ++g) tx->cRv[g] = 0.0f;
 #pragma unroll
-        for (int h = 0; h < NS; ++h) {
-            float t = 0.f;
-            if (h83 != h48) t = (h == h83 ? 1.0f / fmaxf(b83, 1e-6f) : 0.f) - (h == h48 ? 1.0f / fmaxf(b48, 1e-6f) : 0.f);
-            cRb[h] = a83 * R * (t - (h == h83 ? E83 * db83 : 0.f) + (h == h48 ? E48 * db48 : 0.f));
+        for (int h = 0; h < NS; ++h) tx->cRb[h] = 0.0f;
+        if (tie) {
+            // A_6548 = R A_6583, R = G(sigma_6583)/(3 G(sigma_6548)); ln G = ln p + ln beta - ln c [- ln erf(u)]
+            const LfLineX& x83 = sl[cfg.i83];
+            const LfLineX& x48 = sl[cfg.i48];
+            float p83 = x83.p, p48 = x48.p, b83 = x83.beta, b48 = x48.beta, s83 = x83.ln.sig, s48 = x48.ln.sig;
+            float a83 = x83.aeff;
+            int g83 = x83.vg, g48 = x48.vg, h83 = x83.sg, h48 = x48.sg;
+            float R = lf_tie_ratio(MODEL, p83, b83, s83, p48, b48, s48, h83 == h48, sinc_w);
+            float E83 = 0.f, E48 = 0.f;
+            if (MODEL == LF_SINCGAUSS) { E83 = 1.0f / s83 - lf_dlnG(MODEL, s83, sinc_w); E48 = 1.0f / s48 - lf_dlnG(MODEL, s48, sinc_w); }
+#pragma unroll
+            for (int g = 0; g < NV; ++g)
+                tx->cRv[g] = a83 * R * ((g == g83 ? x83.dpdv / p83 - E83 * x83.dsdv : 0.f) - (g == g48 ? x48.dpdv / p48 - E48 * x48.dsdv : 0.f));
+#pragma unroll
+            for (int h = 0; h < NS; ++h) {
+                float t = 0.f;
+                if (h83 != h48) t = (h == h83 ? 1.0f / fmaxf(b83, 1e-6f) : 0.f) - (h == h48 ? 1.0f / fmaxf(b48, 1e-6f) : 0.f);
+                tx->cRb[h] = a83 * R * (t - (h == h83 ? E83 * x83.dsdb : 0.f) + (h == h48 ? E48 * x48.dsdb : 0.f));
+            }
+            tx->R = R;
+            sl[cfg.i48].aeff = R * a83;
         }
-#pragma unroll
-        for (int k = 0; k < L; ++k) if (k == cfg.i48) aeff[k] = R * a83;
     }
-    const float piw = LF_PI_F / sinc_w, iw = 1.0f / sinc_w;
-    const float cont = th[D::IC];
+    w.sync();
+}
+
+// Sum over lanes of acc[0..N): recursive halving, afterwards every element lives (fully summed) in exactly one
+// lane, which stores it to dst[element].  ~4 instructions per element and step instead of a 5-step butterfly
+// on all N values.
+template <int N, int OFF, int LANES> struct LfReduceScatter {
+    static LF_CORE void run(const LfWarp<LANES>& w, float* v, int base, int size, float* dst)
+    {
+        constexpr int H = (N + 1) / 2;
+        const bool up = (w.lane & OFF) != 0;
+#pragma unroll
+        for (int i = 0; i < H; ++i) {
+            float lo = v[i], hi = (H + i < N) ? v[H + i] : 0.0f;
+            float keep = up ? hi : lo, send = up ? lo : hi;
+            v[i] = keep + w.xchg(send, OFF);
+        }
+        LfReduceScatter<H, OFF / 2, LANES>::run(w, v, base + (up ? H : 0), up ? size - H : (size < H ? size : H), dst);
+    }
+};
+template <int N, int LANES> struct LfReduceScatter<N, 0, LANES> {
+    static LF_CORE void run(const LfWarp<LANES>&, float* v, int base, int size, float* dst)
+    {
+#pragma unroll
+        for (int i = 0; i < N; ++i) if (i < size) dst[base + i] = v[i];
+    }
+};
+
+// One pass over the fit window: chi2 = sum r^2, and (into dst[NA], per-warp memory) H = J^T J packed upper
+// followed by g = J^T r, at the parameters the line records `sl` were built for.
+template <int MODEL, int L, int NV, int NS, int LANES>
+LF_CORE void lf_eval(const LfCfg& cfg, const LfWarp<LANES>& w, const float* xo, const LfWork& wk, int nfit, float sinc_w,
+                     float cont, double& chi2_out, float* dst)
+{
+    typedef LfDims<MODEL, L, NV, NS> D;
+    constexpr int P = D::P, NH = D::NH, NA = D::NA;
+    const LfLineX* sl = wk.lines;
+    float* gt = wk.gt;
+    const float iw = 1.0f / sinc_w;
+    float acc[NA];
+#pragma unroll
+    for (int e = 0; e < NA; ++e) acc[e] = 0.0f;
     double chi2 = 0.0;
-#pragma unroll
-    for (int e = 0; e < D::NH; ++e) H[e] = 0.0f;
-#pragma unroll
-    for (int j = 0; j < P; ++j) gr[j] = 0.0f;
-    const int nfit = cfg.fit_hi - cfg.fit_lo;
-    const float* y = spec + cfg.fit_lo;
+    const bool tie = wk.tie->active != 0;
     for (int n0 = 0; n0 < nfit; n0 += LANES) {
-        int n = n0 + w.lane;
-        bool live = n < nfit;
-        float x = live ? xo[n] : 0.0f;
-        float yn = live ? y[n] * inv_wmax : 0.0f;
+        const int n = n0 + w.lane;
+        const bool live = n < nfit;
+        const float x = live ? xo[n] : 0.0f;
+        const float yn = live ? wk.yw[n] : 0.0f;
+        float S = 0.0f, C = 1.0f;
+        if (MODEL != LF_GAUSSIAN && live) { S = wk.sw[n]; C = wk.cw[n]; }
+        float Jv[NV], Js[NS];
+#pragma unroll
+        for (int g = 0; g < NV; ++g) Jv[g] = 0.0f;
+#pragma unroll
+        for (int h = 0; h < NS; ++h) Js[h] = 0.0f;
+        float m = cont;
+#pragma unroll 1
+        for (int k = 0; k < L; ++k) {
+            const LfLineX& X = sl[k];
+            const float dx = lf_dx(X.ln, x);
+            bool all_far = false;
+            if (MODEL == LF_SINCGAUSS) all_far = w.all(lf_is_far(X.ln, dx));
+            if (MODEL == LF_GAUSSIAN) {
+                float b = dx * X.ln.is2s;
+                if (w.all(b * b > 100.0f)) { gt[k * LANES + w.lane] = 0.0f; continue; }   // exp(-100) = 0 in FP32
+            }
+            float s = 0.0f, c = 1.0f;
+            if (MODEL != LF_GAUSSIAN) { s = S * X.ck - C * X.sk; c = C * X.ck + S * X.sk; }
+            float g, gp, gs;
+            lf_profile_sc<MODEL>(X.ln, dx, s, c, iw, all_far, g, gp, gs);
+            const float A = X.aeff;
+            m += A * g;
+            const float tp = A * gp, ts = A * gs;
+            const float tv = tp * X.dpdv + ts * X.dsdv;
+            const float tb = ts * X.dsdb;
+            gt[k * LANES + w.lane] = g;
+#pragma unroll
+            for (int gg = 0; gg < NV; ++gg) Jv[gg] += (NV == 1 || X.vg == gg) ? tv : 0.0f;
+            if (MODEL != LF_SINC) {
+#pragma unroll
+                for (int hh = 0; hh < NS; ++hh) Js[hh] += (NS == 1 || X.sg == hh) ? tb : 0.0f;
+            }
+        }
         float J[P];
 #pragma unroll
-        for (int j = 0; j < P; ++j) J[j] = 0.0f;
-        J[D::IC] = 1.0f;
-        float m = cont, g48v = 0.0f;
-#pragma unroll
-        for (int k = 0; k < L; ++k) {
-            float dx = lf_dx(ln[k], x);
-            bool all_far = false;
-            if (MODEL == LF_SINCGAUSS) all_far = w.all(lf_is_far(ln[k], dx));
-            float g, gp, gs;
-            lf_profile<MODEL>(ln[k], dx, piw, iw, all_far, g, gp, gs);
-            float A = aeff[k];
-            m += A * g;
-            float tp = A * gp, ts = A * gs;
-            float tv = tp * dpdv[k] + ts * dsdv[k];
-            float tb = ts * dsdb[k];
-            if (tie && k == cfg.i48) { g48v = g; } else { J[k] += g; }
-#pragma unroll
-            for (int gg = 0; gg < NV; ++gg) if (NV == 1 || cfg.vg[k] == gg) J[D::IV + gg] += tv;
-            if (MODEL != LF_SINC) {
-#pragma unroll
-                for (int hh = 0; hh < NS; ++hh) if (NS == 1 || cfg.sg[k] == hh) J[D::IS + hh] += tb;
-            }
-        }
+        for (int k = 0; k < L; ++k) J[k] = gt[k * LANES + w.lane];
         if (tie) {
+            const float g48v = gt[cfg.i48 * LANES + w.lane];
+            const float R = wk.tie->R;
 #pragma unroll
-            for (int k = 0; k < L; ++k) if (k == cfg.i83) J[k] += R * g48v;
+            for (int k = 0; k < L; ++k) {
+                if (k == cfg.i48) J[k] = 0.0f;
+                if (k == cfg.i83) J[k] += R * g48v;
+            }
 #pragma unroll
-            for (int gg = 0; gg < NV; ++gg) J[D::IV + gg] += g48v * cRv[gg];
+            for (int gg = 0; gg < NV; ++gg) Jv[gg] += g48v * wk.tie->cRv[gg];
             if (MODEL != LF_SINC) {
 #pragma unroll
-                for (int hh = 0; hh < NS; ++hh) J[D::IS + hh] += g48v * cRb[hh];
+                for (int hh = 0; hh < NS; ++hh) Js[hh] += g48v * wk.tie->cRb[hh];
             }
         }
+#pragma unroll
+        for (int gg = 0; gg < NV; ++gg) J[D::IV + gg] = Jv[gg];
+#pragma unroll
+        for (int hh = 0; hh < NS; ++hh) J[D::IS + hh] = (MODEL != LF_SINC) ? Js[hh] : 0.0f;
+        J[D::IC] = 1.0f;
         if (live) {
-            float r = yn - m;
+            const float r = yn - m;
             chi2 += (double)r * (double)r;
 #pragma unroll
             for (int i = 0; i < P; ++i) {
-                gr[i] += J[i] * r;
+                acc[NH + i] += J[i] * r;
 #pragma unroll
-                for (int j = i; j < P; ++j) H[LfSym<P>::idx(i, j)] += J[i] * J[j];
+                for (int j = i; j < P; ++j) acc[LfSym<P>::idx(i, j)] += J[i] * J[j];
             }
         }
     }
     chi2_out = w.sum(chi2);
-#pragma unroll
-    for (int e = 0; e < D::NH; ++e) H[e] = w.sum(H[e]);
-#pragma unroll
-    for (int j = 0; j < P; ++j) gr[j] = w.sum(gr[j]);
+    w.sync();
+    LfReduceScatter<NA, LANES / 2, LANES>::run(w, acc, 0, NA, dst);
+    w.sync();
 }
 
 // Solve (D^-1/2 H D^-1/2 + lam I) s = D^-1/2 g with fixed columns pinned, delta = D^-1/2 s.  Returns false if the
-// Cholesky factorisation meets a non-positive pivot.
+// Cholesky factorisation meets a non-positive pivot.  `hg` = [H packed | g] in per-warp memory.
 template <int P>
-LF_CORE bool lf_solve(const float (&H)[P * (P + 1) / 2], const float (&gr)[P], unsigned fixedmask, float lam,
-                      float (&delta)[P], float& pred)
+LF_CORE bool lf_solve(const float* hg, unsigned fixedmask, float lam, float (&delta)[P], float& pred)
 {
-    float sc[P], M[P * (P + 1) / 2], b[P];
+    constexpr int NH = P * (P + 1) / 2;
+    float sc[P], M[NH], b[P];
 #pragma unroll
     for (int j = 0; j < P; ++j) {
-        float d = H[LfSym<P>::idx(j, j)];
+        float d = hg[LfSym<P>::idx(j, j)];
         bool fx = ((fixedmask >> j) & 1u) || !(d > 1e-30f);
         sc[j] = fx ? 0.0f : LF_RSQRT(d);
-        b[j] = gr[j] * sc[j];
+        b[j] = hg[NH + j] * sc[j];
     }
 #pragma unroll
     for (int i = 0; i < P; ++i)
 #pragma unroll
         for (int j = i; j < P; ++j) {
-            float v = H[LfSym<P>::idx(i, j)] * sc[i] * sc[j];
+            float v = hg[LfSym<P>::idx(i, j)] * sc[i] * sc[j];
             if (i == j) v = (sc[i] == 0.0f) ? 1.0f : v + lam;
             M[LfSym<P>::idx(i, j)] = v;
         }
@@ -465,15 +513,10 @@ LF_CORE bool lf_solve(const float (&H)[P * (P + 1) / 2], const float (&gr)[P], u
     return ok;
 }
 
-struct LfFitResult {
-    double chi2;       // sum of squared residuals of the normalised window at the solution
-    int iters, evals, flags;
-};
-
-// Box of the reduced parameters (LuciFit.py:614-633 amplitudes/continuum; :539-541 sigma of the last line).
+// Box of the reduced parameters (LuciFit.py:614-633 amplitudes/continuum; :539-541 sigma of the last line), written
+// to per-warp memory by lane 0 (callers sync).
 template <int MODEL, int L, int NV, int NS>
-LF_CORE void lf_bounds(const LfCfg& cfg, const float (&th)[LfDims<MODEL, L, NV, NS>::P],
-                       float (&lo)[LfDims<MODEL, L, NV, NS>::P], float (&hi)[LfDims<MODEL, L, NV, NS>::P])
+LF_CORE void lf_bounds(const LfCfg& cfg, const float* th, float* lo, float* hi)
 {
     typedef LfDims<MODEL, L, NV, NS> D;
 #pragma unroll
@@ -481,10 +524,8 @@ LF_CORE void lf_bounds(const LfCfg& cfg, const float (&th)[LfDims<MODEL, L, NV, 
 #pragma unroll
     for (int g = 0; g < NV; ++g) { lo[D::IV + g] = -INFINITY; hi[D::IV + g] = INFINITY; }
     // sigma box applies to the LAST line only (late-binding lambda in the reference); other groups: beta >= 0
-    float vlast = 0.0f;
-#pragma unroll
-    for (int g = 0; g < NV; ++g) if (NV == 1 || cfg.vg[L - 1] == g) vlast = th[D::IV + g];
-    float plast = cfg.p0[L - 1] / (1.0f + vlast * (1.0f / LF_C_KMS));
+    const float vlast = th[D::IV + (NV == 1 ? 0 : cfg.vg[L - 1])];
+    const float plast = cfg.p0[L - 1] / (1.0f + vlast * (1.0f / LF_C_KMS));
 #pragma unroll
     for (int h = 0; h < NS; ++h) {
         lo[D::IS + h] = 0.0f;
@@ -493,69 +534,156 @@ LF_CORE void lf_bounds(const LfCfg& cfg, const float (&th)[LfDims<MODEL, L, NV, 
     lo[D::IC] = -1e-8f; hi[D::IC] = 0.99f;
 }
 
-// Levenberg-Marquardt on sum r^2 (the noise is a common factor of the reference's nll, LuciFit.py:516, and does
-// not move the optimum).  `st` = per-warp scratch holding the current (H, g) so a rejected step can be re-solved.
+// ---------------------------------------------------------------------------------------------- stage: prep
+// Reads the spaxel's spectrum, computes everything Fit.__init__ does plus the initial vector, writes the state.
 template <int MODEL, int L, int NV, int NS, int LANES>
-LF_CORE void lf_lm(const LfCfg& cfg, const LfWarp<LANES>& w, const float* xo, const float* spec, float inv_wmax, float sinc_w,
-                   float (&th)[LfDims<MODEL, L, NV, NS>::P], float* st, LfFitResult& res)
+LF_CORE void lf_stage_prep(const LfCfg& cfg, const LfWarp<LANES>& w, const float* gspec, float theta_deg, float vel0,
+                           float broad0, const LfWork& wk, float* state)
 {
     typedef LfDims<MODEL, L, NV, NS> D;
-    constexpr int P = D::P, NH = D::NH;
-    float H[NH], gr[P];
-    double chi2;
-    float lo[P], hi[P];
-    lf_bounds<MODEL, L, NV, NS>(cfg, th, lo, hi);
-#pragma unroll
-    for (int j = 0; j < P; ++j) th[j] = fminf(fmaxf(th[j], lo[j]), hi[j]);
-    lf_eval<MODEL, L, NV, NS, LANES>(cfg, w, xo, spec, inv_wmax, sinc_w, th, chi2, H, gr);
-    int evals = 1, iters = 0, flags = 0;
-    float lam = 1e-3f, nu = 2.0f;
-    const double ftol = (double)cfg.ftol;
-    bool done = false;
-    while (!done && iters < cfg.max_iter && evals < 250) {
-        // stash current normal equations (warp-uniform) so a rejection can re-solve without re-evaluating
-#pragma unroll
-        for (int e = 0; e < NH; ++e) if ((e % LANES) == w.lane || LANES == 1) st[e] = H[e];
-#pragma unroll
-        for (int j = 0; j < P; ++j) if (((NH + j) % LANES) == w.lane || LANES == 1) st[NH + j] = gr[j];
-        w.sync();
-        unsigned fixedmask = 0;
-#pragma unroll
-        for (int j = 0; j < P; ++j) {
-            bool at_lo = th[j] <= lo[j] && gr[j] <= 0.0f;
-            bool at_hi = th[j] >= hi[j] && gr[j] >= 0.0f;
-            if (at_lo || at_hi) fixedmask |= 1u << j;
+    const int nz = cfg.nz;
+    float* spec = wk.spec;
+    float smax = -INFINITY, wmax = -INFINITY, tmax = -INFINITY;
+    int nan_ct = 0;
+    w.sync();
+    for (int i = w.lane; i < nz; i += LANES) {
+        float s = gspec[i];
+        if (cfg.bkg) s -= cfg.bkg[i];
+        spec[i] = s;
+        nan_ct += (s != s);
+        smax = fmaxf(smax, s);
+        if (i >= cfg.fit_lo && i < cfg.fit_hi) wmax = fmaxf(wmax, s);
+        float st = s;
+        if (cfg.trans) { float t = cfg.trans[i]; if (t > 0.5f) st = s / t; }
+        tmax = fmaxf(tmax, st);
+    }
+    smax = w.max(smax); wmax = w.max(wmax); tmax = w.max(tmax);
+    nan_ct = w.sum(nan_ct);
+    w.sync();
+    int bad = 0;
+    if (nan_ct > 0) bad |= LF_ST_NAN_INPUT;
+    if (!(smax > 0.0f) || !(wmax > 0.0f) || !isfinite(smax)) bad |= LF_ST_BAD_NORM;
+    if (bad) {                                         // reference returns zeros for unusable spectra
+        if (w.lane == 0) reinterpret_cast<int*>(state)[LF_SO_STATUS] = bad;
+        return;
+    }
+    // noise: population std of spectrum_normalized over the noise window (LuciFit.py:327-331)
+    double noise;
+    {
+        int n = cfg.noise_hi - cfg.noise_lo;
+        double s1 = 0.0;
+        for (int i = cfg.noise_lo + w.lane; i < cfg.noise_hi; i += LANES) s1 += (double)spec[i];
+        s1 = w.sum(s1);
+        double mean = n > 0 ? s1 / n : 0.0;
+        double s2 = 0.0;
+        for (int i = cfg.noise_lo + w.lane; i < cfg.noise_hi; i += LANES) { double d = (double)spec[i] - mean; s2 += d * d; }
+        s2 = w.sum(s2);
+        noise = n > 0 ? sqrt(s2 / n) / (double)smax : NAN;
+    }
+    const double cont0 = lf_cont_estimate(w, spec, cfg.cont_lo, cfg.cont_hi, 1.0, wk.sortv, wk.sortd, wk.npad) / (double)smax;
+    // scale: ML-prior path max(spectrum_restricted) * max(spectrum_T) ; plain path max(spectrum_T)
+    const double scale = cfg.ml_scale ? ((double)wmax / (double)smax) * (double)tmax : (double)tmax;
+    const double ct = fabs(cos((double)theta_deg * 0.017453292519943295));
+    const double corr = 1.0 / ct;
+    const double sinc_w = corr * cfg.axis_k;
+    // initial vector (LuciFit.py:663-672, 410-423): amplitude = max over +-5 channels around the expected
+    // centre minus the continuum guess; centres from the prior velocity; sigma from the prior broadening.
+    if (vel0 != vel0) vel0 = 0.0f;                     // LuciFit.py:406-409
+    if (broad0 != broad0) broad0 = 1.0f;
+    broad0 = fabsf(broad0);
+    float* th = state + LF_SO_TH;
+    for (int k = w.lane; k < L; k += LANES) {
+        double lam = cfg.line_nm[k];
+        double pos = 1e7 / (((double)vel0 / 299792.0) * lam + lam);
+        int ind = lf_nearest_axis(cfg.axis, nz, pos);
+        float amp;
+        if (ind + 5 > nz - 1) {
+            amp = spec[ind];                           // IndexError branch (LuciFit.py:420-421)
+        } else {
+            amp = -INFINITY;
+            for (int d = -5; d <= 5; ++d) { int i = ind + d; if (i < 0) i += nz; amp = fmaxf(amp, spec[i]); }
         }
+        th[k] = (float)((double)amp / (double)smax - cont0);
+    }
+    if (w.lane == 0) {
+#pragma unroll
+        for (int g = 0; g < NV; ++g) th[D::IV + g] = vel0;
+#pragma unroll
+        for (int h = 0; h < NS; ++h) th[D::IS + h] = broad0;
+        th[D::IC] = (float)cont0;
+        double* sd = reinterpret_cast<double*>(state);
+        sd[LF_SO_NOISE / 2] = noise; sd[LF_SO_SCALE / 2] = scale; sd[LF_SO_CORR / 2] = corr; sd[LF_SO_SINCW / 2] = sinc_w;
+        state[LF_SO_INVW] = 1.0f / wmax;
+        reinterpret_cast<int*>(state)[LF_SO_STATUS] = 0;
+    }
+    w.sync();
+}
+
+// Stages the normalised fit window and the phase table of one spaxel into per-warp memory:
+//   yw[n] = (cube[fit_lo + n] - bkg) * mul, optionally divided by the transmission (the `out` stage).
+template <int MODEL, int LANES>
+LF_CORE void lf_stage_window(const LfCfg& cfg, const LfWarp<LANES>& w, const float* xo, const float* gspec, float mul,
+                             bool use_trans, double sinc_w, const LfWork& wk)
+{
+    const int nfit = cfg.fit_hi - cfg.fit_lo;
+    w.sync();
+    for (int n = w.lane; n < nfit; n += LANES) {
+        int i = cfg.fit_lo + n;
+        float s = gspec[i];
+        if (cfg.bkg) s -= cfg.bkg[i];
+        if (use_trans && cfg.trans) { float t = cfg.trans[i]; if (t > 0.5f) s = s / t; }
+        wk.yw[n] = s * mul;
+    }
+    if (MODEL != LF_GAUSSIAN) lf_phase_table(w, xo, nfit, 1.0 / sinc_w, wk.sw, wk.cw);
+    w.sync();
+}
+
+// ------------------------------------------------------------------------------------------------ stage: lm
+// Levenberg-Marquardt on sum r^2 (the noise is a common factor of the reference's nll, LuciFit.py:516, and does not
+// move the optimum).  The accepted and the trial normal equations live in per-warp memory (wk.hb), theta / trial
+// theta / box in wk.thb, so that the evaluation loop owns the registers.
+template <int MODEL, int L, int NV, int NS, int LANES>
+LF_CORE void lf_stage_lm(const LfCfg& cfg, const LfWarp<LANES>& w, const float* xo, const float* gspec, const LfWork& wk,
+                         float* state)
+{
+    typedef LfDims<MODEL, L, NV, NS> D;
+    constexpr int P = D::P, NA = D::NA;
+    int status = reinterpret_cast<const int*>(state)[LF_SO_STATUS];
+    if (status & LF_ST_BADMASK) return;
+    const double sinc_w_d = reinterpret_cast<const double*>(state)[LF_SO_SINCW / 2];
+    const float sinc_w = (float)sinc_w_d;
+    const double inv_w = 1.0 / sinc_w_d;
+    const int nfit = cfg.fit_hi - cfg.fit_lo;
+    lf_stage_window<MODEL, LANES>(cfg, w, xo, gspec, state[LF_SO_INVW], false, sinc_w_d, wk);
+    float* th = wk.thb;
+    float* tht = wk.thb + P;
+    float* lo = wk.thb + 2 * P;
+    float* hi = wk.thb + 3 * P;
+    float* hcur = wk.hb;
+    float* htri = wk.hb + NA;
+    if (w.lane == 0) {
+        for (int j = 0; j < P; ++j) th[j] = state[LF_SO_TH + j];
+        lf_bounds<MODEL, L, NV, NS>(cfg, th, lo, hi);
+        for (int j = 0; j < P; ++j) { th[j] = fminf(fmaxf(th[j], lo[j]), hi[j]); tht[j] = th[j]; }
+    }
+    w.sync();
+    int evals = 0, iters = 0, flags = 0, tries = 0;
+    float lam = 1e-3f, nu = 2.0f, pred = 0.0f;
+    double chi2 = 0.0;
+    const double ftol = (double)cfg.ftol;
+    bool first = true, done = false;
+    unsigned fixedmask = 0;
+    while (true) {
+        // ---- evaluate the trial point
+        double chi2t;
+        lf_setup_lines<MODEL, L, NV, NS, LANES>(cfg, w, tht, sinc_w, inv_w, wk.lines, wk.tie);
+        lf_eval<MODEL, L, NV, NS, LANES>(cfg, w, xo, wk, nfit, sinc_w, tht[D::IC], chi2t, htri);
+        ++evals;
         bool accepted = false;
-        for (int tries = 0; tries < 12 && !accepted && !done; ++tries) {
-            float delta[P], pred;
-            bool ok = lf_solve<P>(H, gr, fixedmask, lam, delta, pred);
-            if (!ok) { lam *= 10.0f; flags |= LF_ST_SINGULAR; continue; }
-            float tht[P];
-            float rel = 0.0f;
-#pragma unroll
-            for (int j = 0; j < P; ++j) {
-                tht[j] = fminf(fmaxf(th[j] + delta[j], lo[j]), hi[j]);
-                float sc = (j >= D::IV && j < D::IS) ? 1.0f : fmaxf(fabsf(th[j]), 1e-3f);   // velocities: km/s absolute
-                rel = fmaxf(rel, fabsf(tht[j] - th[j]) / sc);
-            }
-            // The predicted decrease is below what an FP32 evaluation of sum r^2 can resolve: take the (Newton-like)
-            // step and stop -- evaluating it would only return rounding noise.
-            if ((double)pred <= ftol * chi2 && rel < 1e-2f) {
-#pragma unroll
-                for (int j = 0; j < P; ++j) th[j] = tht[j];
-                done = true; flags |= LF_ST_CONVERGED;
-                ++iters;
-                break;
-            }
-            double chi2t;
-            float Ht[NH], grt[P];
-            lf_eval<MODEL, L, NV, NS, LANES>(cfg, w, xo, spec, inv_wmax, sinc_w, tht, chi2t, Ht, grt);
-            ++evals;
-            bool finite = chi2t == chi2t;
-#if defined(LF_TRACE)
-            printf("  it %d try %d lam %.2e chi2 %.10e chi2t %.10e pred %.3e rel %.2e\n", iters, tries, lam, chi2, chi2t, pred, rel);
-#endif
+        if (first) {
+            first = false; accepted = true; chi2 = chi2t;
+        } else {
+            const bool finite = chi2t == chi2t;
             // An FP32 evaluation resolves sum r^2 to a few 1e-6 relative; once the predicted decrease is that small
             // the gradient (still accurate) is trusted and the step is taken even if chi2 appears to rise by noise.
             const double slack = ((double)pred <= 1e-4 * chi2) ? 4e-6 * chi2 : 0.0;
@@ -566,140 +694,200 @@ LF_CORE void lf_lm(const LfCfg& cfg, const LfWarp<LANES>& w, const float* xo, co
                 lam *= fmaxf(1.0f / 3.0f, f);
                 lam = fmaxf(lam, 1e-7f);
                 nu = 2.0f;
-#pragma unroll
-                for (int j = 0; j < P; ++j) { th[j] = tht[j]; gr[j] = grt[j]; }
-#pragma unroll
-                for (int e = 0; e < NH; ++e) H[e] = Ht[e];
                 accepted = true;
                 ++iters;
                 chi2 = chi2t;
             } else {
-                // rejected: restore the stashed system and increase the damping; inside the FP32 noise floor of
+                // rejected: keep the accepted system and increase the damping; inside the FP32 noise floor of
                 // sum r^2 (relative ~1e-6) a rejection only means "converged"
-#pragma unroll
-                for (int e = 0; e < NH; ++e) H[e] = st[e];
-#pragma unroll
-                for (int j = 0; j < P; ++j) gr[j] = st[NH + j];
                 lam *= nu; nu *= 2.0f;
+                ++tries;
                 if (finite && (double)pred <= 1e-5 * chi2) { done = true; flags |= LF_ST_CONVERGED; }
             }
         }
-        if (!accepted && !done) { done = true; flags |= LF_ST_MAXITER; }
-        if (accepted) lf_bounds<MODEL, L, NV, NS>(cfg, th, lo, hi);
+        if (accepted) {
+            float* t = hcur; hcur = htri; htri = t;       // the trial system becomes the accepted one
+            w.sync();
+            if (w.lane == 0) {
+                for (int j = 0; j < P; ++j) th[j] = tht[j];
+                lf_bounds<MODEL, L, NV, NS>(cfg, th, lo, hi);
+            }
+            w.sync();
+            tries = 0;
+            fixedmask = 0;
+#pragma unroll
+            for (int j = 0; j < P; ++j) {
+                float gj = hcur[D::NH + j];
+                bool at_lo = th[j] <= lo[j] && gj <= 0.0f;
+                bool at_hi = th[j] >= hi[j] && gj >= 0.0f;
+                if (at_lo || at_hi) fixedmask |= 1u << j;
+            }
+            if (!(iters < cfg.max_iter && evals < 250)) { flags |= LF_ST_MAXITER; done = true; }
+        }
+        if (done) break;
+        // ---- propose the next trial point
+        bool go = false;
+        while (!go && !done) {
+            if (tries >= 12) { done = true; flags |= LF_ST_MAXITER; break; }
+            float delta[P];
+            bool ok = lf_solve<P>(hcur, fixedmask, lam, delta, pred);
+            if (!ok) { lam *= 10.0f; flags |= LF_ST_SINGULAR; ++tries; continue; }
+            float tn[P];
+            float rel = 0.0f;
+#pragma unroll
+            for (int j = 0; j < P; ++j) {
+                float tj = th[j];
+                tn[j] = fminf(fmaxf(tj + delta[j], lo[j]), hi[j]);
+                float sc = (j >= D::IV && j < D::IS) ? 1.0f : fmaxf(fabsf(tj), 1e-3f);   // velocities: km/s absolute
+                rel = fmaxf(rel, fabsf(tn[j] - tj) / sc);
+            }
+            w.sync();
+#pragma unroll
+            for (int j = 0; j < P; ++j) if (w.lane == (j % LANES)) tht[j] = tn[j];
+            w.sync();
+            // The predicted decrease is below what an FP32 evaluation of sum r^2 can resolve: take the (Newton-like)
+            // step and stop -- evaluating it would only return rounding noise.
+            if ((double)pred <= ftol * chi2 && rel < 1e-2f) {
+                if (w.lane == 0) {
+                    for (int j = 0; j < P; ++j) th[j] = tht[j];
+                }
+                w.sync();
+                done = true; flags |= LF_ST_CONVERGED;
+                ++iters;
+                break;
+            }
+            go = true;
+        }
+        if (done) break;
     }
-    if (!done) flags |= LF_ST_MAXITER;
 #pragma unroll
     for (int j = 0; j < P; ++j) if (th[j] <= lo[j] || th[j] >= hi[j]) flags |= LF_ST_BOUND;
-    res.chi2 = chi2; res.iters = iters; res.evals = evals; res.flags = flags;
+    for (int j = w.lane; j < P; j += LANES) state[LF_SO_TH + j] = th[j];
+    if (w.lane == 0) reinterpret_cast<int*>(state)[LF_SO_STATUS] = (iters & 0xff) | ((evals & 0xff) << 8) | flags;
+    w.sync();
 }
 
-// Expand the reduced solution to the reference's fit_sol layout [A, p, sigma]*L + [continuum] in normalised units.
-template <int MODEL, int L, int NV, int NS>
-LF_CORE void lf_expand(const LfCfg& cfg, float sinc_w, const float (&th)[LfDims<MODEL, L, NV, NS>::P],
-                       double (&A)[L], double (&p)[L], double (&sg)[L], double (&vel)[L], double (&beta)[L])
+// Expand the reduced solution to the reference's fit_sol layout [A, p, sigma]*L + [continuum] in normalised units:
+// lane k writes line k of apd = [A | p | sigma] (float64).
+template <int MODEL, int L, int NV, int NS, int LANES>
+LF_CORE void lf_expand(const LfCfg& cfg, const LfWarp<LANES>& w, float sinc_w, const float* th, double* apd)
 {
     typedef LfDims<MODEL, L, NV, NS> D;
-#pragma unroll
-    for (int k = 0; k < L; ++k) {
-        float v = 0.f, b = 0.f;
-#pragma unroll
-        for (int g = 0; g < NV; ++g) if (NV == 1 || cfg.vg[k] == g) v = th[D::IV + g];
-#pragma unroll
-        for (int h = 0; h < NS; ++h) if (NS == 1 || cfg.sg[k] == h) b = th[D::IS + h];
-        vel[k] = (double)v; beta[k] = (double)b;
-        p[k] = 1e7 / (cfg.line_nm[k] * (1.0 + (double)v / 299792.0));
-        sg[k] = p[k] * (double)b / 299792.0;
-        A[k] = (double)th[k];
-    }
-    bool tie = cfg.i48 >= 0;
-    if (tie && MODEL == LF_SINC) {
-#pragma unroll
-        for (int k = 0; k < L; ++k) if ((k == cfg.i83 || k == cfg.i48) && beta[k] == 0.0) tie = false;
-    }
-    if (tie) {
-        float p83 = 1.f, p48 = 1.f, b83 = 1.f, b48 = 1.f, s83 = 1.f, s48 = 1.f;
-        double a83 = 0;
-        LfLine t;
-#pragma unroll
-        for (int k = 0; k < L; ++k) {
-            if (k == cfg.i83) { p83 = (float)p[k]; b83 = (float)beta[k]; lf_line_setup(MODEL, 0.f, 0.f, (float)sg[k], sinc_w, t); s83 = t.sig; a83 = A[k]; }
-            if (k == cfg.i48) { p48 = (float)p[k]; b48 = (float)beta[k]; lf_line_setup(MODEL, 0.f, 0.f, (float)sg[k], sinc_w, t); s48 = t.sig; }
+    w.sync();
+    for (int k = w.lane; k < L; k += LANES) {
+        float v = th[D::IV + (NV == 1 ? 0 : cfg.vg[k])], b = th[D::IS + (NS == 1 ? 0 : cfg.sg[k])];
+        double p = 1e7 / (cfg.line_nm[k] * (1.0 + (double)v / 299792.0));
+        double sg = p * (double)b / 299792.0;
+        double A = (double)th[k];
+        bool tie = cfg.i48 >= 0 && k == cfg.i48;
+        if (tie) {
+            float v83 = th[D::IV + (NV == 1 ? 0 : cfg.vg[cfg.i83])], b83 = th[D::IS + (NS == 1 ? 0 : cfg.sg[cfg.i83])];
+            if (MODEL == LF_SINC && (b == 0.0f || b83 == 0.0f)) tie = false;
+            if (tie) {
+                double p83 = 1e7 / (cfg.line_nm[cfg.i83] * (1.0 + (double)v83 / 299792.0));
+                double sg83 = p83 * (double)b83 / 299792.0;
+                LfLine t;
+                lf_line_setup(MODEL, 0.f, 0.f, (float)sg83, sinc_w, t);
+                float s83 = t.sig;
+                lf_line_setup(MODEL, 0.f, 0.f, (float)sg, sinc_w, t);
+                float s48 = t.sig;
+                bool same = (NS == 1) || cfg.sg[cfg.i83] == cfg.sg[cfg.i48];
+                float R = lf_tie_ratio(MODEL, (float)p83, b83, s83, (float)p, b, s48, same, sinc_w);
+                A = (double)th[cfg.i83] * (double)R;
+            }
         }
-        bool same = (NS == 1) || cfg.sg[cfg.i83] == cfg.sg[cfg.i48];
-        float R = lf_tie_ratio(MODEL, p83, b83, s83, p48, b48, s48, same, sinc_w);
-#pragma unroll
-        for (int k = 0; k < L; ++k) if (k == cfg.i48) A[k] = a83 * (double)R;
+        apd[k] = A; apd[L + k] = p; apd[2 * L + k] = sg;
     }
+    w.sync();
 }
 
-// ---------------------------------------------------------------------------------------------- outputs
+// ----------------------------------------------------------------------------------------------- stage: out
 // Row layout of the per-spaxel result (K = 7 L + 5 floats), the 12 quantities Luci.fit_calc collects
 // (LuciBase.py:381-392, 406):
 //   [0,L) amplitudes | [L,2L) fluxes | [2L,3L) flux errors | [3L,4L) velocities | [4L,5L) velocity errors |
 //   [5L,6L) broadenings | [6L,7L) broadening errors | chi2 | corr | axis_step | continuum | continuum error
 template <int MODEL, int L, int NV, int NS, int LANES>
-LF_CORE void lf_outputs(const LfCfg& cfg, const LfWarp<LANES>& w, const float* xo, const float* spec, const LfPrep& pr,
-                        const float (&th)[LfDims<MODEL, L, NV, NS>::P], const double* unc /* [3L+1] normalised or null */,
-                        float* out_row, float* out_sol, float* out_unc)
+LF_CORE void lf_stage_out(const LfCfg& cfg, const LfWarp<LANES>& w, const float* xo, const float* gspec, const LfWork& wk,
+                          const float* state, const double* unc /* [3L+1] normalised or null */,
+                          float* out_row, int32_t* out_status, float* out_sol, float* out_unc)
 {
     typedef LfDims<MODEL, L, NV, NS> D;
-    const float sinc_w = (float)pr.sinc_w;
-    double A[L], p[L], sg[L], vel[L], beta[L];
-    lf_expand<MODEL, L, NV, NS>(cfg, sinc_w, th, A, p, sg, vel, beta);
+    const int status = reinterpret_cast<const int*>(state)[LF_SO_STATUS];
+    if (status & LF_ST_BADMASK) {
+        for (int j = w.lane; j < 7 * L + 5; j += LANES) out_row[j] = 0.0f;
+        if (out_sol) for (int j = w.lane; j < 3 * L + 1; j += LANES) out_sol[j] = 0.0f;
+        if (out_unc) for (int j = w.lane; j < 3 * L + 1; j += LANES) out_unc[j] = 0.0f;
+        if (w.lane == 0) *out_status = status;
+        return;
+    }
+    const double* sd = reinterpret_cast<const double*>(state);
+    const double noise = sd[LF_SO_NOISE / 2], scale = sd[LF_SO_SCALE / 2], corr = sd[LF_SO_CORR / 2], sinc_w_d = sd[LF_SO_SINCW / 2];
+    const float sinc_w = (float)sinc_w_d;
+    const double inv_w = 1.0 / sinc_w_d;
+    const float* th = state + LF_SO_TH;
+    const int nfit = cfg.fit_hi - cfg.fit_lo;
+    lf_stage_window<MODEL, LANES>(cfg, w, xo, gspec, (float)(1.0 / scale), true, sinc_w_d, wk);
+    double* apd = wk.apd;
+    lf_expand<MODEL, L, NV, NS, LANES>(cfg, w, sinc_w, th, apd);
     const double cont = (double)th[D::IC];
     // chi2 with every line centre snapped to the nearest axis sample (Model.plot, LuciFunctions.py:113-115 etc.;
     // LuciFit.py:799-801, 1065-1068).  The scale cancels: chi2 = sum (s_T/scale - m)^2 / (noise (N - P_full)).
-    LfLine ln[L];
-#pragma unroll
-    for (int k = 0; k < L; ++k) {
-        int idx = lf_argmin_axis(w, cfg.axis, cfg.nz, p[k]);
+    LfLineX* sl = wk.lines;
+    for (int k = w.lane; k < L; k += LANES) {
+        int idx = lf_nearest_axis(cfg.axis, cfg.nz, apd[L + k]);
+        LfLineX x;
         float pps, ppl;
         lf_split(cfg.axis[idx] - cfg.x_ref, pps, ppl);
-        lf_line_setup(MODEL, pps, ppl, (float)sg[k], sinc_w, ln[k]);
+        lf_line_setup(MODEL, pps, ppl, (float)apd[2 * L + k], sinc_w, x.ln);
+        x.aeff = (float)apd[k];
+        x.dpdv = x.dsdv = x.dsdb = 0.0f; x.vg = x.sg = 0; x.p = x.beta = 0.0f;
+        x.ck = 1.0f; x.sk = 0.0f;
+        if (MODEL != LF_GAUSSIAN) lf_phase(((double)x.ln.pp + (double)x.ln.dp) * inv_w, x.sk, x.ck);
+        sl[k] = x;
     }
-    const float piw = LF_PI_F / sinc_w, iw = 1.0f / sinc_w;
-    const int nfit = cfg.fit_hi - cfg.fit_lo;
-    const float inv_scale = (float)(1.0 / pr.scale);
+    w.sync();
+    const float iw = 1.0f / sinc_w;
     double S = 0.0;
     for (int n0 = 0; n0 < nfit; n0 += LANES) {
-        int n = n0 + w.lane;
-        bool live = n < nfit;
-        float x = live ? xo[n] : 0.0f;
+        const int n = n0 + w.lane;
+        const bool live = n < nfit;
+        const float x = live ? xo[n] : 0.0f;
+        float Sx = 0.0f, Cx = 1.0f;
+        if (MODEL != LF_GAUSSIAN && live) { Sx = wk.sw[n]; Cx = wk.cw[n]; }
         float m = (float)cont;
-#pragma unroll
+#pragma unroll 1
         for (int k = 0; k < L; ++k) {
-            float dx = lf_dx(ln[k], x);
+            const LfLineX& X = sl[k];
+            const float dx = lf_dx(X.ln, x);
             bool all_far = false;
-            if (MODEL == LF_SINCGAUSS) all_far = w.all(lf_is_far(ln[k], dx));
+            if (MODEL == LF_SINCGAUSS) all_far = w.all(lf_is_far(X.ln, dx));
+            float s = 0.0f, c = 1.0f;
+            if (MODEL != LF_GAUSSIAN) { s = Sx * X.ck - Cx * X.sk; c = Cx * X.ck + Sx * X.sk; }
             float g, gp, gs;
-            lf_profile<MODEL>(ln[k], dx, piw, iw, all_far, g, gp, gs);
-            m += (float)A[k] * g;
+            lf_profile_sc<MODEL>(X.ln, dx, s, c, iw, all_far, g, gp, gs);
+            m += X.aeff * g;
         }
         if (live) {
-            float s = spec[cfg.fit_lo + n];
-            if (cfg.trans) { float t = cfg.trans[cfg.fit_lo + n]; if (t > 0.5f) s = s / t; }
-            float r = s * inv_scale - m;
+            float r = wk.yw[n] - m;
             S += (double)r * (double)r;
         }
     }
     S = w.sum(S);
-    const double chi2 = S / (pr.noise * (double)(nfit - (3 * L + 1)));
+    const double chi2 = S / (noise * (double)(nfit - (3 * L + 1)));
     const double FWHM_COEFF = 2.3548200450309493;
     const double SQ2PI = 2.5066282746310002, PI = 3.141592653589793;
-    float row[7 * L + 5];
-#pragma unroll
-    for (int k = 0; k < L; ++k) {
-        double Ak = A[k] * pr.scale, s = sg[k], pk = p[k];
-        double uA = unc ? unc[3 * k] * pr.scale : 0.0, up = unc ? unc[3 * k + 1] : 0.0, us = unc ? unc[3 * k + 2] : 0.0;
+    for (int k = w.lane; k < L; k += LANES) {
+        double Ak = apd[k] * scale, s = apd[2 * L + k], pk = apd[L + k];
+        double uA = unc ? unc[3 * k] * scale : 0.0, up = unc ? unc[3 * k + 1] : 0.0, us = unc ? unc[3 * k + 2] : 0.0;
         double flux, ferr;
         if (MODEL == LF_GAUSSIAN) {
             flux = (1.20671 / FWHM_COEFF) * SQ2PI * Ak * s;
             ferr = flux * sqrt((uA / Ak) * (uA / Ak) + (us / s) * (us / s));
         } else if (MODEL == LF_SINC) {
-            flux = PI * sqrt(PI) * Ak * pr.sinc_w;
+            flux = PI * sqrt(PI) * Ak * sinc_w_d;
             ferr = flux * sqrt((uA / Ak) * (uA / Ak) + (us / s) * (us / s));
         } else {
-            double c0 = 1.4142135623730951 * pr.sinc_w;
+            double c0 = 1.4142135623730951 * sinc_w_d;
             double ef = erf(s / c0);
             flux = (1.20671 / (PI * FWHM_COEFF)) * Ak * (SQ2PI * s / ef);
             double t = ef - (2.0 * PI) / (sqrt(PI) * c0) * exp(-s * s / (c0 * c0));
@@ -710,217 +898,176 @@ LF_CORE void lf_outputs(const LfCfg& cfg, const LfWarp<LANES>& w, const float* x
         double verr = 299792.0 * up * (1e7 / (lam * pk * pk));                  // :57
         double broad = pk > 0 ? fabs(299792.0 * s / pk) : 0.0;                  // :82-88
         double berr = (pk > 0 && s > 0) ? (299792.0 * s / pk) * sqrt((us / s) * (us / s) + (up / pk) * (up / pk)) : 0.0;
-        row[k] = (float)Ak; row[L + k] = (float)flux; row[2 * L + k] = (float)ferr;
-        row[3 * L + k] = (float)v; row[4 * L + k] = (float)verr;
-        row[5 * L + k] = (float)broad; row[6 * L + k] = (float)berr;
+        out_row[k] = (float)Ak; out_row[L + k] = (float)flux; out_row[2 * L + k] = (float)ferr;
+        out_row[3 * L + k] = (float)v; out_row[4 * L + k] = (float)verr;
+        out_row[5 * L + k] = (float)broad; out_row[6 * L + k] = (float)berr;
+        if (out_sol) { out_sol[3 * k] = (float)Ak; out_sol[3 * k + 1] = (float)pk; out_sol[3 * k + 2] = (float)s; }
     }
-    row[7 * L] = (float)chi2;
-    row[7 * L + 1] = (float)pr.corr;
-    row[7 * L + 2] = (float)pr.sinc_w;             // axis_step == sinc_width (LuciFit.py:214-215, 222-223)
-    row[7 * L + 3] = (float)(cont * pr.scale);
-    row[7 * L + 4] = (float)(unc ? unc[3 * L] * pr.scale : 0.0);
-#pragma unroll
-    for (int j = 0; j < 7 * L + 5; ++j) if (LANES == 1 || (j % LANES) == w.lane) out_row[j] = row[j];
-    if (out_sol) {
-#pragma unroll
-        for (int k = 0; k < L; ++k) {
-            if (w.lane == 0) {
-                out_sol[3 * k] = (float)(A[k] * pr.scale);
-                out_sol[3 * k + 1] = (float)p[k];
-                out_sol[3 * k + 2] = (float)sg[k];
-            }
-        }
-        if (w.lane == 0) out_sol[3 * L] = (float)(cont * pr.scale);
+    if (w.lane == 0) {
+        out_row[7 * L] = (float)chi2;
+        out_row[7 * L + 1] = (float)corr;
+        out_row[7 * L + 2] = (float)sinc_w_d;          // axis_step == sinc_width (LuciFit.py:214-215, 222-223)
+        out_row[7 * L + 3] = (float)(cont * scale);
+        out_row[7 * L + 4] = (float)(unc ? unc[3 * L] * scale : 0.0);
+        if (out_sol) out_sol[3 * L] = (float)(cont * scale);
+        *out_status = status;
     }
     if (out_unc) {
         for (int j = w.lane; j < 3 * L + 1; j += LANES) {
             double u = unc ? unc[j] : 0.0;
-            if (j == 3 * L || (j % 3) == 0) u *= pr.scale;
+            if (j == 3 * L || (j % 3) == 0) u *= scale;
             out_unc[j] = (float)u;
         }
     }
+    w.sync();
 }
 
-// Per-warp scratch layout (bytes), after the nz-float spectrum buffer.
-struct LfScratch {
-    double* dvals;            // LF_MAX_CONT_WIN
-    double* ddev;             // LF_MAX_CONT_WIN
-    unsigned char* alive;     // LF_MAX_CONT_WIN
-    float* st;                // NH + P   (stash of the normal equations)
-    double* hess;             // (3L+1)^2 + 2(3L+1)  (uncertainty stage)
-    float* tile;              // LANES x (3L+2)       (uncertainty stage)
-};
-
-template <int MODEL, int L, int NV, int NS, int LANES>
-LF_CORE void lf_uncertainty(const LfCfg& cfg, const LfWarp<LANES>& w, const float* xo, const float* spec, const LfPrep& pr,
-                            const float (&th)[LfDims<MODEL, L, NV, NS>::P], const LfScratch& sc, double* unc);
-
-// The whole pipeline for one spaxel.
-template <int MODEL, int L, int NV, int NS, int LANES>
-LF_CORE void lf_fit_spaxel(const LfCfg& cfg, const LfWarp<LANES>& w, const float* xo, const float* gspec, float theta_deg,
-                           float vel0, float broad0, float* spec, const LfScratch& sc,
-                           float* out_row, int32_t* out_status, float* out_sol, float* out_unc)
-{
-    typedef LfDims<MODEL, L, NV, NS> D;
-    LfPrep pr;
-    lf_prep(cfg, w, gspec, theta_deg, spec, sc.dvals, sc.ddev, sc.alive, pr);
-    if (pr.bad) {                                      // reference returns zeros for unusable spectra
-        for (int j = w.lane; j < 7 * L + 5; j += LANES) out_row[j] = 0.0f;
-        if (out_sol) for (int j = w.lane; j < 3 * L + 1; j += LANES) out_sol[j] = 0.0f;
-        if (out_unc) for (int j = w.lane; j < 3 * L + 1; j += LANES) out_unc[j] = 0.0f;
-        if (w.lane == 0) *out_status = pr.bad;
-        return;
-    }
-    // initial vector (LuciFit.py:663-672, 410-423): amplitude = max over +-5 channels around the expected
-    // centre minus the continuum guess; centres from the prior velocity; sigma from the prior broadening.
-    float th[D::P];
-    if (vel0 != vel0) vel0 = 0.0f;                     // LuciFit.py:406-409
-    if (broad0 != broad0) broad0 = 1.0f;
-    broad0 = fabsf(broad0);
-#pragma unroll
-    for (int k = 0; k < L; ++k) {
-        double lam = cfg.line_nm[k];
-        double pos = 1e7 / (((double)vel0 / 299792.0) * lam + lam);
-        int ind = lf_argmin_axis(w, cfg.axis, cfg.nz, pos);
-        float amp;
-        if (ind + 5 > cfg.nz - 1) {
-            amp = spec[ind];                           // IndexError branch (LuciFit.py:420-421)
-        } else {
-            amp = -INFINITY;
-            for (int d = -5; d <= 5; ++d) { int i = ind + d; if (i < 0) i += cfg.nz; amp = fmaxf(amp, spec[i]); }
-        }
-        th[k] = (float)((double)amp / (double)pr.smax - pr.cont0);
-    }
-#pragma unroll
-    for (int g = 0; g < NV; ++g) th[D::IV + g] = vel0;
-#pragma unroll
-    for (int h = 0; h < NS; ++h) th[D::IS + h] = broad0;
-    th[D::IC] = (float)pr.cont0;
-    LfFitResult res;
-    lf_lm<MODEL, L, NV, NS, LANES>(cfg, w, xo, spec, pr.inv_wmax, (float)pr.sinc_w, th, sc.st, res);
-    const double* unc = 0;
-    if (cfg.uncertainty) {
-        lf_uncertainty<MODEL, L, NV, NS, LANES>(cfg, w, xo, spec, pr, th, sc, sc.hess + (3 * L + 1) * (3 * L + 1));
-        unc = sc.hess + (3 * L + 1) * (3 * L + 1);
-    }
-    lf_outputs<MODEL, L, NV, NS, LANES>(cfg, w, xo, spec, pr, th, unc, out_row, out_sol, out_unc);
-    int st = (res.iters & 0xff) | ((res.evals & 0xff) << 8) | res.flags;
-    if (w.lane == 0) *out_status = st;
-}
-
-// ------------------------------------------------------------------------------------------ uncertainties
+// ----------------------------------------------------------------------------------------------- stage: unc
 // 1-sigma errors exactly as the reference defines them (LuciFit.py:713-722, LuciUtility.py:409-434): finite
 // difference Hessian of the nll with delta = 0.1 on ALL 3L+1 unconstrained parameters [A, p, sigma]*L + [c]
 // (normalised units), unc = sqrt(|diag(-(H/2)^-1)|).  The 4 (3L+1)^2 objective calls of hessianComp are
 // restructured using the additivity of the model over lines: for i, j in different lines
 // H_ij = sum D_i D_j / noise^2 with D_i the central difference of the line profile; inside a line the exact
 // second-difference expressions are accumulated.  13 unit-profile evaluations per line and sample.
-struct LfLineVar { LfLine v[13]; };
 // variant order: 0 (p,s) 1 (p+d,s) 2 (p-d,s) 3 (p,s+d) 4 (p,s-d) 5 (p+2d,s) 6 (p-2d,s) 7 (p,s+2d) 8 (p,s-2d)
 //                9 (p+d,s+d) 10 (p+d,s-d) 11 (p-d,s+d) 12 (p-d,s-d)
+LF_HD float lf_var_dp(int v)
+{
+    return (v == 1 || v == 9 || v == 10) ? 0.1f : (v == 2 || v == 11 || v == 12) ? -0.1f : v == 5 ? 0.2f : v == 6 ? -0.2f : 0.0f;
+}
+LF_HD float lf_var_ds(int v)
+{
+    return (v == 3 || v == 9 || v == 11) ? 0.1f : (v == 4 || v == 10 || v == 12) ? -0.1f : v == 7 ? 0.2f : v == 8 ? -0.2f : 0.0f;
+}
+
 template <int MODEL, int L, int NV, int NS, int LANES>
-LF_CORE void lf_uncertainty(const LfCfg& cfg, const LfWarp<LANES>& w, const float* xo, const float* spec, const LfPrep& pr,
-                            const float (&th)[LfDims<MODEL, L, NV, NS>::P], const LfScratch& sc, double* unc)
+LF_CORE void lf_stage_unc(const LfCfg& cfg, const LfWarp<LANES>& w, const float* xo, const float* gspec, const LfWork& wk,
+                          const float* state, double* unc)
 {
     typedef LfDims<MODEL, L, NV, NS> D;
     constexpr int PF = 3 * L + 1;
     constexpr int STRIDE = PF | 1;
     constexpr int NE = PF * (PF + 1) / 2;
     constexpr int SLOTS = (NE + LANES - 1) / LANES;
-    const float sinc_w = (float)pr.sinc_w;
+    const int status = reinterpret_cast<const int*>(state)[LF_SO_STATUS];
+    if (status & LF_ST_BADMASK) return;
+    const double* sd = reinterpret_cast<const double*>(state);
+    const double noise = sd[LF_SO_NOISE / 2], sinc_w_d = sd[LF_SO_SINCW / 2];
+    const float sinc_w = (float)sinc_w_d;
+    const double inv_w = 1.0 / sinc_w_d;
+    const float* th = state + LF_SO_TH;
     const float dl = 0.1f;
-    double A[L], p[L], sg[L], vel[L], beta[L];
-    lf_expand<MODEL, L, NV, NS>(cfg, sinc_w, th, A, p, sg, vel, beta);
-    // line set-ups of all variants: built lane-parallel into per-warp scratch (tile area is big enough: see host)
-    LfLine* lines = reinterpret_cast<LfLine*>(sc.hess);    // 13 L structs (hess is reused afterwards -> copy out first)
-    const float dp_[13] = {0, dl, -dl, 0, 0, 2 * dl, -2 * dl, 0, 0, dl, dl, -dl, -dl};
-    const float ds_[13] = {0, 0, 0, dl, -dl, 0, 0, 2 * dl, -2 * dl, dl, -dl, dl, -dl};
+    const int nfit = cfg.fit_hi - cfg.fit_lo;
+    lf_stage_window<MODEL, LANES>(cfg, w, xo, gspec, state[LF_SO_INVW], false, sinc_w_d, wk);
+    double* apd = wk.apd;
+    lf_expand<MODEL, L, NV, NS, LANES>(cfg, w, sinc_w, th, apd);
+    // line set-ups of all variants, built lane-parallel
+    LfLineX* lines = wk.lines;
     for (int e = w.lane; e < 13 * L; e += LANES) {
         int k = e / 13, v = e % 13;
         float pp, pl;
-        lf_split(p[k] - cfg.x_ref, pp, pl);
-        float s = (float)sg[k] + ds_[v];
-        LfLine t;
-        lf_line_setup(MODEL, pp, pl - dp_[v], s, sinc_w, t);
-        lines[e] = t;
+        lf_split(apd[L + k] - cfg.x_ref, pp, pl);
+        float s = (float)apd[2 * L + k] + lf_var_ds(v);
+        LfLineX x;
+        lf_line_setup(MODEL, pp, pl - lf_var_dp(v), s, sinc_w, x.ln);
+        x.aeff = (float)apd[k];
+        x.dpdv = x.dsdv = x.dsdb = 0.0f; x.vg = x.sg = 0; x.p = x.beta = 0.0f;
+        x.ck = 1.0f; x.sk = 0.0f;
+        if (MODEL != LF_GAUSSIAN) lf_phase(((double)x.ln.pp + (double)x.ln.dp) * inv_w, x.sk, x.ck);
+        lines[e] = x;
     }
     w.sync();
-    const float piw = LF_PI_F / sinc_w, iw = 1.0f / sinc_w;
-    const int nfit = cfg.fit_hi - cfg.fit_lo;
-    const float* y = spec + cfg.fit_lo;
+    const float iw = 1.0f / sinc_w;
     const float cont = th[D::IC];
     float gram[SLOTS];
 #pragma unroll
     for (int s = 0; s < SLOTS; ++s) gram[s] = 0.0f;
-    float sAp[L], sAs[L], spp[L], sss[L], sps[L];
-#pragma unroll
-    for (int k = 0; k < L; ++k) sAp[k] = sAs[k] = spp[k] = sss[k] = sps[k] = 0.0f;
-    float* tile = sc.tile;
+    // per-line second-difference sums: [5][L] per lane, kept in per-warp memory (rolled line loop)
+    float* sums = wk.gt + 13 * LANES;                  // [5 L][LANES]
+    for (int e = 0; e < 5 * L; ++e) sums[e * LANES + w.lane] = 0.0f;
+    float* tile = wk.tile;
+    float* gvt = wk.gt;                                // [13][LANES]
     for (int n0 = 0; n0 < nfit; n0 += LANES) {
-        int n = n0 + w.lane;
-        bool live = n < nfit;
-        float x = live ? xo[n] : 0.0f;
-        float yn = live ? y[n] * pr.inv_wmax : 0.0f;
-        float g0[L];
-        float m = cont;
-#pragma unroll
-        for (int k = 0; k < L; ++k) {
-            const LfLine& l0 = lines[13 * k];
-            float dx = lf_dx(l0, x);
-            bool far = false;
-            if (MODEL == LF_SINCGAUSS) far = w.all(lf_is_far(l0, dx));
-            float gp, gs;
-            lf_profile<MODEL>(l0, dx, piw, iw, far, g0[k], gp, gs);
-            m += (float)A[k] * g0[k];
-        }
-        float r0 = yn - m;
+        const int n = n0 + w.lane;
+        const bool live = n < nfit;
+        const float x = live ? xo[n] : 0.0f;
+        const float yn = live ? wk.yw[n] : 0.0f;
+        float Sx = 0.0f, Cx = 1.0f;
+        if (MODEL != LF_GAUSSIAN && live) { Sx = wk.sw[n]; Cx = wk.cw[n]; }
         float* trow = tile + w.lane * STRIDE;
-#pragma unroll
+        // pass 1: model value at the solution (residual r0) and the unit profiles g0
+        float m = cont;
+#pragma unroll 1
         for (int k = 0; k < L; ++k) {
-            float Ak = (float)A[k];
-            float gv[13];
-            gv[0] = g0[k];
-#pragma unroll
+            const LfLineX& X = lines[13 * k];
+            const float dx = lf_dx(X.ln, x);
+            bool far = false;
+            if (MODEL == LF_SINCGAUSS) far = w.all(lf_is_far(X.ln, dx));
+            float s = 0.0f, c = 1.0f;
+            if (MODEL != LF_GAUSSIAN) { s = Sx * X.ck - Cx * X.sk; c = Cx * X.ck + Sx * X.sk; }
+            float g, gp, gs;
+            lf_profile_sc<MODEL>(X.ln, dx, s, c, iw, far, g, gp, gs);
+            trow[3 * k] = live ? g : 0.0f;
+            m += X.aeff * g;
+        }
+        const float r0 = yn - m;
+        // pass 2: the 12 shifted variants of every line
+#pragma unroll 1
+        for (int k = 0; k < L; ++k) {
+            const float Ak = lines[13 * k].aeff;
+            const float g0 = trow[3 * k];
+            gvt[w.lane] = g0;
+#pragma unroll 1
             for (int v = 1; v < 13; ++v) {
-                if (MODEL == LF_SINC && ds_[v] != 0.0f) { gv[v] = (dp_[v] == 0.0f) ? g0[k] : 0.0f; continue; }
-                const LfLine& lv = lines[13 * k + v];
-                float dx = lf_dx(lv, x);
-                bool far = false;
-                if (MODEL == LF_SINCGAUSS) far = w.all(lf_is_far(lv, dx));
-                float gp, gs;
-                lf_profile<MODEL>(lv, dx, piw, iw, far, gv[v], gp, gs);
+                float gv;
+                if (MODEL == LF_SINC && lf_var_ds(v) != 0.0f) {
+                    gv = (lf_var_dp(v) == 0.0f) ? g0 : 0.0f;            // filled from variants 1 / 2 below
+                } else {
+                    const LfLineX& X = lines[13 * k + v];
+                    const float dx = lf_dx(X.ln, x);
+                    bool far = false;
+                    if (MODEL == LF_SINCGAUSS) far = w.all(lf_is_far(X.ln, dx));
+                    float s = 0.0f, c = 1.0f;
+                    if (MODEL != LF_GAUSSIAN) { s = Sx * X.ck - Cx * X.sk; c = Cx * X.ck + Sx * X.sk; }
+                    float gp, gs;
+                    lf_profile_sc<MODEL>(X.ln, dx, s, c, iw, far, gv, gp, gs);
+                }
+                gvt[v * LANES + w.lane] = gv;
             }
+            float gv[13];
+#pragma unroll
+            for (int v = 0; v < 13; ++v) gv[v] = gvt[v * LANES + w.lane];
             if (MODEL == LF_SINC) { gv[9] = gv[10] = gv[1]; gv[11] = gv[12] = gv[2]; }
-            float Dp = Ak * (gv[1] - gv[2]) * (0.5f / dl);
-            float Ds = Ak * (gv[3] - gv[4]) * (0.5f / dl);
-            trow[3 * k] = live ? g0[k] : 0.0f;
+            const float Dp = Ak * (gv[1] - gv[2]) * (0.5f / dl);
+            const float Ds = Ak * (gv[3] - gv[4]) * (0.5f / dl);
             trow[3 * k + 1] = live ? Dp : 0.0f;
             trow[3 * k + 2] = live ? Ds : 0.0f;
             if (live) {
-                float base = Ak * g0[k];
+                const float base = Ak * g0;
+                float* sk_ = sums + (5 * k) * LANES + w.lane;
                 // (A, p): D^{s,t} = (A + s d) g(p + t d) - A g0
                 {
                     float a = (Ak + dl) * gv[1] - base, b = (Ak + dl) * gv[2] - base;
                     float c = (Ak - dl) * gv[1] - base, d = (Ak - dl) * gv[2] - base;
-                    sAp[k] += a * a - b * b - c * c + d * d - 2.0f * r0 * (a - b - c + d);
+                    sk_[0] += a * a - b * b - c * c + d * d - 2.0f * r0 * (a - b - c + d);
                 }
                 {
                     float a = (Ak + dl) * gv[3] - base, b = (Ak + dl) * gv[4] - base;
                     float c = (Ak - dl) * gv[3] - base, d = (Ak - dl) * gv[4] - base;
-                    sAs[k] += a * a - b * b - c * c + d * d - 2.0f * r0 * (a - b - c + d);
+                    sk_[LANES] += a * a - b * b - c * c + d * d - 2.0f * r0 * (a - b - c + d);
                 }
                 {
-                    float a = Ak * (gv[5] - g0[k]), b = Ak * (gv[6] - g0[k]);
-                    spp[k] += a * a + b * b - 2.0f * r0 * (a + b);
+                    float a = Ak * (gv[5] - g0), b = Ak * (gv[6] - g0);
+                    sk_[2 * LANES] += a * a + b * b - 2.0f * r0 * (a + b);
                 }
                 {
-                    float a = Ak * (gv[7] - g0[k]), b = Ak * (gv[8] - g0[k]);
-                    sss[k] += a * a + b * b - 2.0f * r0 * (a + b);
+                    float a = Ak * (gv[7] - g0), b = Ak * (gv[8] - g0);
+                    sk_[3 * LANES] += a * a + b * b - 2.0f * r0 * (a + b);
                 }
                 {
-                    float a = Ak * (gv[9] - g0[k]), b = Ak * (gv[10] - g0[k]);
-                    float c = Ak * (gv[11] - g0[k]), d = Ak * (gv[12] - g0[k]);
-                    sps[k] += a * a - b * b - c * c + d * d - 2.0f * r0 * (a - b - c + d);
+                    float a = Ak * (gv[9] - g0), b = Ak * (gv[10] - g0);
+                    float c = Ak * (gv[11] - g0), d = Ak * (gv[12] - g0);
+                    sk_[4 * LANES] += a * a - b * b - c * c + d * d - 2.0f * r0 * (a - b - c + d);
                 }
             }
         }
@@ -942,9 +1089,9 @@ LF_CORE void lf_uncertainty(const LfCfg& cfg, const LfWarp<LANES>& w, const floa
         w.sync();
     }
     // assemble H (double) in scratch
-    double noise2 = pr.noise * pr.noise;
+    double noise2 = noise * noise;
     if (!(noise2 == noise2)) noise2 = 1e-2;                       // LuciFit.py:514-515
-    double* Hm = sc.hess;
+    double* Hm = wk.hess;
     w.sync();
 #pragma unroll
     for (int s = 0; s < SLOTS; ++s) {
@@ -959,10 +1106,11 @@ LF_CORE void lf_uncertainty(const LfCfg& cfg, const LfWarp<LANES>& w, const floa
     }
     w.sync();
     const double f8 = 1.0 / (8.0 * (double)dl * (double)dl * noise2);
-#pragma unroll
+#pragma unroll 1
     for (int k = 0; k < L; ++k) {
-        double vAp = (double)w.sum(sAp[k]) * f8, vAs = (double)w.sum(sAs[k]) * f8;
-        double vpp = (double)w.sum(spp[k]) * f8, vss = (double)w.sum(sss[k]) * f8, vps = (double)w.sum(sps[k]) * f8;
+        const float* sk_ = sums + (5 * k) * LANES + w.lane;
+        double vAp = (double)w.sum(sk_[0]) * f8, vAs = (double)w.sum(sk_[LANES]) * f8;
+        double vpp = (double)w.sum(sk_[2 * LANES]) * f8, vss = (double)w.sum(sk_[3 * LANES]) * f8, vps = (double)w.sum(sk_[4 * LANES]) * f8;
         if (w.lane == 0) {
             int a = 3 * k, b = 3 * k + 1, c = 3 * k + 2;
             Hm[a * PF + b] = Hm[b * PF + a] = vAp;
@@ -978,7 +1126,8 @@ LF_CORE void lf_uncertainty(const LfCfg& cfg, const LfWarp<LANES>& w, const floa
     }
     w.sync();
     // in-place Gauss-Jordan inverse with row pivoting
-    int* piv = reinterpret_cast<int*>(unc + PF);                  // PF ints after the unc vector
+    double* uv = Hm + PF * PF;                                     // PF doubles, then PF ints of pivots
+    int* piv = reinterpret_cast<int*>(uv + PF);
     bool singular = false;
     for (int c = 0; c < PF; ++c) {
         double best = 1e300; int bi = 0x7fffffff;
@@ -1016,4 +1165,53 @@ LF_CORE void lf_uncertainty(const LfCfg& cfg, const LfWarp<LANES>& w, const floa
         unc[j] = u;
     }
     w.sync();
+}
+
+// ------------------------------------------------------------------------------------ per-warp scratch layout
+// Byte offsets inside one warp's scratch area, per stage (computed on the host by lf_make_plan; the test harness
+// uses the same layout with LANES = 1).  Offset 0 is `spec` (prep) or `yw` (lm / unc / out).
+struct LfLayout {
+    int lanes;
+    int npad;                                              // continuum window padded to a power of two
+    int prep_sortv, prep_sortd, prep_bytes;
+    int lm_sw, lm_cw, lm_lines, lm_tie, lm_gt, lm_hb, lm_thb, lm_bytes;
+    int un_sw, un_cw, un_lines, un_apd, un_gt, un_tile, un_hess, un_bytes;
+    int out_sw, out_cw, out_lines, out_apd, out_bytes;
+};
+
+enum { LF_STAGE_PREP = 0, LF_STAGE_LM = 1, LF_STAGE_UNC = 2, LF_STAGE_OUT = 3 };
+
+LF_CORE LfWork lf_work_at(int stage, const LfLayout& ly, unsigned char* base)
+{
+    LfWork wk;
+    wk.spec = reinterpret_cast<float*>(base);
+    wk.yw = reinterpret_cast<float*>(base);
+    wk.sortv = 0; wk.sortd = 0; wk.npad = ly.npad;
+    wk.sw = 0; wk.cw = 0; wk.lines = 0; wk.tie = 0; wk.gt = 0; wk.hb = 0; wk.thb = 0; wk.apd = 0; wk.tile = 0; wk.hess = 0;
+    if (stage == LF_STAGE_PREP) {
+        wk.sortv = reinterpret_cast<double*>(base + ly.prep_sortv);
+        wk.sortd = reinterpret_cast<double*>(base + ly.prep_sortd);
+    } else if (stage == LF_STAGE_LM) {
+        wk.sw = reinterpret_cast<float*>(base + ly.lm_sw);
+        wk.cw = reinterpret_cast<float*>(base + ly.lm_cw);
+        wk.lines = reinterpret_cast<LfLineX*>(base + ly.lm_lines);
+        wk.tie = reinterpret_cast<LfTieX*>(base + ly.lm_tie);
+        wk.gt = reinterpret_cast<float*>(base + ly.lm_gt);
+        wk.hb = reinterpret_cast<float*>(base + ly.lm_hb);
+        wk.thb = reinterpret_cast<float*>(base + ly.lm_thb);
+    } else if (stage == LF_STAGE_UNC) {
+        wk.sw = reinterpret_cast<float*>(base + ly.un_sw);
+        wk.cw = reinterpret_cast<float*>(base + ly.un_cw);
+        wk.lines = reinterpret_cast<LfLineX*>(base + ly.un_lines);
+        wk.apd = reinterpret_cast<double*>(base + ly.un_apd);
+        wk.gt = reinterpret_cast<float*>(base + ly.un_gt);
+        wk.tile = reinterpret_cast<float*>(base + ly.un_tile);
+        wk.hess = reinterpret_cast<double*>(base + ly.un_hess);
+    } else {
+        wk.sw = reinterpret_cast<float*>(base + ly.out_sw);
+        wk.cw = reinterpret_cast<float*>(base + ly.out_cw);
+        wk.lines = reinterpret_cast<LfLineX*>(base + ly.out_lines);
+        wk.apd = reinterpret_cast<double*>(base + ly.out_apd);
+    }
+    return wk;
 }

@@ -1,15 +1,22 @@
-// lucifit_fit_kernel.cuh -- the fused per-spaxel kernel (one warp per spaxel) and its launcher.
+// lucifit_fit_kernel.cuh -- the four stage kernels of the fit path (one warp per spaxel, grid-stride over the
+// slice) and their launcher.  Each kernel keeps one small hot loop resident in the SM's instruction cache; a spaxel
+// travels between them as a state record in the caller's workspace (lucifit_core.cuh, LF_SO_*).
 #pragma once
 #include <cuda_runtime.h>
 #include "lucifit_core.cuh"
 
-#define LF_WARPS_PER_BLOCK 8
+#define LF_PREP_WARPS 8
+#define LF_LM_WARPS 4
+#define LF_UNC_WARPS 4
+#define LF_OUT_WARPS 8
 
 struct LfLaunch {
     LfCfg cfg;
-    long long n;
+    LfLayout ly;
+    long long n;                 // spaxels of this slice
     const float* cube;
-    const long long* index;
+    const long long* index;      // already offset to the slice, or null
+    long long index_base;        // row of the slice's first spaxel when index is null
     const float* theta;
     const float* vel0;
     const float* broad0;
@@ -17,59 +24,124 @@ struct LfLaunch {
     float* out_sol;
     float* out_unc;
     int* status;
-    int off_u, off_v, per_warp, cont_cap, xo_bytes;   // shared-memory layout (bytes)
+    float* state;                // [n][cfg.state_floats]
+    double* unc_ws;              // [n][3L+1] or null
+    int xo_bytes;
     cudaStream_t stream;
     int sm_count;
 };
 typedef cudaError_t (*lf_launch_fn)(const LfLaunch&);
 
-template <int MODEL, int L, int NG>
-__global__ void __launch_bounds__(LF_WARPS_PER_BLOCK * 32, 2)
-lf_fit_kernel(const __grid_constant__ LfLaunch a)
+__device__ __forceinline__ const float* lf_stage_xo(const LfLaunch& a, unsigned char* smem)
 {
-    extern __shared__ __align__(16) unsigned char lf_smem[];
-    float* xo_s = reinterpret_cast<float*>(lf_smem);
+    float* xo_s = reinterpret_cast<float*>(smem);
     const int nfit = a.cfg.fit_hi - a.cfg.fit_lo;
     for (int i = threadIdx.x; i < nfit; i += blockDim.x) xo_s[i] = a.cfg.xo[i];
     __syncthreads();
+    return xo_s;
+}
+
+template <int MODEL, int L, int NG>
+__global__ void __launch_bounds__(LF_PREP_WARPS * 32)
+lf_prep_kernel(const __grid_constant__ LfLaunch a)
+{
+    extern __shared__ __align__(16) unsigned char lf_smem[];
     const int warp = threadIdx.x >> 5;
-    unsigned char* base = lf_smem + a.xo_bytes + (size_t)warp * a.per_warp;
-    float* spec = reinterpret_cast<float*>(base);
-    LfScratch sc;
-    sc.dvals = reinterpret_cast<double*>(base + a.off_u);
-    sc.ddev = sc.dvals + a.cont_cap;
-    sc.alive = reinterpret_cast<unsigned char*>(sc.ddev + a.cont_cap);
-    sc.hess = reinterpret_cast<double*>(base + a.off_u);
-    sc.st = reinterpret_cast<float*>(base + a.off_v);
-    sc.tile = sc.st;
+    LfWork wk = lf_work_at(LF_STAGE_PREP, a.ly, lf_smem + (size_t)warp * a.ly.prep_bytes);
     LfWarp<32> w;
-    constexpr int K = 7 * L + 5, PF = 3 * L + 1;
-    const long long stride = (long long)gridDim.x * LF_WARPS_PER_BLOCK;
-    for (long long s = (long long)blockIdx.x * LF_WARPS_PER_BLOCK + warp; s < a.n; s += stride) {
-        long long row = a.index ? a.index[s] : s;
-        lf_fit_spaxel<MODEL, L, NG, NG, 32>(a.cfg, w, xo_s, a.cube + row * (long long)a.cfg.nz, a.theta[s],
-                                            a.vel0 ? a.vel0[s] : 0.0f, a.broad0 ? a.broad0[s] : 0.0f, spec, sc,
-                                            a.out_rows + s * K, a.status + s, a.out_sol ? a.out_sol + s * PF : nullptr,
-                                            a.out_unc ? a.out_unc + s * PF : nullptr);
-        __syncwarp();
+    const long long stride = (long long)gridDim.x * LF_PREP_WARPS;
+    for (long long s = (long long)blockIdx.x * LF_PREP_WARPS + warp; s < a.n; s += stride) {
+        const long long row = a.index ? a.index[s] : a.index_base + s;
+        lf_stage_prep<MODEL, L, NG, NG, 32>(a.cfg, w, a.cube + row * (long long)a.cfg.nz, a.theta[s],
+                                            a.vel0 ? a.vel0[s] : 0.0f, a.broad0 ? a.broad0[s] : 0.0f, wk,
+                                            a.state + s * (long long)a.cfg.state_floats);
     }
 }
 
 template <int MODEL, int L, int NG>
-cudaError_t lf_launch(const LfLaunch& a)
+__global__ void __launch_bounds__(LF_LM_WARPS * 32)
+lf_lm_kernel(const __grid_constant__ LfLaunch a)
 {
-    auto kern = lf_fit_kernel<MODEL, L, NG>;
-    size_t smem = (size_t)a.xo_bytes + (size_t)LF_WARPS_PER_BLOCK * a.per_warp;
+    extern __shared__ __align__(16) unsigned char lf_smem[];
+    const float* xo_s = lf_stage_xo(a, lf_smem);
+    const int warp = threadIdx.x >> 5;
+    LfWork wk = lf_work_at(LF_STAGE_LM, a.ly, lf_smem + a.xo_bytes + (size_t)warp * a.ly.lm_bytes);
+    LfWarp<32> w;
+    const long long stride = (long long)gridDim.x * LF_LM_WARPS;
+    for (long long s = (long long)blockIdx.x * LF_LM_WARPS + warp; s < a.n; s += stride) {
+        const long long row = a.index ? a.index[s] : a.index_base + s;
+        lf_stage_lm<MODEL, L, NG, NG, 32>(a.cfg, w, xo_s, a.cube + row * (long long)a.cfg.nz, wk,
+                                          a.state + s * (long long)a.cfg.state_floats);
+    }
+}
+
+template <int MODEL, int L, int NG>
+__global__ void __launch_bounds__(LF_UNC_WARPS * 32)
+lf_unc_kernel(const __grid_constant__ LfLaunch a)
+{
+    extern __shared__ __align__(16) unsigned char lf_smem[];
+    const float* xo_s = lf_stage_xo(a, lf_smem);
+    const int warp = threadIdx.x >> 5;
+    LfWork wk = lf_work_at(LF_STAGE_UNC, a.ly, lf_smem + a.xo_bytes + (size_t)warp * a.ly.un_bytes);
+    LfWarp<32> w;
+    const long long stride = (long long)gridDim.x * LF_UNC_WARPS;
+    for (long long s = (long long)blockIdx.x * LF_UNC_WARPS + warp; s < a.n; s += stride) {
+        const long long row = a.index ? a.index[s] : a.index_base + s;
+        lf_stage_unc<MODEL, L, NG, NG, 32>(a.cfg, w, xo_s, a.cube + row * (long long)a.cfg.nz, wk,
+                                           a.state + s * (long long)a.cfg.state_floats, a.unc_ws + s * (3 * L + 1));
+    }
+}
+
+template <int MODEL, int L, int NG>
+__global__ void __launch_bounds__(LF_OUT_WARPS * 32)
+lf_out_kernel(const __grid_constant__ LfLaunch a)
+{
+    extern __shared__ __align__(16) unsigned char lf_smem[];
+    const float* xo_s = lf_stage_xo(a, lf_smem);
+    const int warp = threadIdx.x >> 5;
+    LfWork wk = lf_work_at(LF_STAGE_OUT, a.ly, lf_smem + a.xo_bytes + (size_t)warp * a.ly.out_bytes);
+    LfWarp<32> w;
+    constexpr int K = 7 * L + 5, PF = 3 * L + 1;
+    const long long stride = (long long)gridDim.x * LF_OUT_WARPS;
+    for (long long s = (long long)blockIdx.x * LF_OUT_WARPS + warp; s < a.n; s += stride) {
+        const long long row = a.index ? a.index[s] : a.index_base + s;
+        lf_stage_out<MODEL, L, NG, NG, 32>(a.cfg, w, xo_s, a.cube + row * (long long)a.cfg.nz, wk,
+                                           a.state + s * (long long)a.cfg.state_floats,
+                                           a.unc_ws ? a.unc_ws + s * PF : nullptr, a.out_rows + s * K, a.status + s,
+                                           a.out_sol ? a.out_sol + s * PF : nullptr,
+                                           a.out_unc ? a.out_unc + s * PF : nullptr);
+    }
+}
+
+template <typename K>
+static cudaError_t lf_launch_one(K kern, const LfLaunch& a, int warps, size_t smem)
+{
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     int occ = 0;
-    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, LF_WARPS_PER_BLOCK * 32, smem);
+    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, warps * 32, smem);
     if (e != cudaSuccess) return e;
     if (occ < 1) return cudaErrorLaunchOutOfResources;
-    long long want = (a.n + LF_WARPS_PER_BLOCK - 1) / LF_WARPS_PER_BLOCK;
-    long long cap = (long long)a.sm_count * occ;
+    long long want = (a.n + warps - 1) / warps;
+    long long cap = (long long)a.sm_count * occ;          // one resident wave, grid-stride inside
     int grid = (int)(want < cap ? want : cap);
     if (grid < 1) grid = 1;
-    kern<<<grid, LF_WARPS_PER_BLOCK * 32, smem, a.stream>>>(a);
+    kern<<<grid, warps * 32, smem, a.stream>>>(a);
     return cudaGetLastError();
+}
+
+// Enqueues prep -> lm -> [unc] -> out for one slice.
+template <int MODEL, int L, int NG>
+cudaError_t lf_launch(const LfLaunch& a)
+{
+    cudaError_t e;
+    e = lf_launch_one(lf_prep_kernel<MODEL, L, NG>, a, LF_PREP_WARPS, (size_t)LF_PREP_WARPS * a.ly.prep_bytes);
+    if (e != cudaSuccess) return e;
+    e = lf_launch_one(lf_lm_kernel<MODEL, L, NG>, a, LF_LM_WARPS, (size_t)a.xo_bytes + (size_t)LF_LM_WARPS * a.ly.lm_bytes);
+    if (e != cudaSuccess) return e;
+    if (a.unc_ws) {
+        e = lf_launch_one(lf_unc_kernel<MODEL, L, NG>, a, LF_UNC_WARPS, (size_t)a.xo_bytes + (size_t)LF_UNC_WARPS * a.ly.un_bytes);
+        if (e != cudaSuccess) return e;
+    }
+    return lf_launch_one(lf_out_kernel<MODEL, L, NG>, a, LF_OUT_WARPS, (size_t)a.xo_bytes + (size_t)LF_OUT_WARPS * a.ly.out_bytes);
 }

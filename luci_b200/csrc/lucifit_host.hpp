@@ -19,11 +19,14 @@ struct LfPlan {
     std::vector<double> axis;  // [nz]
     std::vector<float> xo;     // [nfit]
     std::vector<float> trans;  // [nz] or empty
-    // workspace table offsets (bytes)
+    // workspace table offsets (bytes); the per-spaxel state records follow the tables
     size_t off_axis, off_xo, off_trans, table_bytes;
-    // per-warp shared scratch (bytes)
-    size_t off_u, off_v, per_warp_bytes, cont_cap;
+    size_t state_bytes;        // per spaxel: state record (+ float64 uncertainties when requested)
+    LfLayout ly;               // per-warp scratch layout of the four stage kernels (for `lanes` lanes)
 };
+
+// Spaxels per pass of the four stage kernels: bounds the state area of the workspace.
+#define LF_SLICE_SPAXELS (1 << 20)
 
 static inline size_t lf_align(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
@@ -49,16 +52,53 @@ static inline int lf_bucket(int L, int nv, int ns)
     return L;
 }
 
-static inline size_t lf_hess_bytes(int L)
+// Per-warp scratch layout for `lanes` lanes per spaxel (32 on the device, 1 in the CPU harness).
+static inline void lf_make_layout(int L, int P, int nz, int nfit, int ncont, int lanes, LfLayout& ly)
 {
-    size_t pf = 3 * (size_t)L + 1;
-    size_t a = 13 * (size_t)L * sizeof(LfLine);
-    size_t b = (pf * pf + 2 * pf) * sizeof(double);
-    return a > b ? a : b;
+    const size_t NA = (size_t)P * (P + 1) / 2 + P, PF = 3 * (size_t)L + 1;
+    int cap = ncont > LF_MAX_CONT_WIN ? LF_MAX_CONT_WIN : ncont;
+    int npad = 2;
+    while (npad < cap) npad <<= 1;
+    ly.lanes = lanes;
+    ly.npad = npad;
+    const size_t win = lf_align(sizeof(float) * nfit, 16);
+    size_t o;
+    // prep: spec | sorted window | deviations
+    o = lf_align(sizeof(float) * nz, 16);
+    ly.prep_sortv = (int)o; o += sizeof(double) * npad;
+    ly.prep_sortd = (int)o; o += sizeof(double) * npad;
+    ly.prep_bytes = (int)lf_align(o, 16);
+    // lm: yw | sw | cw | lines[L] | tie | gt[L][lanes] | hb[2][NA] | thb[4][P]
+    o = win;
+    ly.lm_sw = (int)o; o += win;
+    ly.lm_cw = (int)o; o += win;
+    ly.lm_lines = (int)o; o += sizeof(LfLineX) * L;
+    ly.lm_tie = (int)o; o = lf_align(o + sizeof(LfTieX), 16);
+    ly.lm_gt = (int)o; o = lf_align(o + sizeof(float) * L * lanes, 16);
+    ly.lm_hb = (int)o; o = lf_align(o + sizeof(float) * 2 * NA, 16);
+    ly.lm_thb = (int)o; o = lf_align(o + sizeof(float) * 4 * P, 16);
+    ly.lm_bytes = (int)o;
+    // unc: yw | sw | cw | lines[13 L] | apd[3 L] | gt[(13 + 5 L)][lanes] | tile[lanes][PF|1] | hess
+    o = win;
+    ly.un_sw = (int)o; o += win;
+    ly.un_cw = (int)o; o += win;
+    ly.un_lines = (int)o; o += sizeof(LfLineX) * 13 * L;
+    ly.un_apd = (int)o; o = lf_align(o + sizeof(double) * 3 * L, 16);
+    ly.un_gt = (int)o; o = lf_align(o + sizeof(float) * (13 + 5 * L) * lanes, 16);
+    ly.un_tile = (int)o; o = lf_align(o + sizeof(float) * lanes * (PF | 1), 16);
+    ly.un_hess = (int)o; o = lf_align(o + sizeof(double) * (PF * PF + 2 * PF), 16);
+    ly.un_bytes = (int)o;
+    // out: yw | sw | cw | lines[L] | apd[3 L]
+    o = win;
+    ly.out_sw = (int)o; o += win;
+    ly.out_cw = (int)o; o += win;
+    ly.out_lines = (int)o; o += sizeof(LfLineX) * L;
+    ly.out_apd = (int)o; o = lf_align(o + sizeof(double) * 3 * L, 16);
+    ly.out_bytes = (int)o;
 }
 
 // Returns "" on success, else an error message.
-static inline std::string lf_make_plan(const lucifit_config* c, LfPlan& pl)
+static inline std::string lf_make_plan(const lucifit_config* c, LfPlan& pl, int lanes = 32)
 {
     if (!c) return "config is NULL";
     if (c->model < 0 || c->model > 2) return "model must be 0 (gaussian), 1 (sinc) or 2 (sincgauss)";
@@ -94,6 +134,8 @@ static inline std::string lf_make_plan(const lucifit_config* c, LfPlan& pl)
     d.ftol = c->ftol > 0 ? (float)c->ftol : 1e-8f;
     d.n_out = 7 * L + 5;
     pl.axis.assign(c->axis, c->axis + c->nz);
+    for (int i = 1; i < c->nz; ++i)
+        if (!(pl.axis[i] > pl.axis[i - 1])) return "axis must be strictly increasing (cm^-1)";
     d.x_ref = pl.axis[c->fit_lo];
     for (int k = 0; k < L; ++k) {
         if (!(c->line_nm[k] > 0)) return "line_nm must be positive";
@@ -117,34 +159,9 @@ static inline std::string lf_make_plan(const lucifit_config* c, LfPlan& pl)
     pl.off_xo = lf_align(pl.off_axis + sizeof(double) * c->nz, 256);
     pl.off_trans = lf_align(pl.off_xo + sizeof(float) * pl.nfit, 256);
     pl.table_bytes = lf_align(pl.off_trans + (c->transmission ? sizeof(float) * c->nz : 0), 256);
-    // per-warp scratch: spectrum | U = max(continuum clip scratch, Hessian scratch) | V = max(LM stash, tile)
-    size_t cap = (size_t)(pl.ncont > LF_MAX_CONT_WIN ? LF_MAX_CONT_WIN : pl.ncont);
-    cap = lf_align(cap > 0 ? cap : 1, 8);
-    pl.cont_cap = cap;
-    size_t u_bytes = 2 * cap * sizeof(double) + cap;
     const int P = L + 2 * pl.nv_t + 1;
-    size_t v_bytes = (size_t)(P * (P + 1) / 2 + P) * sizeof(float);
-    if (d.uncertainty) {
-        size_t hb = lf_hess_bytes(L);
-        if (hb > u_bytes) u_bytes = hb;
-        size_t tb = 32 * (size_t)((3 * L + 1) | 1) * sizeof(float);
-        if (tb > v_bytes) v_bytes = tb;
-    }
-    pl.off_u = lf_align(sizeof(float) * c->nz, 16);
-    pl.off_v = lf_align(pl.off_u + u_bytes, 16);
-    pl.per_warp_bytes = lf_align(pl.off_v + v_bytes, 16);
+    d.state_floats = (int)lf_align((size_t)LF_SO_TH + P, 2);
+    pl.state_bytes = sizeof(float) * d.state_floats + (d.uncertainty ? sizeof(double) * (3 * (size_t)L + 1) : 0);
+    lf_make_layout(L, P, c->nz, pl.nfit, pl.ncont, lanes, pl.ly);
     return "";
-}
-
-static inline LfScratch lf_scratch_at(const LfPlan& pl, unsigned char* warp_base)
-{
-    LfScratch sc;
-    unsigned char* u = warp_base + pl.off_u;
-    sc.dvals = reinterpret_cast<double*>(u);
-    sc.ddev = sc.dvals + pl.cont_cap;
-    sc.alive = reinterpret_cast<unsigned char*>(sc.ddev + pl.cont_cap);
-    sc.hess = reinterpret_cast<double*>(u);
-    sc.st = reinterpret_cast<float*>(warp_base + pl.off_v);
-    sc.tile = sc.st;
-    return sc;
 }

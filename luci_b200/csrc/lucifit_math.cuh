@@ -50,10 +50,11 @@ LF_HD void lf_sincospi(float d, float& s, float& c)
 // Faddeeva function w(z) = exp(-z^2) erfc(-iz) for z = x + i y, y >= 0, |error| ~ 2e-7 (FP32).
 //   |z|^2 >= 36 : Laplace continued fraction, 5 levels, as a rational function of u = z^2
 //                 (w ~ i/sqrt(pi) * z (u^2 - 7u + 8.25) / (u^3 - 7.5u^2 + 11.25u - 1.875));
-//   |z|^2 >= 1e4: first three terms of the asymptotic series (avoids FP32 overflow of |zD|^2);
+//   |z|^2 >= 300: first three terms of the asymptotic series (next term 15/(8 z^6) < 7e-8 relative; also avoids
+//                 the FP32 overflow of |zD|^2 further out);
 //   otherwise   : Weideman's N = 16 rational expansion (SIAM J. Numer. Anal. 31 (1994) 1497).
 #define LF_W_R2_CF 36.0f
-#define LF_W_R2_ASY 1.0e4f
+#define LF_W_R2_ASY 300.0f
 // Far region, split as w(z) = (i/sqrt pi) w1 + w2 with w1 = 1/z and w2 = O(z^-3) evaluated without
 // cancellation; the split is what keeps the wing derivatives of the sincgauss profile accurate in FP32.
 // For the 5-level fraction  w2 = (i/sqrt pi) (u^2/2 - 3u + 1.875) / (z D(u)),  D = u^3 - 7.5u^2 + 11.25u - 1.875.
@@ -126,6 +127,20 @@ LF_HD void lf_faddeeva(float x, float y, float& wr, float& wi)
         lf_faddeeva_near(x, y, wr, wi);
 }
 
+// sin(pi t), cos(pi t) for a phase t carried in double (t = offset / sinc width, |t| up to ~1e3 half periods): the
+// range reduction is exact, the result is good to ~1e-7 absolute.  Used for the per-sample phase table and the
+// per-line phase constants of the fit kernels (sin(pi (x - p)/w) = S_x C_p - C_x S_p).
+LF_HD void lf_phase(double t, float& s, float& c)
+{
+    double r = t - 2.0 * rint(0.5 * t);               // r in [-1, 1]
+#if defined(__CUDA_ARCH__)
+    sincospif((float)r, &s, &c);
+#else
+    s = (float)sin(3.141592653589793 * r);
+    c = (float)cos(3.141592653589793 * r);
+#endif
+}
+
 // ---------------------------------------------------------------------------------------------------
 // Per-line constants, refreshed once per model evaluation (warp-uniform).
 struct LfLine {
@@ -171,9 +186,11 @@ LF_HD void lf_line_setup(int model, float pp, float dp, float sig, float sinc_w,
 //   sincgauss: g = exp(-b^2) Re erf(a + i b)/erf(a) = [exp(-b^2) - exp(-a^2) Re(e^{-2iab} w(ia - b))]/erf(a)
 //              dg/db = -2 b g + q sin(2ab),  dg/da = q (cos(2ab) - g),  q = (2/sqrt pi) exp(-a^2)/erf(a)
 // which is algebraically the reference's Dawson expression (LuciFunctions.py:229-232) without its e^{+a^2}.
+// `s`, `c` = sin, cos(pi dx / w): the caller supplies them (the fit kernels rotate a per-sample phase table by a
+// per-line constant instead of spending two MUFU ops per line and sample); unused by the gaussian.
 template <int MODEL>
-LF_HD void lf_profile(const LfLine& ln, float dx, float piw /* pi/w */, float iw /* 1/w */, bool all_far,
-                      float& g, float& g_p, float& g_s)
+LF_HD void lf_profile_sc(const LfLine& ln, float dx, float s, float c, float iw /* 1/w */, bool all_far,
+                         float& g, float& g_p, float& g_s)
 {
     if (MODEL == LF_GAUSSIAN) {
         float b = dx * ln.is2s;
@@ -183,8 +200,6 @@ LF_HD void lf_profile(const LfLine& ln, float dx, float piw /* pi/w */, float iw
         g_s = g * 2.0f * b2 * ln.isig;
     } else if (MODEL == LF_SINC) {
         float d = dx * iw;
-        float s, c;
-        lf_sincospi(d, s, c);
         float ad = fabsf(d);
         float gd;                                     // dg/dd
         if (ad < 2e-2f) {
@@ -199,9 +214,7 @@ LF_HD void lf_profile(const LfLine& ln, float dx, float piw /* pi/w */, float iw
         g_p = -gd * iw;
         g_s = 0.0f;
     } else {
-        float b = dx * ln.is2s;
-        float s, c;
-        lf_sincospi(dx * iw, s, c);                   // 2ab = pi dx / w
+        float b = dx * ln.is2s;                       // 2ab = pi dx / w is the angle of (s, c)
         const float a = ln.a;
         float r2 = b * b + a * a;
         bool far = all_far || r2 >= LF_W_R2_CF;
@@ -230,6 +243,16 @@ LF_HD void lf_profile(const LfLine& ln, float dx, float piw /* pi/w */, float iw
         g_p = -gb * ln.is2s;
         g_s = gal * a * ln.isig;
     }
+}
+
+// Stand-alone form: computes the phase itself (synthetic-cube generator, unit tests).
+template <int MODEL>
+LF_HD void lf_profile(const LfLine& ln, float dx, float piw /* pi/w */, float iw /* 1/w */, bool all_far,
+                      float& g, float& g_p, float& g_s)
+{
+    float s = 0.0f, c = 1.0f;
+    if (MODEL != LF_GAUSSIAN) lf_sincospi(dx * iw, s, c);
+    lf_profile_sc<MODEL>(ln, dx, s, c, iw, all_far, g, g_p, g_s);
 }
 
 // "far" test used to pick the warp-uniform wing path of the sincgauss evaluation: continued-fraction region

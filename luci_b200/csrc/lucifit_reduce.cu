@@ -232,7 +232,7 @@ __global__ void __launch_bounds__(RED_WARPS * 32) lf_sim_kernel(const __grid_con
         for (int k = 0; k < a.L; ++k) {
             double lam_cm = 1e7 / a.line_nm[k];
             double pos = ((double)a.vel[s * a.L + k] / 3e5) * lam_cm + lam_cm;                 // LuciSim.py:185
-            int idx = lf_argmin_axis(w, a.axis, a.nz, pos);                           // :186-187 (snap)
+            int idx = lf_nearest_axis(a.axis, a.nz, pos);                           // :186-187 (snap)
             double psn = a.axis[idx];
             double sigma = ((double)a.broad[s * a.L + k] * psn) / (3e5 * corr);                // :189
             float hi, lo;

@@ -13,18 +13,29 @@ static void run_batch(const LfPlan& pl, int64_t n, const float* cube, const int6
                       int32_t* status)
 {
     LfWarp<1> w;
-    std::vector<unsigned char> buf(pl.per_warp_bytes + 64);
+    const LfLayout& ly = pl.ly;
+    size_t bytes = ly.prep_bytes;
+    if ((size_t)ly.lm_bytes > bytes) bytes = ly.lm_bytes;
+    if ((size_t)ly.un_bytes > bytes) bytes = ly.un_bytes;
+    if ((size_t)ly.out_bytes > bytes) bytes = ly.out_bytes;
+    std::vector<unsigned char> buf(bytes + 64);
     unsigned char* base = buf.data();
     base += (16 - ((uintptr_t)base & 15)) & 15;
-    LfScratch sc = lf_scratch_at(pl, base);
-    float* spec = reinterpret_cast<float*>(base);
     const int K = 7 * L + 5, PF = 3 * L + 1;
+    std::vector<double> state_d(pl.dev.state_floats / 2 + 1);
+    float* state = reinterpret_cast<float*>(state_d.data());
+    std::vector<double> unc(PF + 1);
     for (int64_t s = 0; s < n; ++s) {
         int64_t row = index ? index[s] : s;
-        lf_fit_spaxel<MODEL, L, NG, NG, 1>(pl.dev, w, pl.dev.xo, cube + row * (int64_t)pl.dev.nz, theta[s],
-                                           vel0 ? vel0[s] : 0.0f, broad0 ? broad0[s] : 0.0f, spec, sc,
-                                           out_rows + s * K, status + s, out_sol ? out_sol + s * PF : 0,
-                                           out_unc ? out_unc + s * PF : 0);
+        const float* gspec = cube + row * (int64_t)pl.dev.nz;
+        lf_stage_prep<MODEL, L, NG, NG, 1>(pl.dev, w, gspec, theta[s], vel0 ? vel0[s] : 0.0f, broad0 ? broad0[s] : 0.0f,
+                                           lf_work_at(LF_STAGE_PREP, ly, base), state);
+        lf_stage_lm<MODEL, L, NG, NG, 1>(pl.dev, w, pl.dev.xo, gspec, lf_work_at(LF_STAGE_LM, ly, base), state);
+        if (pl.dev.uncertainty)
+            lf_stage_unc<MODEL, L, NG, NG, 1>(pl.dev, w, pl.dev.xo, gspec, lf_work_at(LF_STAGE_UNC, ly, base), state, unc.data());
+        lf_stage_out<MODEL, L, NG, NG, 1>(pl.dev, w, pl.dev.xo, gspec, lf_work_at(LF_STAGE_OUT, ly, base), state,
+                                          pl.dev.uncertainty ? unc.data() : 0, out_rows + s * K, status + s,
+                                          out_sol ? out_sol + s * PF : 0, out_unc ? out_unc + s * PF : 0);
     }
 }
 
@@ -33,7 +44,7 @@ extern "C" int hostemu_fit_batch(const lucifit_config* cfg, int64_t n, const flo
                                  float* out_rows, float* out_sol, float* out_unc, int32_t* status)
 {
     LfPlan pl;
-    std::string err = lf_make_plan(cfg, pl);
+    std::string err = lf_make_plan(cfg, pl, 1);
     if (!err.empty()) { fprintf(stderr, "hostemu: %s\n", err.c_str()); return -1; }
     // the uncertainty scratch is always reserved in the harness
     pl.dev.axis = pl.axis.data();

@@ -13,7 +13,8 @@ from .constants import LINE_DICT, MODEL_CODE, continuum_window, fit_window, nois
 
 MAX_LINES = 8
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, 'liblucifit.so')
+# LUCIFIT_LIB: developer override (kernel experiments build variant libraries next to the shipped one)
+LIB_PATH = os.environ.get('LUCIFIT_LIB') or os.path.join(_HERE, 'liblucifit.so')
 
 
 class LucifitUnavailable(RuntimeError):

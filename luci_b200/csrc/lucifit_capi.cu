@@ -12,6 +12,17 @@ static int cuda_fail(cudaError_t e, const char* what)
     return fail(LUCIFIT_ECUDA, std::string(what) + ": " + cudaGetErrorString(e));
 }
 
+#if defined(LF_DEV_MODEL) && defined(LF_DEV_L)
+// developer build (csrc/dev_variant.sh): a single (model, n_lines) instance, for quick kernel experiments
+#define LF_DEV_CAT2(a, b, c, d) a##b##c##d
+#define LF_DEV_CAT(a, b, c, d) LF_DEV_CAT2(a, b, c, d)
+extern "C" lf_launch_fn LF_DEV_CAT(lf_launcher_m, LF_DEV_MODEL, _l, LF_DEV_L)(int bucket);
+static lf_launch_fn find_launcher(int model, int L, int bucket)
+{
+    if (model == LF_DEV_MODEL && L == LF_DEV_L) return LF_DEV_CAT(lf_launcher_m, LF_DEV_MODEL, _l, LF_DEV_L)(bucket);
+    return nullptr;
+}
+#else
 #define LF_DECL(m, l) extern "C" lf_launch_fn lf_launcher_m##m##_l##l(int bucket);
 #define LF_DECL_ALL(m) LF_DECL(m, 1) LF_DECL(m, 2) LF_DECL(m, 3) LF_DECL(m, 4) LF_DECL(m, 5) LF_DECL(m, 6) LF_DECL(m, 7) LF_DECL(m, 8)
 LF_DECL_ALL(0) LF_DECL_ALL(1) LF_DECL_ALL(2)
@@ -23,6 +34,7 @@ static lf_launch_fn find_launcher(int model, int L, int bucket)
     LF_CASE_ALL(0) LF_CASE_ALL(1) LF_CASE_ALL(2)
     return nullptr;
 }
+#endif
 
 struct LfSimArgs {
     int model, L, nz;

@@ -227,7 +227,31 @@ struct LF_ALIGN16 LfLineX {
     float ck, sk;      // cos, sin of the line's phase pi (centre - x_ref)/w
     int vg, sg;        // group indices
     float p, beta;
+    // sincgauss wing path (all lanes of a chunk beyond |z|^2 = 300, exp(-b^2) = 0): every per-line factor folded
+    float a2;          // a^2
+    float neae;        // -exp(-a^2)/erf(a):                      g    = neae T
+    float c_m;         // A neae:                                 model += c_m T
+    float c_q;         // 2a + q,  U = c_q T - c_ia2 r^2 T2       (dg/dalpha = -neae U)
+    float c_ia2;       // 2/a
+    float c_v1;        // -A neae dpdv / (sqrt2 sigma):           dm/dv    = c_v1 Tb + c_v2 U
+    float c_v2;        // -A neae a dsdv / sigma
+    float c_b2;        // -A neae a dsdb / sigma:                 dm/dbeta = c_b2 U
 };
+
+// Folds the amplitude in effect into the wing-path factors of a line record (after aeff is final).
+LF_CORE void lf_fold_wing(LfLineX& x)
+{
+    const LfLine& l = x.ln;
+    const float eae = l.ea * l.ierf;
+    x.a2 = l.a * l.a;
+    x.neae = -eae;
+    x.c_m = -x.aeff * eae;
+    x.c_q = 2.0f * l.a + l.q;
+    x.c_ia2 = 2.0f * l.ia;
+    x.c_v1 = x.aeff * eae * l.is2s * x.dpdv;
+    x.c_v2 = x.aeff * eae * l.a * l.isig * x.dsdv;
+    x.c_b2 = x.aeff * eae * l.a * l.isig * x.dsdb;
+}
 struct LfTieX {        // warp-uniform constants of the [NII] tie for one evaluation
     float R;
     float cRv[LF_MAX_LINES];
@@ -288,6 +312,7 @@ LF_CORE void lf_setup_lines(const LfCfg& cfg, const LfWarp<LANES>& w, const floa
         x.vg = g; x.sg = h;
         x.ck = 1.0f; x.sk = 0.0f;
         if (MODEL != LF_GAUSSIAN) lf_phase(((double)x.ln.pp + (double)x.ln.dp) * inv_w, x.sk, x.ck);
+        lf_fold_wing(x);
         sl[k] = x;
     }
     w.sync();
@@ -325,6 +350,7 @@ LF_CORE void lf_setup_lines(const LfCfg& cfg, const LfWarp<LANES>& w, const floa
             }
             tx->R = R;
             sl[cfg.i48].aeff = R * a83;
+            lf_fold_wing(sl[cfg.i48]);
         }
     }
     w.sync();
@@ -389,20 +415,46 @@ LF_CORE void lf_eval(const LfCfg& cfg, const LfWarp<LANES>& w, const float* xo, 
             const LfLineX& X = sl[k];
             const float dx = lf_dx(X.ln, x);
             bool all_far = false;
-            if (MODEL == LF_SINCGAUSS) all_far = w.all(lf_is_far(X.ln, dx));
             if (MODEL == LF_GAUSSIAN) {
                 float b = dx * X.ln.is2s;
                 if (w.all(b * b > 100.0f)) { gt[k * LANES + w.lane] = 0.0f; continue; }   // exp(-100) = 0 in FP32
             }
             float s = 0.0f, c = 1.0f;
             if (MODEL != LF_GAUSSIAN) { s = S * X.ck - C * X.sk; c = C * X.ck + S * X.sk; }
-            float g, gp, gs;
-            lf_profile_sc<MODEL>(X.ln, dx, s, c, iw, all_far, g, gp, gs);
-            const float A = X.aeff;
-            m += A * g;
-            const float tp = A * gp, ts = A * gs;
-            const float tv = tp * X.dpdv + ts * X.dsdv;
-            const float tb = ts * X.dsdb;
+            float g, tv, tb;
+            bool wing = false;
+            if (MODEL == LF_SINCGAUSS) {
+                const float b = dx * X.ln.is2s;
+                const float r2 = b * b + X.a2;
+                wing = w.all(b * b >= 40.0f && r2 >= LF_W_R2_ASY);
+                if (wing) {
+                    // the whole chunk is in the asymptotic region of w(z) and exp(-b^2) = 0: the wing formulas of
+                    // lf_profile_sc with every per-line factor pre-multiplied (lf_fold_wing)
+                    const float inv = LF_RCP(r2);
+                    const float w1r = -b * inv, w1i = -X.ln.a * inv;                       // 1/z, z = -b + i a
+                    const float sr = w1r * w1r - w1i * w1i, si = 2.0f * w1r * w1i;         // 1/z^2
+                    const float fr = 0.5f * sr * (1.0f + 1.5f * sr) - 0.75f * si * si, fi = 0.5f * si + 1.5f * sr * si;
+                    const float qr = w1r * fr - w1i * fi, qi = w1r * fi + w1i * fr;        // w2 = (i/sqrt pi) q
+                    const float T2 = LF_ISQRTPI_F * (s * qr - c * qi);
+                    const float T = LF_ISQRTPI_F * (s * w1r - c * w1i) + T2;
+                    const float Tb = (LF_2ISQRTPI_F * X.ln.a) * (c * w1r + s * w1i) - 2.0f * b * T2;
+                    const float U = X.c_q * T - (X.c_ia2 * r2) * T2;
+                    g = X.neae * T;
+                    m += X.c_m * T;
+                    tv = Tb * X.c_v1 + U * X.c_v2;
+                    tb = U * X.c_b2;
+                }
+            }
+            if (!wing) {
+                float gp, gs;
+                if (MODEL == LF_SINCGAUSS) all_far = w.all(lf_is_far(X.ln, dx));
+                lf_profile_sc<MODEL>(X.ln, dx, s, c, iw, all_far, g, gp, gs);
+                const float A = X.aeff;
+                m += A * g;
+                const float tp = A * gp, ts = A * gs;
+                tv = tp * X.dpdv + ts * X.dsdv;
+                tb = ts * X.dsdb;
+            }
             gt[k * LANES + w.lane] = g;
 #pragma unroll
             for (int gg = 0; gg < NV; ++gg) Jv[gg] += (NV == 1 || X.vg == gg) ? tv : 0.0f;
@@ -412,22 +464,23 @@ LF_CORE void lf_eval(const LfCfg& cfg, const LfWarp<LANES>& w, const float* xo, 
             }
         }
         float J[P];
-#pragma unroll
-        for (int k = 0; k < L; ++k) J[k] = gt[k * LANES + w.lane];
         if (tie) {
+            // amplitude columns: dm/dA_83 = g_83 + R g_48, the 6548 column is dead (fixed up in the lane's own tile
+            // slots so that J keeps compile-time register indices)
             const float g48v = gt[cfg.i48 * LANES + w.lane];
-            const float R = wk.tie->R;
+            gt[cfg.i83 * LANES + w.lane] += wk.tie->R * g48v;
+            gt[cfg.i48 * LANES + w.lane] = 0.0f;
 #pragma unroll
-            for (int k = 0; k < L; ++k) {
-                if (k == cfg.i48) J[k] = 0.0f;
-                if (k == cfg.i83) J[k] += R * g48v;
-            }
+            for (int k = 0; k < L; ++k) J[k] = gt[k * LANES + w.lane];
 #pragma unroll
             for (int gg = 0; gg < NV; ++gg) Jv[gg] += g48v * wk.tie->cRv[gg];
             if (MODEL != LF_SINC) {
 #pragma unroll
                 for (int hh = 0; hh < NS; ++hh) Js[hh] += g48v * wk.tie->cRb[hh];
             }
+        } else {
+#pragma unroll
+            for (int k = 0; k < L; ++k) J[k] = gt[k * LANES + w.lane];
         }
 #pragma unroll
         for (int gg = 0; gg < NV; ++gg) J[D::IV + gg] = Jv[gg];
@@ -473,22 +526,25 @@ LF_CORE bool lf_solve(const float* hg, unsigned fixedmask, float lam, float (&de
             if (i == j) v = (sc[i] == 0.0f) ? 1.0f : v + lam;
             M[LfSym<P>::idx(i, j)] = v;
         }
-    // in-place Cholesky M = U^T U (upper), then forward/back substitution
+    // in-place Cholesky M = U^T U (upper), then forward/back substitution.  Every loop has the compile-time trip
+    // count P with the triangular condition inside, so that the unroller resolves all indices (M stays in registers).
     bool ok = true;
 #pragma unroll
     for (int i = 0; i < P; ++i) {
         float d = M[LfSym<P>::idx(i, i)];
 #pragma unroll
-        for (int k = 0; k < i; ++k) d -= M[LfSym<P>::idx(k, i)] * M[LfSym<P>::idx(k, i)];
+        for (int k = 0; k < P; ++k) if (k < i) d -= M[LfSym<P>::idx(k, i)] * M[LfSym<P>::idx(k, i)];
         if (!(d > 1e-12f)) { ok = false; d = 1.0f; }
         float inv = LF_RSQRT(d);
         M[LfSym<P>::idx(i, i)] = inv;                      // store 1/U_ii
 #pragma unroll
-        for (int j = i + 1; j < P; ++j) {
-            float v = M[LfSym<P>::idx(i, j)];
+        for (int j = 0; j < P; ++j) {
+            if (j > i) {
+                float v = M[LfSym<P>::idx(i, j)];
 #pragma unroll
-            for (int k = 0; k < i; ++k) v -= M[LfSym<P>::idx(k, i)] * M[LfSym<P>::idx(k, j)];
-            M[LfSym<P>::idx(i, j)] = v * inv;
+                for (int k = 0; k < P; ++k) if (k < i) v -= M[LfSym<P>::idx(k, i)] * M[LfSym<P>::idx(k, j)];
+                M[LfSym<P>::idx(i, j)] = v * inv;
+            }
         }
     }
     float z[P];
@@ -496,15 +552,16 @@ LF_CORE bool lf_solve(const float* hg, unsigned fixedmask, float lam, float (&de
     for (int i = 0; i < P; ++i) {                          // U^T z = b
         float v = b[i];
 #pragma unroll
-        for (int k = 0; k < i; ++k) v -= M[LfSym<P>::idx(k, i)] * z[k];
+        for (int k = 0; k < P; ++k) if (k < i) v -= M[LfSym<P>::idx(k, i)] * z[k];
         z[i] = v * M[LfSym<P>::idx(i, i)];
     }
     float s[P];
 #pragma unroll
-    for (int i = P - 1; i >= 0; --i) {                     // U s = z
+    for (int ii = 0; ii < P; ++ii) {                       // U s = z
+        const int i = P - 1 - ii;
         float v = z[i];
 #pragma unroll
-        for (int k = i + 1; k < P; ++k) v -= M[LfSym<P>::idx(i, k)] * s[k];
+        for (int k = 0; k < P; ++k) if (k > i) v -= M[LfSym<P>::idx(i, k)] * s[k];
         s[i] = v * M[LfSym<P>::idx(i, i)];
     }
     pred = 0.0f;                                           // predicted decrease of sum r^2: s.(lam s + b)

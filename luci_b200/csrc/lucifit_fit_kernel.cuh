@@ -6,7 +6,15 @@
 #include "lucifit_core.cuh"
 
 #define LF_PREP_WARPS 8
+#ifndef LF_LM_WARPS
 #define LF_LM_WARPS 4
+#endif
+// Resident CTAs per SM the LM kernel is compiled for (register cap), by size of the normal equations: up to 8
+// unknowns (44 accumulators) fit 96 registers without spilling; larger systems get the registers they need.
+#ifndef LF_LM_MINB_SMALL
+#define LF_LM_MINB_SMALL 4
+#endif
+template <int NA> struct LfLmBlocks { enum { V = NA <= 44 ? LF_LM_MINB_SMALL : NA <= 77 ? 3 : 2 }; };
 #define LF_UNC_WARPS 4
 #define LF_OUT_WARPS 8
 
@@ -59,7 +67,7 @@ lf_prep_kernel(const __grid_constant__ LfLaunch a)
 }
 
 template <int MODEL, int L, int NG>
-__global__ void __launch_bounds__(LF_LM_WARPS * 32)
+__global__ void __launch_bounds__(LF_LM_WARPS * 32, (LfLmBlocks<LfDims<MODEL, L, NG, NG>::NA>::V))
 lf_lm_kernel(const __grid_constant__ LfLaunch a)
 {
     extern __shared__ __align__(16) unsigned char lf_smem[];

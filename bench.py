@@ -271,11 +271,13 @@ def main():
     W = mean_E * nfit * (L * F_MODEL[model] + P_red * (P_red + 3)) + mean_E * P_red ** 3 / 3.0
     if unc:
         W += 24 * L * nfit * (F_MODEL[model] / 2.0) + (3 * L + 1) ** 3
-    kern_ms = float(np.mean(step_ms))
-    if world > 1:                                                   # time the kernel without the gather
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        barrier(); e0.record(); engine.fit_batch(cfg, cube, theta, v0, b0); e1.record(); e1.synchronize()
-        kern_ms = e0.elapsed_time(e1)
+    # the dominant kernel (lf_lm_kernel) timed alone: the same pipeline stage by stage with CUDA events around every
+    # launch on the launching stream (engine.fit_batch(time_stages=True) -> lucifit_fit_stages)
+    barrier()
+    engine.fit_batch(cfg, cube, theta, v0, b0, time_stages=True)
+    stage_ms = engine.fit_batch(cfg, cube, theta, v0, b0, time_stages=True)['stage_ms']
+    kern_ms = ldist.max_over_ranks(float(stage_ms['lm']), dev)
+    n_slices = (n_local + engine.SLICE_SPAXELS - 1) // engine.SLICE_SPAXELS
     fp32_peak = engine.peak_probe(dev, 0)
     mufu_peak = engine.peak_probe(dev, 1)
     achieved = (W * n_local) / (kern_ms * 1e-3) / 1e12
@@ -286,11 +288,21 @@ def main():
     except Exception:
         pass
     hbm_peak = float(peaks.get('hbm_gbs', 6650.0))
+    traffic, traffic_src = None, None
+    try:                                                            # DRAM bytes of the kernel from the committed ncu capture
+        tr = json.load(open(os.path.join(ROOT, 'profiles', 'lm_traffic.json')))
+        traffic = float(tr['dram_bytes_per_spaxel']) * n_local
+        traffic_src = tr['source']
+    except Exception:
+        pass
     roofline = {'bound': 'fp32', 'achieved': achieved, 'peak': fp32_peak, 'unit': 'TFLOP/s',
-                'frac': achieved / fp32_peak if fp32_peak else None, 'traffic': None,
-                'peak_source': 'lucifit_peak_probe FFMA chains, measured in this run (nominal 74.4 at 1965 MHz)',
+                'frac': achieved / fp32_peak if fp32_peak else None, 'traffic': traffic, 'traffic_source': traffic_src,
+                'peak_source': 'lucifit_peak_probe FFMA chains, measured in this run (nominal 74.4 at 1965 MHz); '
+                               'MEASURED_PEAKS.json has no FP32 figure',
                 'mufu_peak_tops': mufu_peak, 'mean_evals_E': mean_E, 'flop_per_spaxel_W': W,
-                'kernel': 'lf_fit_kernel<%s,L=5,groups=1>' % model, 'kernel_ms': kern_ms,
+                'kernel': 'lf_lm_kernel<%s,L=5,groups=1>' % model, 'kernel_ms': kern_ms,
+                'launches': n_slices, 'stage_ms': {k: float(v) for k, v in stage_ms.items()},
+                'kernel_share_of_step': kern_ms / sum(stage_ms.values()),
                 'hbm_gbs_sanity': alg_bytes / (kern_ms * 1e-3) / 1e9, 'hbm_peak_gbs': hbm_peak,
                 'algorithmic_bytes': alg_bytes}
 

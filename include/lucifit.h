@@ -77,7 +77,8 @@ typedef struct lucifit_config {
  *   chi2 corr axis_step continuum continuum_error           (the 12 lists of Luci.fit_calc, LuciBase.py:406) */
 int lucifit_row_floats(int n_lines);
 
-/* Device workspace needed by lucifit_fit_batch for this configuration (independent of n_spaxel). */
+/* Device workspace needed by lucifit_fit_batch: constant tables plus the per-spaxel state records of one slice
+ * (min(n_spaxel, 2^20) spaxels; larger batches are processed slice by slice). */
 int lucifit_workspace_bytes(const lucifit_config* cfg, int64_t n_spaxel, size_t* bytes);
 
 /* Fit n_spaxel spectra.
@@ -96,6 +97,25 @@ int lucifit_fit_batch(const lucifit_config* cfg, int64_t n_spaxel, const float* 
                       const int64_t* spaxel_index, const float* theta_deg, const float* vel0, const float* broad0,
                       const float* bkg, float* out_rows, float* out_fit_sol, float* out_unc, int32_t* out_status,
                       void* workspace, size_t workspace_bytes, void* stream);
+
+/* The same pipeline run stage by stage (each stage is one kernel launch; a spaxel travels between stages as a
+ * state record inside `workspace`, so the calls of one pipeline must use the same cfg / workspace / n_spaxel, in
+ * order, on one stream; n_spaxel <= 2^20 when `stages` is not LUCIFIT_STAGE_ALL).  lucifit_fit_batch is
+ * lucifit_fit_stages(cfg, LUCIFIT_STAGE_ALL, ...).  Used to time or profile one stage (bench.py) and to interleave
+ * other work between stages.
+ *   PREP   Fit.__init__ + cont_estimate + line_vals_estimate   (LuciFit.py:49-173, 382-486)
+ *   LM     calculate_params, the optimiser                      (LuciFit.py:635-687)
+ *   UNC    uncertainties (only when cfg->uncertainty)           (LuciFit.py:713-722, LuciUtility.py:409-434)
+ *   OUT    chi2, fluxes, velocities, broadenings, rows          (LuciFit.py:799-834, LuciFitParameters.py) */
+#define LUCIFIT_STAGE_PREP 1
+#define LUCIFIT_STAGE_LM 2
+#define LUCIFIT_STAGE_UNC 4
+#define LUCIFIT_STAGE_OUT 8
+#define LUCIFIT_STAGE_ALL 15
+int lucifit_fit_stages(const lucifit_config* cfg, int stages, int64_t n_spaxel, const float* cube,
+                       const int64_t* spaxel_index, const float* theta_deg, const float* vel0, const float* broad0,
+                       const float* bkg, float* out_rows, float* out_fit_sol, float* out_unc, int32_t* out_status,
+                       void* workspace, size_t workspace_bytes, void* stream);
 
 /* Deep image: deep[s] = nansum_z cube[s][z] for s < n_spaxel - n_zero_tail, 0 for the rest
  * (create_deep_image leaves the trailing nx mod 10 x-rows zero, LuciBase.py:173-177). */

@@ -40,7 +40,7 @@ class lucifit_config(C.Structure):
     ]
 
 
-EXPORTS = ['lucifit_row_floats', 'lucifit_workspace_bytes', 'lucifit_fit_batch', 'lucifit_deep_image',
+EXPORTS = ['lucifit_row_floats', 'lucifit_workspace_bytes', 'lucifit_fit_batch', 'lucifit_fit_stages', 'lucifit_deep_image',
            'lucifit_snr_map', 'lucifit_bin_cube', 'lucifit_sim_cube', 'lucifit_peak_probe', 'lucifit_last_error',
            'lucifit_version']
 
@@ -57,6 +57,8 @@ def declare(lib):
     lib.lucifit_workspace_bytes.restype = C.c_int
     lib.lucifit_fit_batch.argtypes = [cfgp, i64, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, sz, vp]
     lib.lucifit_fit_batch.restype = C.c_int
+    lib.lucifit_fit_stages.argtypes = [cfgp, C.c_int, i64, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, sz, vp]
+    lib.lucifit_fit_stages.restype = C.c_int
     lib.lucifit_deep_image.argtypes = [vp, i64, C.c_int, i64, vp, vp]
     lib.lucifit_deep_image.restype = C.c_int
     lib.lucifit_snr_map.argtypes = [vp, i64, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, vp, vp, vp]

@@ -98,6 +98,18 @@ int lucifit_fit_batch(const lucifit_config* cfg, int64_t n_spaxel, const float* 
                       const float* bkg, float* out_rows, float* out_fit_sol, float* out_unc, int32_t* out_status,
                       void* workspace, size_t workspace_bytes, void* stream)
 {
+    return lucifit_fit_stages(cfg, LUCIFIT_STAGE_ALL, n_spaxel, cube, spaxel_index, theta_deg, vel0, broad0, bkg, out_rows,
+                              out_fit_sol, out_unc, out_status, workspace, workspace_bytes, stream);
+}
+
+int lucifit_fit_stages(const lucifit_config* cfg, int stages, int64_t n_spaxel, const float* cube,
+                       const int64_t* spaxel_index, const float* theta_deg, const float* vel0, const float* broad0,
+                       const float* bkg, float* out_rows, float* out_fit_sol, float* out_unc, int32_t* out_status,
+                       void* workspace, size_t workspace_bytes, void* stream)
+{
+    if ((stages & ~LUCIFIT_STAGE_ALL) != 0 || stages == 0) return fail(LUCIFIT_EINVAL, "stages must be a non-empty subset of LUCIFIT_STAGE_ALL");
+    if (stages != LUCIFIT_STAGE_ALL && n_spaxel > LF_SLICE_SPAXELS)
+        return fail(LUCIFIT_EINVAL, "a partial pipeline keeps its state in the workspace: at most 2^20 spaxels per call");
     LfPlan pl;
     std::string err = lf_make_plan(cfg, pl);
     if (!err.empty()) return fail(LUCIFIT_EINVAL, err);
@@ -152,7 +164,7 @@ int lucifit_fit_batch(const lucifit_config* cfg, int64_t n_spaxel, const float* 
         a.out_sol = out_fit_sol ? out_fit_sol + s0 * PF : nullptr;
         a.out_unc = out_unc ? out_unc + s0 * PF : nullptr;
         a.status = out_status + s0;
-        e = fn(a);
+        e = fn(a, stages);
         if (e != cudaSuccess) return cuda_fail(e, "launch fit stage kernels");
     }
     return 0;

@@ -38,7 +38,7 @@ struct LfLaunch {
     cudaStream_t stream;
     int sm_count;
 };
-typedef cudaError_t (*lf_launch_fn)(const LfLaunch&);
+typedef cudaError_t (*lf_launch_fn)(const LfLaunch&, int stages);
 
 __device__ __forceinline__ const float* lf_stage_xo(const LfLaunch& a, unsigned char* smem)
 {
@@ -138,18 +138,24 @@ static cudaError_t lf_launch_one(K kern, const LfLaunch& a, int warps, size_t sm
     return cudaGetLastError();
 }
 
-// Enqueues prep -> lm -> [unc] -> out for one slice.
+// Enqueues the requested stages (bit 0 prep, 1 lm, 2 unc, 3 out) for one slice, in pipeline order.
 template <int MODEL, int L, int NG>
-cudaError_t lf_launch(const LfLaunch& a)
+cudaError_t lf_launch(const LfLaunch& a, int stages)
 {
-    cudaError_t e;
-    e = lf_launch_one(lf_prep_kernel<MODEL, L, NG>, a, LF_PREP_WARPS, (size_t)LF_PREP_WARPS * a.ly.prep_bytes);
-    if (e != cudaSuccess) return e;
-    e = lf_launch_one(lf_lm_kernel<MODEL, L, NG>, a, LF_LM_WARPS, (size_t)a.xo_bytes + (size_t)LF_LM_WARPS * a.ly.lm_bytes);
-    if (e != cudaSuccess) return e;
-    if (a.unc_ws) {
+    cudaError_t e = cudaSuccess;
+    if (stages & 1) {
+        e = lf_launch_one(lf_prep_kernel<MODEL, L, NG>, a, LF_PREP_WARPS, (size_t)LF_PREP_WARPS * a.ly.prep_bytes);
+        if (e != cudaSuccess) return e;
+    }
+    if (stages & 2) {
+        e = lf_launch_one(lf_lm_kernel<MODEL, L, NG>, a, LF_LM_WARPS, (size_t)a.xo_bytes + (size_t)LF_LM_WARPS * a.ly.lm_bytes);
+        if (e != cudaSuccess) return e;
+    }
+    if ((stages & 4) && a.unc_ws) {
         e = lf_launch_one(lf_unc_kernel<MODEL, L, NG>, a, LF_UNC_WARPS, (size_t)a.xo_bytes + (size_t)LF_UNC_WARPS * a.ly.un_bytes);
         if (e != cudaSuccess) return e;
     }
-    return lf_launch_one(lf_out_kernel<MODEL, L, NG>, a, LF_OUT_WARPS, (size_t)a.xo_bytes + (size_t)LF_OUT_WARPS * a.ly.out_bytes);
+    if (stages & 8)
+        e = lf_launch_one(lf_out_kernel<MODEL, L, NG>, a, LF_OUT_WARPS, (size_t)a.xo_bytes + (size_t)LF_OUT_WARPS * a.ly.out_bytes);
+    return e;
 }

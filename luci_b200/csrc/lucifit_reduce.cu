@@ -13,25 +13,40 @@
 #include <cuda_runtime.h>
 #include <math.h>
 #include <stdint.h>
+#include <stdlib.h>
 #include "lucifit_core.cuh"
 
 #define RED_WARPS 8
+#define RED_UNROLL 8
 
-struct SnrAcc {
-    float sum, asum, mx, fsum, n1, n2;   // nansum, nansum|.|, nanmax, flux-window nansum, noise-window sum / sumsq
-    int cnt, ncnt;
+struct SnrAcc {                   // four independent chains (one per float4 component) keep the FP32 adds pipelined
+    float4 sum, asum;             // nansum, nansum|.|
+    float mx;                     // nanmax
+    int nan;                      // NaN count
 };
 
-__device__ __forceinline__ void snr_take(SnrAcc& a, float v, int z, int flo, int fhi, int nlo, int nhi, float shift)
+__device__ __forceinline__ void snr_take1(float& sum, float& asum, float& mx, int& nan, float v)
 {
-    if (v == v) {
-        a.sum += v; a.asum += fabsf(v); a.mx = fmaxf(a.mx, v); a.cnt += 1;
-        if (z >= flo && z < fhi) a.fsum += v;
-        if (z >= nlo && z < nhi) { float d = v - shift; a.n1 += d; a.n2 += d * d; a.ncnt += 1; }
-    }
+    const bool bad = v != v;
+    const float z = bad ? 0.0f : v;
+    sum += z; asum += fabsf(z);
+    mx = fmaxf(mx, bad ? -INFINITY : v);
+    nan += bad;
+}
+__device__ __forceinline__ void snr_take4(SnrAcc& a, const float4& q)
+{
+    int n0 = 0, n1 = 0, n2 = 0, n3 = 0;
+    float m0 = -INFINITY, m1 = -INFINITY, m2 = -INFINITY, m3 = -INFINITY;
+    snr_take1(a.sum.x, a.asum.x, m0, n0, q.x); snr_take1(a.sum.y, a.asum.y, m1, n1, q.y);
+    snr_take1(a.sum.z, a.asum.z, m2, n2, q.z); snr_take1(a.sum.w, a.asum.w, m3, n3, q.w);
+    a.mx = fmaxf(fmaxf(a.mx, fmaxf(m0, m1)), fmaxf(m2, m3));
+    a.nan += (n0 + n1) + (n2 + n3);
 }
 
-// MODE 0: deep only; MODE 1: SNR method 1 (+deep)
+// MODE 0: deep only; MODE 1: SNR method 1 (+deep).  The streaming loop carries only the whole-spectrum moments;
+// the noise-window variance is accumulated in float64 from samples loaded up front (independent of the streaming
+// loads, so nothing serialises behind them), which keeps the per-sample window tests out of the loop that has to
+// keep up with HBM.
 template <int MODE>
 __global__ void __launch_bounds__(RED_WARPS * 32)
 lf_reduce_kernel(const float* __restrict__ cube, long long n_spaxel, int nz, long long n_live, int flo, int fhi,
@@ -42,57 +57,220 @@ lf_reduce_kernel(const float* __restrict__ cube, long long n_spaxel, int nz, lon
     for (long long s = (long long)blockIdx.x * RED_WARPS + warp; s < n_spaxel; s += stride) {
         const float* row = cube + s * (long long)nz;
         SnrAcc a;
-        a.sum = a.asum = a.fsum = a.n1 = a.n2 = 0.0f; a.mx = -INFINITY; a.cnt = a.ncnt = 0;
-        float shift = 0.0f;
-        if (MODE == 1) shift = row[nlo < nz ? nlo : 0];      // shifted two-moment variance (stable in FP32)
-        if (shift != shift) shift = 0.0f;
+        a.sum = a.asum = make_float4(0.f, 0.f, 0.f, 0.f); a.mx = -INFINITY; a.nan = 0;
+        double n1 = 0.0, n2 = 0.0;
+        int ncnt = 0;
+        if (MODE == 1) {
+            for (int z = nlo + lane; z < nhi; z += 32) {
+                const float v = __ldg(row + z);
+                if (v == v) { n1 += (double)v; n2 += (double)v * (double)v; ncnt += 1; }
+            }
+        }
         // peel to 16-byte alignment, then float4 body
         int head = (int)(((16 - ((uintptr_t)row & 15)) & 15) >> 2);
         if (head > nz) head = nz;
         if (lane < head) {
             float v = row[lane];
-            if (MODE == 0) { if (v == v) a.sum += v; } else snr_take(a, v, lane, flo, fhi, nlo, nhi, shift);
+            if (MODE == 0) { if (v == v) a.sum.x += v; } else snr_take1(a.sum.x, a.asum.x, a.mx, a.nan, v);
         }
         const int nvec = (nz - head) >> 2;
         const float4* r4 = reinterpret_cast<const float4*>(row + head);
-        for (int i = lane; i < nvec; i += 32) {
-            float4 q = __ldcs(r4 + i);                        // streaming: every byte is read exactly once
-            int z = head + 4 * i;
-            if (MODE == 0) {
-                a.sum += (q.x == q.x ? q.x : 0.f) + (q.y == q.y ? q.y : 0.f) + (q.z == q.z ? q.z : 0.f) + (q.w == q.w ? q.w : 0.f);
-            } else {
-                snr_take(a, q.x, z, flo, fhi, nlo, nhi, shift); snr_take(a, q.y, z + 1, flo, fhi, nlo, nhi, shift);
-                snr_take(a, q.z, z + 2, flo, fhi, nlo, nhi, shift); snr_take(a, q.w, z + 3, flo, fhi, nlo, nhi, shift);
+        // RED_UNROLL independent 16-byte loads per lane are issued before any of them is consumed; slots past the
+        // end of the row are filled with NaN, which every accumulator ignores (nansum semantics)
+        for (int i0 = 0; i0 < nvec; i0 += 32 * RED_UNROLL) {
+            float4 q[RED_UNROLL];
+#pragma unroll
+            for (int j = 0; j < RED_UNROLL; ++j) {
+                const int i = i0 + j * 32 + lane;
+                q[j] = i < nvec ? __ldcs(r4 + i) : make_float4(NAN, NAN, NAN, NAN);   // streaming: each byte is read once
+            }
+#pragma unroll
+            for (int j = 0; j < RED_UNROLL; ++j) {
+                if (MODE == 0) {
+                    a.sum.x += (q[j].x == q[j].x ? q[j].x : 0.f) + (q[j].y == q[j].y ? q[j].y : 0.f)
+                             + (q[j].z == q[j].z ? q[j].z : 0.f) + (q[j].w == q[j].w ? q[j].w : 0.f);
+                } else {
+                    const int pad = (i0 + j * 32 + lane) < nvec ? 0 : 4;          // NaN fillers are not data
+                    snr_take4(a, q[j]);
+                    a.nan -= pad;
+                }
             }
         }
         for (int z = head + 4 * nvec + lane; z < nz; z += 32) {
             float v = row[z];
-            if (MODE == 0) { if (v == v) a.sum += v; } else snr_take(a, v, z, flo, fhi, nlo, nhi, shift);
+            if (MODE == 0) { if (v == v) a.sum.x += v; } else snr_take1(a.sum.x, a.asum.x, a.mx, a.nan, v);
         }
+        float sum = (a.sum.x + a.sum.y) + (a.sum.z + a.sum.w), asum = (a.asum.x + a.asum.y) + (a.asum.z + a.asum.w);
+        int nan = a.nan;
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) {
-            a.sum += __shfl_xor_sync(0xffffffffu, a.sum, o);
+            sum += __shfl_xor_sync(0xffffffffu, sum, o);
             if (MODE == 1) {
-                a.asum += __shfl_xor_sync(0xffffffffu, a.asum, o);
+                asum += __shfl_xor_sync(0xffffffffu, asum, o);
                 a.mx = fmaxf(a.mx, __shfl_xor_sync(0xffffffffu, a.mx, o));
-                a.n1 += __shfl_xor_sync(0xffffffffu, a.n1, o);
-                a.n2 += __shfl_xor_sync(0xffffffffu, a.n2, o);
-                a.cnt += __shfl_xor_sync(0xffffffffu, a.cnt, o);
-                a.ncnt += __shfl_xor_sync(0xffffffffu, a.ncnt, o);
+                n1 += __shfl_xor_sync(0xffffffffu, n1, o);
+                n2 += __shfl_xor_sync(0xffffffffu, n2, o);
+                nan += __shfl_xor_sync(0xffffffffu, nan, o);
+                ncnt += __shfl_xor_sync(0xffffffffu, ncnt, o);
             }
         }
         if (lane == 0) {
-            if (deep) deep[s] = s < n_live ? a.sum : 0.0f;
+            if (deep) deep[s] = s < n_live ? sum : 0.0f;
             if (MODE == 1) {
-                float mean = a.sum / (float)a.cnt;
-                float var = a.ncnt > 0 ? fmaxf(a.n2 / a.ncnt - (a.n1 / a.ncnt) * (a.n1 / a.ncnt), 0.0f) : NAN;
+                const int cnt = nz - nan;
+                float mean = sum / (float)cnt;
+                double mu = ncnt > 0 ? n1 / ncnt : 0.0;
+                float var = ncnt > 0 ? (float)fmax(n2 / ncnt - mu * mu, 0.0) : NAN;
                 float std_out = sqrtf(var);
                 float v = (a.mx - mean) / sqrtf(fabsf(std_out));          // LuciBase.py:1159-1161
                 if (v < 0.0f) v = 0.0f;                                   // :1162-1163
-                else v = v / sqrtf(a.asum / (float)a.cnt);                // :1165
+                else v = v / sqrtf(asum / (float)cnt);                    // :1165
                 snr[s] = v;
             }
         }
+    }
+}
+
+// ------------------------------------------------------------------------------------ TMA-staged streaming form
+// The same reductions with the spectra staged through shared memory by the bulk-copy engine (cp.async.bulk, SASS
+// UBLKCP) instead of per-lane loads: a CTA walks tiles of RED_TILE_ROWS consecutive spaxels (contiguous in the cube,
+// a multiple of 16 bytes), keeps RED_STAGES tiles in flight behind mbarriers, and its 8 warps each reduce one row of
+// the tile that has landed.  The bytes in flight per SM (2 CTAs x 3 tiles x 27 KB at nz = 841) no longer depend on
+// the register budget of the arithmetic, which is what the SNR map needs to stay HBM-bound.
+#define RED_TILE_ROWS 8
+#define RED_STAGES 3
+#define RED_TMA_MAX_TILE_BYTES (40 * 1024)
+
+__device__ __forceinline__ unsigned red_smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void red_mbar_init(unsigned long long* bar, int count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(red_smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void red_mbar_expect_tx(unsigned long long* bar, unsigned bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(red_smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void red_bulk_g2s(void* dst, const void* src, unsigned bytes, unsigned long long* bar)
+{
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(red_smem_u32(dst)), "l"(src), "r"(bytes), "r"(red_smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ bool red_mbar_try_wait(unsigned long long* bar, unsigned parity)
+{
+    unsigned ok;
+    asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                 : "=r"(ok) : "r"(red_smem_u32(bar)), "r"(parity) : "memory");
+    return ok != 0;
+}
+
+template <int MODE>
+__global__ void __launch_bounds__(RED_WARPS * 32)
+lf_reduce_tma_kernel(const float* __restrict__ cube, long long n_tiles, int nz, long long n_live, int nlo, int nhi,
+                     float* __restrict__ snr, float* __restrict__ deep)
+{
+    extern __shared__ __align__(128) unsigned char red_smem[];
+    __shared__ __align__(8) unsigned long long full_bar[RED_STAGES];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const unsigned tile_bytes = (unsigned)RED_TILE_ROWS * (unsigned)nz * 4u;
+    const unsigned stage_stride = (tile_bytes + 127u) & ~127u;
+    if (threadIdx.x == 0) {
+        for (int i = 0; i < RED_STAGES; ++i) red_mbar_init(&full_bar[i], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    const long long first = blockIdx.x, step = gridDim.x;
+    if (threadIdx.x == 0) {                                          // prologue: fill the ring
+        for (int i = 0; i < RED_STAGES; ++i) {
+            const long long t = first + (long long)i * step;
+            if (t < n_tiles) {
+                red_mbar_expect_tx(&full_bar[i], tile_bytes);
+                red_bulk_g2s(red_smem + (size_t)i * stage_stride, cube + t * (long long)RED_TILE_ROWS * nz, tile_bytes, &full_bar[i]);
+            }
+        }
+    }
+    int stage = 0;
+    unsigned parity = 0;
+    for (long long t = first; t < n_tiles; t += step) {
+        long long spins = 0;
+        while (!red_mbar_try_wait(&full_bar[stage], parity)) { if (++spins > (1ll << 26)) __trap(); }
+        const float* row = reinterpret_cast<const float*>(red_smem + (size_t)stage * stage_stride) + warp * nz;
+        const long long s = t * RED_TILE_ROWS + warp;
+        // Fast path: no NaN tests at all -- fmaxf drops NaN operands by itself and a NaN anywhere poisons `sum`, which
+        // is checked once per row; only rows that do hold NaNs are redone with the per-sample nansum tests.
+        float sum = 0.0f, asum = 0.0f, mx = -INFINITY;
+        int nan = 0;
+        {
+            float s0 = 0.0f, s1 = 0.0f, s2 = 0.0f, s3 = 0.0f, a0 = 0.0f, a1 = 0.0f, a2 = 0.0f, a3 = 0.0f;
+            float m0 = -INFINITY, m1 = -INFINITY;
+            // 16-byte shared loads over the aligned body of the row (the row starts 4-byte aligned inside the tile)
+            int head = (int)(((16 - ((uintptr_t)row & 15)) & 15) >> 2);
+            if (head > nz) head = nz;
+            if (lane < head) { const float v = row[lane]; s0 += v; if (MODE == 1) { a0 += fabsf(v); m0 = fmaxf(m0, v); } }
+            const int nvec = (nz - head) >> 2;
+            const float4* r4 = reinterpret_cast<const float4*>(row + head);
+            for (int i = lane; i < nvec; i += 32) {
+                const float4 q = r4[i];
+                s0 += q.x; s1 += q.y; s2 += q.z; s3 += q.w;
+                if (MODE == 1) {
+                    a0 += fabsf(q.x); a1 += fabsf(q.y); a2 += fabsf(q.z); a3 += fabsf(q.w);
+                    m0 = fmaxf(m0, fmaxf(q.x, q.y)); m1 = fmaxf(m1, fmaxf(q.z, q.w));
+                }
+            }
+            for (int z = head + 4 * nvec + lane; z < nz; z += 32) {
+                const float v = row[z]; s0 += v; if (MODE == 1) { a0 += fabsf(v); m0 = fmaxf(m0, v); }
+            }
+            sum = (s0 + s1) + (s2 + s3); asum = (a0 + a1) + (a2 + a3); mx = fmaxf(m0, m1);
+        }
+        if (__any_sync(0xffffffffu, sum != sum)) {                    // the row holds NaNs: nansum semantics, per sample
+            sum = 0.0f; asum = 0.0f; mx = -INFINITY; nan = 0;
+            for (int z = lane; z < nz; z += 32) {
+                const float v = row[z];
+                if (MODE == 0) sum += (v == v ? v : 0.0f); else snr_take1(sum, asum, mx, nan, v);
+            }
+        }
+        double n1 = 0.0, n2 = 0.0;
+        int ncnt = 0;
+        if (MODE == 1) {
+            for (int zz = nlo + lane; zz < nhi; zz += 32) {
+                const float v = row[zz];
+                if (v == v) { n1 += (double)v; n2 += (double)v * (double)v; ncnt += 1; }
+            }
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            sum += __shfl_xor_sync(0xffffffffu, sum, o);
+            if (MODE == 1) {
+                asum += __shfl_xor_sync(0xffffffffu, asum, o);
+                mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+                n1 += __shfl_xor_sync(0xffffffffu, n1, o);
+                n2 += __shfl_xor_sync(0xffffffffu, n2, o);
+                nan += __shfl_xor_sync(0xffffffffu, nan, o);
+                ncnt += __shfl_xor_sync(0xffffffffu, ncnt, o);
+            }
+        }
+        if (lane == 0) {
+            if (deep) deep[s] = s < n_live ? sum : 0.0f;
+            if (MODE == 1) {
+                const int cnt = nz - nan;
+                float mean = sum / (float)cnt;
+                double mu = ncnt > 0 ? n1 / ncnt : 0.0;
+                float var = ncnt > 0 ? (float)fmax(n2 / ncnt - mu * mu, 0.0) : NAN;
+                float std_out = sqrtf(var);
+                float v = (mx - mean) / sqrtf(fabsf(std_out));            // LuciBase.py:1159-1161
+                if (v < 0.0f) v = 0.0f;                                   // :1162-1163
+                else v = v / sqrtf(asum / (float)cnt);                    // :1165
+                snr[s] = v;
+            }
+        }
+        __syncthreads();                                             // every warp is done with this stage
+        if (threadIdx.x == 0) {
+            const long long tn = t + (long long)RED_STAGES * step;
+            if (tn < n_tiles) {
+                red_mbar_expect_tx(&full_bar[stage], tile_bytes);
+                red_bulk_g2s(red_smem + (size_t)stage * stage_stride, cube + tn * (long long)RED_TILE_ROWS * nz, tile_bytes, &full_bar[stage]);
+            }
+        }
+        if (++stage == RED_STAGES) { stage = 0; parity ^= 1u; }
     }
 }
 
@@ -321,7 +499,42 @@ extern "C" cudaError_t lf_run_reduce(int mode, const float* cube, long long n_sp
         lf_snr2_kernel<<<grid, RED_WARPS * 32, smem, stream>>>(cube, n_spaxel, nz, n_live, flo, fhi, nlo, nhi, snr, deep);
         return cudaGetLastError();
     }
-    long long cap = (long long)sm_count * 8;            // 8 resident 256-thread CTAs per SM
+    // TMA-staged form for the whole tiles of RED_TILE_ROWS spaxels when the cube is 16-byte aligned and a stage ring
+    // fits; the plain-load kernel below takes what is left (tail rows, unaligned views, very long spectra)
+    const size_t tile_bytes = (size_t)RED_TILE_ROWS * nz * 4;
+    if ((((uintptr_t)cube) & 15) == 0 && tile_bytes <= RED_TMA_MAX_TILE_BYTES && n_spaxel >= RED_TILE_ROWS && !getenv("LUCIFIT_NO_TMA")) {
+        const long long n_tiles = n_spaxel / RED_TILE_ROWS;
+        const size_t smem = RED_STAGES * ((tile_bytes + 127) & ~(size_t)127);
+        cudaError_t e;
+        int occ_t = 0;
+        if (mode == 0) {
+            e = cudaFuncSetAttribute(lf_reduce_tma_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            if (e == cudaSuccess) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_t, lf_reduce_tma_kernel<0>, RED_WARPS * 32, smem);
+        } else {
+            e = cudaFuncSetAttribute(lf_reduce_tma_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            if (e == cudaSuccess) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_t, lf_reduce_tma_kernel<1>, RED_WARPS * 32, smem);
+        }
+        if (e != cudaSuccess) return e;
+        if (occ_t >= 1) {
+            long long cap_t = (long long)sm_count * occ_t;
+            int grid_t = (int)(n_tiles < cap_t ? n_tiles : cap_t);
+            if (mode == 0) lf_reduce_tma_kernel<0><<<grid_t, RED_WARPS * 32, smem, stream>>>(cube, n_tiles, nz, n_live, 0, 0, nullptr, deep);
+            else lf_reduce_tma_kernel<1><<<grid_t, RED_WARPS * 32, smem, stream>>>(cube, n_tiles, nz, n_live, nlo, nhi, snr, deep);
+            e = cudaGetLastError();
+            if (e != cudaSuccess) return e;
+            const long long done = n_tiles * RED_TILE_ROWS;
+            if (done == n_spaxel) return cudaSuccess;
+            cube += done * (long long)nz; n_spaxel -= done; n_live -= done;
+            if (snr) snr += done;
+            if (deep) deep += done;
+            want = (n_spaxel + RED_WARPS - 1) / RED_WARPS;
+        }
+    }
+    int occ = 1;                                        // one resident wave, grid-stride inside
+    if (mode == 0) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, lf_reduce_kernel<0>, RED_WARPS * 32, 0);
+    else cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, lf_reduce_kernel<1>, RED_WARPS * 32, 0);
+    if (occ < 1) occ = 1;
+    long long cap = (long long)sm_count * occ;
     int grid = (int)(want < cap ? want : cap); if (grid < 1) grid = 1;
     if (mode == 0)
         lf_reduce_kernel<0><<<grid, RED_WARPS * 32, 0, stream>>>(cube, n_spaxel, nz, n_live, 0, 0, 0, 0, nullptr, deep);

@@ -57,11 +57,19 @@ def workspace_for(device, nbytes):
     return ws.get(nbytes, device)
 
 
+SLICE_SPAXELS = 1 << 20            # LF_SLICE_SPAXELS of csrc/lucifit_host.hpp
+STAGES = (('prep', 1), ('lm', 2), ('unc', 4), ('out', 8))
+
+
 def fit_batch(cfg: FitConfig, cube, theta, vel0=None, broad0=None, index=None, bkg=None, want_sol=False,
-              want_unc=False):
+              want_unc=False, time_stages=False):
     """One ``lucifit_fit_batch`` call.  ``cube`` is ``[n_rows, nz]`` float32 on the GPU; ``index`` (int64, optional)
     selects the rows to fit; ``theta``/``vel0``/``broad0`` are per *fitted* spaxel.  Returns a dict of device
-    tensors: ``rows [n, 7L+5]``, ``status [n]`` and optionally ``fit_sol`` / ``fit_unc`` ``[n, 3L+1]``."""
+    tensors: ``rows [n, 7L+5]``, ``status [n]`` and optionally ``fit_sol`` / ``fit_unc`` ``[n, 3L+1]``.
+
+    ``time_stages=True`` runs the same pipeline stage by stage through ``lucifit_fit_stages`` (slice by slice) with
+    CUDA events around every kernel on the launching stream and adds ``stage_ms`` (dict, summed over the slices;
+    this synchronises)."""
     lib = _capi.lib()
     require_cuda(cube, 'cube', torch.float32)
     dev = cube.device
@@ -90,13 +98,37 @@ def fit_batch(cfg: FitConfig, cube, theta, vel0=None, broad0=None, index=None, b
     need = C.c_size_t(0)
     check(lib.lucifit_workspace_bytes(cfg.byref(), n, C.byref(need)))
     ws = workspace_for(dev, need.value)
-    with torch.cuda.device(dev):
-        check(lib.lucifit_fit_batch(cfg.byref(), n, _ptr(cube), _ptr(index), _ptr(theta), _ptr(vel0), _ptr(broad0),
-                                    _ptr(bkg), _ptr(rows), _ptr(sol), _ptr(unc), _ptr(status), _ptr(ws),
-                                    C.c_size_t(ws.numel()), _stream()))
-    if n > 0:
-        launch_counter['n'] += 1
+    n_stage = 4 if cfg.c.uncertainty else 3
     out = {'rows': rows, 'status': status}
+    with torch.cuda.device(dev):
+        if not time_stages:
+            check(lib.lucifit_fit_batch(cfg.byref(), n, _ptr(cube), _ptr(index), _ptr(theta), _ptr(vel0), _ptr(broad0),
+                                        _ptr(bkg), _ptr(rows), _ptr(sol), _ptr(unc), _ptr(status), _ptr(ws),
+                                        C.c_size_t(ws.numel()), _stream()))
+        else:
+            marks = []
+            if index is None:
+                index = torch.arange(n, dtype=torch.int64, device=dev)     # slices address rows through the index
+            for lo in range(0, n, SLICE_SPAXELS):
+                hi = min(lo + SLICE_SPAXELS, n)
+                sl = lambda t: None if t is None else t[lo:hi]
+                for name, bit in STAGES:
+                    if bit == 4 and not cfg.c.uncertainty:
+                        continue
+                    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                    e0.record()
+                    check(lib.lucifit_fit_stages(cfg.byref(), bit, hi - lo, _ptr(cube), _ptr(sl(index)), _ptr(sl(theta)),
+                                                 _ptr(sl(vel0)), _ptr(sl(broad0)), _ptr(bkg), _ptr(sl(rows)), _ptr(sl(sol)),
+                                                 _ptr(sl(unc)), _ptr(sl(status)), _ptr(ws), C.c_size_t(ws.numel()),
+                                                 _stream()))
+                    e1.record()
+                    marks.append((name, e0, e1))
+            torch.cuda.current_stream().synchronize()
+            ms = {}
+            for name, e0, e1 in marks:
+                ms[name] = ms.get(name, 0.0) + e0.elapsed_time(e1)
+            out['stage_ms'] = ms
+    launch_counter['n'] += n_stage * ((n + SLICE_SPAXELS - 1) // SLICE_SPAXELS)
     if want_sol:
         out['fit_sol'] = sol
     if want_unc:

@@ -137,3 +137,21 @@ def test_compute_entry_points_fail_loudly_without_cuda():
         engine.fit_batch(cfg, torch.zeros(2, len(ax)), torch.zeros(2))
     with pytest.raises(TypeError, match='no CPU path'):
         engine.deep_image(torch.zeros(2, len(ax)))
+
+
+def test_product_package_never_imports_the_oracle():
+    """oracle/ is test infrastructure: nothing under luci_b200/ (Python or C++/CUDA) may import, include or load it."""
+    import re
+    pkg = os.path.join(ROOT, 'luci_b200')
+    bad = []
+    for dirpath, _, files in os.walk(pkg):
+        if '_obj' in dirpath or '__pycache__' in dirpath:
+            continue
+        for f in files:
+            if not f.endswith(('.py', '.cu', '.cuh', '.hpp', '.h')):
+                continue
+            src = open(os.path.join(dirpath, f), errors='ignore').read()
+            if re.search(r'^\s*(from|import)\s+oracle\b', src, re.M) or re.search(r'#include\s+".*oracle', src) \
+                    or 'hostemu' in src and f.endswith('.py'):
+                bad.append(os.path.join(dirpath, f))
+    assert not bad, bad

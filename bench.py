@@ -144,7 +144,7 @@ def reference_arm(args):
                                    '2048x2064 cube' % (args.model, args.nz)},
             'cpu_baseline': cb,
             'e2e': {'value': cb['value'], 'unit': 'spaxels/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0}}
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 # ------------------------------------------------------------------------------------------------- clocks
@@ -198,8 +198,28 @@ class ClockSampler:
 
 
 # ------------------------------------------------------------------------------------------------- GPU arm
+_REAL_STDOUT = None
+
+
+def quiet_stdout():
+    """Libraries (NCCL's version banner, joblib workers) write to fd 1; the contract is ONE JSON line on stdout.  Send
+    fd 1 to stderr for the duration of the run and keep the real stdout for emit()."""
+    global _REAL_STDOUT
+    if _REAL_STDOUT is None:
+        sys.stdout.flush()
+        _REAL_STDOUT = os.fdopen(os.dup(1), 'w')
+        os.dup2(2, 1)
+
+
+def emit(line):
+    out = _REAL_STDOUT or sys.stdout
+    out.write(json.dumps(line) + '\n')
+    out.flush()
+
+
 def main():
     args = parse()
+    quiet_stdout()
     if args.impl == 'reference':
         reference_arm(args)
         return
@@ -351,13 +371,13 @@ def main():
     # --- end to end: cube in pinned host memory, streamed in chunks through the C ABI
     if not args.no_e2e:
         line['e2e'] = run_e2e(torch, engine, ldist, cfg, cube, theta, v0, b0, dev, args, world, n_total, K)
-    if rank == 0 and not args.no_cpu_baseline:
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:      # reported baseline: rank 0 at N = 1 only
         cb, _, _ = run_cpu_arm(args.nz, model, unc, budget_s=args.cpu_seconds)
         line['cpu_baseline'] = cb
     if world > 1:
         torch.distributed.barrier()
     if rank == 0:
-        print(json.dumps(line), flush=True)
+        emit(line)
     if world > 1:
         torch.distributed.destroy_process_group()
 

@@ -147,15 +147,43 @@ LF_CORE int lf_nearest_axis(const double* axis, int nz, double pos)
 
 // In-place ascending bitonic sort of v[0..npad) (npad a power of two; pad with +inf), all lanes cooperate.
 template <int LANES>
-LF_CORE void lf_sort(const LfWarp<LANES>& w, double* v, int npad)
+LF_CORE void lf_sort(const LfWarp<LANES>& w, float* v, int npad)
 {
+#if defined(__CUDA_ARCH__)
+    if (LANES == 32 && npad <= 64) {
+        // register form for windows of up to 64 samples: element e lives in lane e & 31, register e >> 5; partners
+        // closer than 32 are reached with one shuffle, the distance-32 step is the lane's own pair
+        float r0 = w.lane < npad ? v[w.lane] : INFINITY, r1 = w.lane + 32 < npad ? v[w.lane + 32] : INFINITY;
+#pragma unroll
+        for (int k = 2; k <= 64; k <<= 1) {
+#pragma unroll
+            for (int j = k >> 1; j > 0; j >>= 1) {
+                if (j == 32) {
+                    const float lo = fminf(r0, r1), hi = fmaxf(r0, r1);
+                    r0 = lo; r1 = hi;
+                } else {
+                    const bool asc = k == 64 || (w.lane & k) == 0;
+                    const bool keep_min = ((w.lane & j) == 0) == asc;
+                    const float p0 = __shfl_xor_sync(0xffffffffu, r0, j), p1 = __shfl_xor_sync(0xffffffffu, r1, j);
+                    r0 = keep_min ? fminf(r0, p0) : fmaxf(r0, p0);
+                    r1 = keep_min ? fminf(r1, p1) : fmaxf(r1, p1);
+                }
+            }
+        }
+        w.sync();
+        if (w.lane < npad) v[w.lane] = r0;
+        if (w.lane + 32 < npad) v[w.lane + 32] = r1;
+        w.sync();
+        return;
+    }
+#endif
     for (int k = 2; k <= npad; k <<= 1) {
         for (int j = k >> 1; j > 0; j >>= 1) {
             for (int t = w.lane; t < (npad >> 1); t += LANES) {
                 int i = 2 * j * (t / j) + (t % j);
                 int l = i + j;
                 bool up = (i & k) == 0;
-                double a = v[i], b = v[l];
+                float a = v[i], b = v[l];
                 if ((a > b) == up) { v[i] = b; v[l] = a; }
             }
             w.sync();
@@ -163,41 +191,68 @@ LF_CORE void lf_sort(const LfWarp<LANES>& w, double* v, int npad)
     }
 }
 
-LF_CORE double lf_sorted_median(const double* v, int a, int m)   // median of the sorted range v[a .. a+m)
+LF_CORE double lf_sorted_median(const float* v, int a, int m)   // median of the sorted range v[a .. a+m), float64
 {
     if (m <= 0) return 0.0;
-    if (m & 1) return v[a + m / 2];
-    return 0.5 * (v[a + m / 2 - 1] + v[a + m / 2]);
+    if (m & 1) return (double)v[a + m / 2];
+    return 0.5 * ((double)v[a + m / 2 - 1] + (double)v[a + m / 2]);
+}
+
+// k-th smallest (0-based) of |v[a+i] - med|, i in [0, m), for a SORTED range v: the deviations left of the median
+// (descending index) and right of it are two ascending lists; every element finds its rank in the union with one
+// binary search in the other list, the element of rank k is the answer.  No second sort.
+template <int LANES>
+LF_CORE double lf_dev_kth(const LfWarp<LANES>& w, const float* v, int a, int m, int i0, double med, int k)
+{
+    // left list:  dL(p) = med - v[a + i0 - 1 - p], p in [0, i0)      right list: dR(q) = v[a + i0 + q] - med, q in [0, m - i0)
+    const int nL = i0, nR = m - i0;
+    double found = 0.0;
+    int hit = 0;
+    for (int i = w.lane; i < m; i += LANES) {
+        const bool left = i < i0;
+        const double d = left ? med - (double)v[a + i] : (double)v[a + i] - med;
+        int lo = 0, hi = left ? nR : nL;                            // count of the other list's elements before d
+        while (lo < hi) {
+            const int mid = (lo + hi) >> 1;
+            const double o = left ? (double)v[a + i0 + mid] - med : med - (double)v[a + i0 - 1 - mid];
+            const bool before = left ? (o < d) : (o <= d);          // ties: left elements first (a strict total order)
+            if (before) lo = mid + 1; else hi = mid;
+        }
+        const int rank = (left ? i0 - 1 - i : i - i0) + lo;
+        if (rank == k) { found = d; hit = 1; }
+    }
+    return w.sum(hit ? found : 0.0);                                // exactly one lane hits
 }
 
 // Continuum guess: median of the window after <=3 rounds of 1-sigma clipping about the median with mad_std as the
 // spread (LuciFit.py:474-486; astropy sigma_clip semantics restated in oracle/astro_stats.py).  The window is
-// sorted once; a clip keeps the values inside an interval, so the survivors are always a contiguous range of it.
-// `sv` / `dv` are per-warp scratch of `npad` doubles each.
+// sorted once (float keys are exact: the data are float32); a clip keeps the values inside an interval, so the
+// survivors are always a contiguous range of the sorted window, and the MAD comes from rank counting in it.
+// `sv` is per-warp scratch of `npad` floats.
 template <int LANES>
 LF_CORE double lf_cont_estimate(const LfWarp<LANES>& w, const float* spec, int lo, int hi, double sigma_level,
-                                double* sv, double* dv, int npad)
+                                float* sv, int npad)
 {
     int n = hi - lo;
     if (n > LF_MAX_CONT_WIN) n = LF_MAX_CONT_WIN;
     if (n <= 0) return 0.0;
-    for (int i = w.lane; i < npad; i += LANES) sv[i] = i < n ? (double)spec[lo + i] : INFINITY;
+    w.sync();
+    for (int i = w.lane; i < npad; i += LANES) sv[i] = i < n ? spec[lo + i] : INFINITY;
     w.sync();
     lf_sort(w, sv, npad);
     int a = 0, m = n;
     for (int it = 0; it < 3 && m > 0; ++it) {
-        double med = lf_sorted_median(sv, a, m);
-        int mpad = 2;
-        while (mpad < m) mpad <<= 1;
-        for (int i = w.lane; i < mpad; i += LANES) dv[i] = i < m ? fabs(sv[a + i] - med) : INFINITY;
-        w.sync();
-        lf_sort(w, dv, mpad);
-        double mad = 1.482602218505602 * lf_sorted_median(dv, 0, m);
-        double lo_b = med - sigma_level * mad, hi_b = med + sigma_level * mad;
+        const double med = lf_sorted_median(sv, a, m);
+        int i0 = 0;
+        for (int i = w.lane; i < m; i += LANES) i0 += ((double)sv[a + i] < med);
+        i0 = w.sum(i0);
+        double dmed = lf_dev_kth(w, sv, a, m, i0, med, m / 2);
+        if (!(m & 1)) dmed = 0.5 * (lf_dev_kth(w, sv, a, m, i0, med, m / 2 - 1) + dmed);
+        const double mad = 1.482602218505602 * dmed;
+        const double lo_b = med - sigma_level * mad, hi_b = med + sigma_level * mad;
         int below = 0, above = 0;
-        for (int i = w.lane; i < m; i += LANES) { double x = sv[a + i]; below += !(x >= lo_b); above += !(x <= hi_b); }
+        for (int i = w.lane; i < m; i += LANES) { double x = (double)sv[a + i]; below += !(x >= lo_b); above += !(x <= hi_b); }
         below = w.sum(below); above = w.sum(above);
-        w.sync();
         if (below + above == 0) break;
         a += below; m -= below + above;
     }
@@ -261,8 +316,7 @@ struct LfTieX {        // warp-uniform constants of the [NII] tie for one evalua
 
 struct LfWork {        // pointers into the per-warp scratch (which of them are valid depends on the stage)
     float* spec;       // prep: [nz] background-subtracted spectrum
-    double* sortv;     // prep: [npad] sorted continuum window
-    double* sortd;     // prep: [npad] deviations
+    float* sortv;      // prep: [npad] sorted continuum window
     int npad;
     float* yw;         // lm/unc/out: [nfit] data of the fit window (normalised as the stage needs)
     float* sw;         // [nfit] sin(pi xo/w)
@@ -381,6 +435,19 @@ template <int N, int LANES> struct LfReduceScatter<N, 0, LANES> {
     }
 };
 
+// Wing of the sincgauss profile (|z|^2 >= LF_W_R2_ASY, exp(-b^2) = 0): T = Re[e^{-i phi} w(z)], z = -b + i a, from the
+// three-term asymptotic series, split as w = (i/sqrt pi)/z + w2 (T2 is the w2 part); g = -exp(-a^2)/erf(a) T.
+LF_CORE void lf_wing_terms(float b, float a, float r2, float s, float c, float& T, float& T2, float& w1r, float& w1i)
+{
+    const float inv = LF_RCP(r2);
+    w1r = -b * inv; w1i = -a * inv;                                                    // 1/z
+    const float sr = w1r * w1r - w1i * w1i, si = 2.0f * w1r * w1i;                     // 1/z^2
+    const float fr = 0.5f * sr * (1.0f + 1.5f * sr) - 0.75f * si * si, fi = 0.5f * si + 1.5f * sr * si;
+    const float qr = w1r * fr - w1i * fi, qi = w1r * fi + w1i * fr;                    // w2 = (i/sqrt pi) q
+    T2 = LF_ISQRTPI_F * (s * qr - c * qi);
+    T = LF_ISQRTPI_F * (s * w1r - c * w1i) + T2;
+}
+
 // One pass over the fit window: chi2 = sum r^2, and (into dst[NA], per-warp memory) H = J^T J packed upper
 // followed by g = J^T r, at the parameters the line records `sl` were built for.
 template <int MODEL, int L, int NV, int NS, int LANES>
@@ -430,13 +497,8 @@ LF_CORE void lf_eval(const LfCfg& cfg, const LfWarp<LANES>& w, const float* xo, 
                 if (wing) {
                     // the whole chunk is in the asymptotic region of w(z) and exp(-b^2) = 0: the wing formulas of
                     // lf_profile_sc with every per-line factor pre-multiplied (lf_fold_wing)
-                    const float inv = LF_RCP(r2);
-                    const float w1r = -b * inv, w1i = -X.ln.a * inv;                       // 1/z, z = -b + i a
-                    const float sr = w1r * w1r - w1i * w1i, si = 2.0f * w1r * w1i;         // 1/z^2
-                    const float fr = 0.5f * sr * (1.0f + 1.5f * sr) - 0.75f * si * si, fi = 0.5f * si + 1.5f * sr * si;
-                    const float qr = w1r * fr - w1i * fi, qi = w1r * fi + w1i * fr;        // w2 = (i/sqrt pi) q
-                    const float T2 = LF_ISQRTPI_F * (s * qr - c * qi);
-                    const float T = LF_ISQRTPI_F * (s * w1r - c * w1i) + T2;
+                    float T, T2, w1r, w1i;
+                    lf_wing_terms(b, X.ln.a, r2, s, c, T, T2, w1r, w1i);
                     const float Tb = (LF_2ISQRTPI_F * X.ln.a) * (c * w1r + s * w1i) - 2.0f * b * T2;
                     const float U = X.c_q * T - (X.c_ia2 * r2) * T2;
                     g = X.neae * T;
@@ -637,7 +699,7 @@ LF_CORE void lf_stage_prep(const LfCfg& cfg, const LfWarp<LANES>& w, const float
         s2 = w.sum(s2);
         noise = n > 0 ? sqrt(s2 / n) / (double)smax : NAN;
     }
-    const double cont0 = lf_cont_estimate(w, spec, cfg.cont_lo, cfg.cont_hi, 1.0, wk.sortv, wk.sortd, wk.npad) / (double)smax;
+    const double cont0 = lf_cont_estimate(w, spec, cfg.cont_lo, cfg.cont_hi, 1.0, wk.sortv, wk.npad) / (double)smax;
     // scale: ML-prior path max(spectrum_restricted) * max(spectrum_T) ; plain path max(spectrum_T)
     const double scale = cfg.ml_scale ? ((double)wmax / (double)smax) * (double)tmax : (double)tmax;
     const double ct = fabs(cos((double)theta_deg * 0.017453292519943295));
@@ -900,6 +962,7 @@ LF_CORE void lf_stage_out(const LfCfg& cfg, const LfWarp<LANES>& w, const float*
         x.dpdv = x.dsdv = x.dsdb = 0.0f; x.vg = x.sg = 0; x.p = x.beta = 0.0f;
         x.ck = 1.0f; x.sk = 0.0f;
         if (MODEL != LF_GAUSSIAN) lf_phase(((double)x.ln.pp + (double)x.ln.dp) * inv_w, x.sk, x.ck);
+        lf_fold_wing(x);
         sl[k] = x;
     }
     w.sync();
@@ -917,9 +980,19 @@ LF_CORE void lf_stage_out(const LfCfg& cfg, const LfWarp<LANES>& w, const float*
             const LfLineX& X = sl[k];
             const float dx = lf_dx(X.ln, x);
             bool all_far = false;
-            if (MODEL == LF_SINCGAUSS) all_far = w.all(lf_is_far(X.ln, dx));
             float s = 0.0f, c = 1.0f;
             if (MODEL != LF_GAUSSIAN) { s = Sx * X.ck - Cx * X.sk; c = Cx * X.ck + Sx * X.sk; }
+            if (MODEL == LF_SINCGAUSS) {
+                const float b = dx * X.ln.is2s;
+                const float r2 = b * b + X.a2;
+                if (w.all(b * b >= 40.0f && r2 >= LF_W_R2_ASY)) {      // whole chunk in the wing of this line
+                    float T, T2, w1r, w1i;
+                    lf_wing_terms(b, X.ln.a, r2, s, c, T, T2, w1r, w1i);
+                    m += X.c_m * T;
+                    continue;
+                }
+                all_far = w.all(lf_is_far(X.ln, dx));
+            }
             float g, gp, gs;
             lf_profile_sc<MODEL>(X.ln, dx, s, c, iw, all_far, g, gp, gs);
             m += X.aeff * g;
@@ -1031,6 +1104,7 @@ LF_CORE void lf_stage_unc(const LfCfg& cfg, const LfWarp<LANES>& w, const float*
         x.dpdv = x.dsdv = x.dsdb = 0.0f; x.vg = x.sg = 0; x.p = x.beta = 0.0f;
         x.ck = 1.0f; x.sk = 0.0f;
         if (MODEL != LF_GAUSSIAN) lf_phase(((double)x.ln.pp + (double)x.ln.dp) * inv_w, x.sk, x.ck);
+        lf_fold_wing(x);
         lines[e] = x;
     }
     w.sync();
@@ -1082,12 +1156,25 @@ LF_CORE void lf_stage_unc(const LfCfg& cfg, const LfWarp<LANES>& w, const float*
                 } else {
                     const LfLineX& X = lines[13 * k + v];
                     const float dx = lf_dx(X.ln, x);
-                    bool far = false;
-                    if (MODEL == LF_SINCGAUSS) far = w.all(lf_is_far(X.ln, dx));
                     float s = 0.0f, c = 1.0f;
                     if (MODEL != LF_GAUSSIAN) { s = Sx * X.ck - Cx * X.sk; c = Cx * X.ck + Sx * X.sk; }
-                    float gp, gs;
-                    lf_profile_sc<MODEL>(X.ln, dx, s, c, iw, far, gv, gp, gs);
+                    bool wing = false;
+                    if (MODEL == LF_SINCGAUSS) {
+                        const float b = dx * X.ln.is2s;
+                        const float r2 = b * b + X.a2;
+                        wing = w.all(b * b >= 40.0f && r2 >= LF_W_R2_ASY);
+                        if (wing) {                                 // value-only wing form (see lf_eval)
+                            float T, T2, w1r, w1i;
+                            lf_wing_terms(b, X.ln.a, r2, s, c, T, T2, w1r, w1i);
+                            gv = X.neae * T;
+                        }
+                    }
+                    if (!wing) {
+                        bool far = false;
+                        if (MODEL == LF_SINCGAUSS) far = w.all(lf_is_far(X.ln, dx));
+                        float gp, gs;
+                        lf_profile_sc<MODEL>(X.ln, dx, s, c, iw, far, gv, gp, gs);
+                    }
                 }
                 gvt[v * LANES + w.lane] = gv;
             }
@@ -1230,7 +1317,7 @@ LF_CORE void lf_stage_unc(const LfCfg& cfg, const LfWarp<LANES>& w, const float*
 struct LfLayout {
     int lanes;
     int npad;                                              // continuum window padded to a power of two
-    int prep_sortv, prep_sortd, prep_bytes;
+    int prep_sortv, prep_bytes;
     int lm_sw, lm_cw, lm_lines, lm_tie, lm_gt, lm_hb, lm_thb, lm_bytes;
     int un_sw, un_cw, un_lines, un_apd, un_gt, un_tile, un_hess, un_bytes;
     int out_sw, out_cw, out_lines, out_apd, out_bytes;
@@ -1243,11 +1330,10 @@ LF_CORE LfWork lf_work_at(int stage, const LfLayout& ly, unsigned char* base)
     LfWork wk;
     wk.spec = reinterpret_cast<float*>(base);
     wk.yw = reinterpret_cast<float*>(base);
-    wk.sortv = 0; wk.sortd = 0; wk.npad = ly.npad;
+    wk.sortv = 0; wk.npad = ly.npad;
     wk.sw = 0; wk.cw = 0; wk.lines = 0; wk.tie = 0; wk.gt = 0; wk.hb = 0; wk.thb = 0; wk.apd = 0; wk.tile = 0; wk.hess = 0;
     if (stage == LF_STAGE_PREP) {
-        wk.sortv = reinterpret_cast<double*>(base + ly.prep_sortv);
-        wk.sortd = reinterpret_cast<double*>(base + ly.prep_sortd);
+        wk.sortv = reinterpret_cast<float*>(base + ly.prep_sortv);
     } else if (stage == LF_STAGE_LM) {
         wk.sw = reinterpret_cast<float*>(base + ly.lm_sw);
         wk.cw = reinterpret_cast<float*>(base + ly.lm_cw);

@@ -63,10 +63,9 @@ static inline void lf_make_layout(int L, int P, int nz, int nfit, int ncont, int
     ly.npad = npad;
     const size_t win = lf_align(sizeof(float) * nfit, 16);
     size_t o;
-    // prep: spec | sorted window | deviations
+    // prep: spec | sorted window
     o = lf_align(sizeof(float) * nz, 16);
-    ly.prep_sortv = (int)o; o += sizeof(double) * npad;
-    ly.prep_sortd = (int)o; o += sizeof(double) * npad;
+    ly.prep_sortv = (int)o; o += sizeof(float) * npad;
     ly.prep_bytes = (int)lf_align(o, 16);
     // lm: yw | sw | cw | lines[L] | tie | gt[L][lanes] | hb[2][NA] | thb[4][P]
     o = win;

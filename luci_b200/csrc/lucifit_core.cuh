@@ -858,7 +858,7 @@ LF_CORE void lf_stage_lm(const LfCfg& cfg, const LfWarp<LANES>& w, const float* 
                 float tj = th[j];
                 tn[j] = fminf(fmaxf(tj + delta[j], lo[j]), hi[j]);
                 float sc = (j >= D::IV && j < D::IS) ? 1.0f : fmaxf(fabsf(tj), 1e-3f);   // velocities: km/s absolute
-                rel = fmaxf(rel, fabsf(tn[j] - tj) / sc);
+                rel = fmaxf(rel, fabsf(tn[j] - tj) * LF_RCP(sc));
             }
             w.sync();
 #pragma unroll

@@ -54,17 +54,20 @@ LF_HD void lf_sincospi(float d, float& s, float& c)
 // Faddeeva function w(z) = exp(-z^2) erfc(-iz) for z = x + i y, y >= 0, |error| ~ 2e-7 (FP32).
 //   |z|^2 >= 36 : Laplace continued fraction, 5 levels, as a rational function of u = z^2
 //                 (w ~ i/sqrt(pi) * z (u^2 - 7u + 8.25) / (u^3 - 7.5u^2 + 11.25u - 1.875));
-//   |z|^2 >= 300: first three terms of the asymptotic series (next term 15/(8 z^6) < 7e-8 relative; also avoids
-//                 the FP32 overflow of |zD|^2 further out);
+//   |z|^2 >= 1e4: first three terms of the asymptotic series (avoids the FP32 overflow of |zD|^2 further out; the
+//                 series is already good to 7e-8 from |z|^2 = 300 = LF_W_R2_ASY, which is where the fit kernels'
+//                 warp-uniform wing path starts -- per lane the fraction is kept up to 1e4 so that a mixed chunk
+//                 does not pay for a third divergent branch);
 //   otherwise   : Weideman's N = 16 rational expansion (SIAM J. Numer. Anal. 31 (1994) 1497).
 #define LF_W_R2_CF 36.0f
 #define LF_W_R2_ASY 300.0f
+#define LF_W_R2_ASY_LANE 1.0e4f
 // Far region, split as w(z) = (i/sqrt pi) w1 + w2 with w1 = 1/z and w2 = O(z^-3) evaluated without
 // cancellation; the split is what keeps the wing derivatives of the sincgauss profile accurate in FP32.
 // For the 5-level fraction  w2 = (i/sqrt pi) (u^2/2 - 3u + 1.875) / (z D(u)),  D = u^3 - 7.5u^2 + 11.25u - 1.875.
 LF_HD void lf_faddeeva_far_split(float x, float y, float r2, float& w1r, float& w1i, float& w2r, float& w2i)
 {
-    if (r2 >= LF_W_R2_ASY) {
+    if (r2 >= LF_W_R2_ASY_LANE) {
         float inv = LF_RCP(r2);
         w1r = x * inv; w1i = -y * inv;                               // 1/z
         float sr = w1r * w1r - w1i * w1i, si = 2.0f * w1r * w1i;     // s = 1/z^2

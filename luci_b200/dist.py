@@ -50,26 +50,44 @@ def split_even(n, rank, world):
     return lo, lo + base + (1 if rank < rem else 0)
 
 
-def gather_rows(local_rows, dst=0):
+def gather_rows(local_rows, dst=0, counts=None, out=None):
     """Gather ``[n_r, K]`` row blocks of all ranks to ``dst`` in rank order (concatenated ``[sum n_r, K]``); other
-    ranks get ``None``.  Shards may differ in length: blocks are padded to the longest one."""
+    ranks get ``None``.  Shards may differ in length.
+
+    ``counts`` (rows per rank, e.g. from :func:`shard_bounds`) avoids the exchange of the block lengths, which costs a
+    host synchronisation; ``out`` is an optional preallocated ``[sum n_r, K]`` destination on ``dst``.  Every block
+    is received straight into its slice of the destination (point-to-point, no padding, no concatenation)."""
     if not dist.is_initialized() or dist.get_world_size() == 1:
         return local_rows
     world, rank = dist.get_world_size(), dist.get_rank()
-    n_local = torch.tensor([local_rows.shape[0]], dtype=torch.int64, device=local_rows.device)
-    counts = [torch.zeros_like(n_local) for _ in range(world)]
-    dist.all_gather(counts, n_local)
-    counts = [int(c.item()) for c in counts]
-    nmax = max(counts)
+    if counts is None:
+        n_local = torch.tensor([local_rows.shape[0]], dtype=torch.int64, device=local_rows.device)
+        got = [torch.zeros_like(n_local) for _ in range(world)]
+        dist.all_gather(got, n_local)
+        counts = [int(c.item()) for c in got]
     K = local_rows.shape[1]
-    padded = torch.zeros((nmax, K), dtype=local_rows.dtype, device=local_rows.device)
-    padded[:local_rows.shape[0]] = local_rows
-    if rank == dst:
-        bufs = [torch.empty_like(padded) for _ in range(world)]
-        dist.gather(padded, bufs, dst=dst)
-        return torch.cat([b[:c] for b, c in zip(bufs, counts)], dim=0)
-    dist.gather(padded, None, dst=dst)
-    return None
+    if rank != dst:
+        if local_rows.shape[0] > 0:
+            dist.send(local_rows.contiguous(), dst=dst)
+        return None
+    total = sum(counts)
+    if out is None:
+        out = torch.empty((total, K), dtype=local_rows.dtype, device=local_rows.device)
+    offs = [0]
+    for c in counts:
+        offs.append(offs[-1] + c)
+    reqs = []
+    for r in range(world):
+        if counts[r] == 0:
+            continue
+        blk = out[offs[r]:offs[r + 1]]
+        if r == dst:
+            blk.copy_(local_rows)
+        else:
+            reqs.append(dist.irecv(blk, src=r))
+    for q in reqs:
+        q.wait()
+    return out
 
 
 def max_over_ranks(value, device=None):

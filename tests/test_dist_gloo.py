@@ -32,6 +32,14 @@ def _worker(rank, world, port, q):
     s = torch.arange(lo * ny, hi * ny, dtype=torch.float32)
     local = s[:, None] * 10 + torch.arange(K, dtype=torch.float32)[None, :]
     got = ldist.gather_rows(local, dst=0)
+    # same gather with the shard sizes known up front and a preallocated destination (what bench.py does)
+    counts = [(b - a) * ny for a, b in (ldist.shard_bounds(nx, q, w) for q in range(w))]
+    out = torch.full((nx * ny, K), -1.0) if r == 0 else None
+    got2 = ldist.gather_rows(local, dst=0, counts=counts, out=out)
+    if r == 0:
+        assert got2 is out and torch.equal(got, got2)
+    else:
+        assert got2 is None
     tmax = ldist.max_over_ranks(1.0 + r)
     tsum = ldist.sum_over_ranks(float(hi - lo))
     if r == 0:

@@ -62,7 +62,7 @@ STAGES = (('prep', 1), ('lm', 2), ('unc', 4), ('out', 8))
 
 
 def fit_batch(cfg: FitConfig, cube, theta, vel0=None, broad0=None, index=None, bkg=None, want_sol=False,
-              want_unc=False, time_stages=False):
+              want_unc=False, time_stages=False, rows=None, status=None):
     """One ``lucifit_fit_batch`` call.  ``cube`` is ``[n_rows, nz]`` float32 on the GPU; ``index`` (int64, optional)
     selects the rows to fit; ``theta``/``vel0``/``broad0`` are per *fitted* spaxel.  Returns a dict of device
     tensors: ``rows [n, 7L+5]``, ``status [n]`` and optionally ``fit_sol`` / ``fit_unc`` ``[n, 3L+1]``.
@@ -91,8 +91,18 @@ def fit_batch(cfg: FitConfig, cube, theta, vel0=None, broad0=None, index=None, b
         if bkg.numel() != cfg.c.nz:
             raise ValueError('bkg must have nz entries')
     K, PF = cfg.row_floats, 3 * cfg.L + 1
-    rows = torch.empty((n, K), dtype=torch.float32, device=dev)
-    status = torch.empty((n,), dtype=torch.int32, device=dev)
+    if rows is None:
+        rows = torch.empty((n, K), dtype=torch.float32, device=dev)
+    else:                                                  # caller-owned outputs (streaming pipelines reuse them)
+        require_cuda(rows, 'rows', torch.float32)
+        if tuple(rows.shape) != (n, K):
+            raise ValueError('rows must be [n, 7L+5]')
+    if status is None:
+        status = torch.empty((n,), dtype=torch.int32, device=dev)
+    else:
+        require_cuda(status, 'status', torch.int32)
+        if status.numel() != n:
+            raise ValueError('status must have n entries')
     sol = torch.empty((n, PF), dtype=torch.float32, device=dev) if want_sol else None
     unc = torch.empty((n, PF), dtype=torch.float32, device=dev) if want_unc else None
     need = C.c_size_t(0)
@@ -134,6 +144,59 @@ def fit_batch(cfg: FitConfig, cube, theta, vel0=None, broad0=None, index=None, b
     if want_unc:
         out['fit_unc'] = unc
     return out
+
+
+class HostCubeStream:
+    """Fits a cube that lives in pinned HOST memory: the spectra are streamed to the GPU in chunks on a copy stream
+    while the previous chunk is being fitted, and the result rows are copied back on a third stream, so the whole
+    cube never has to be resident (the reference keeps ``cube_final`` in host RAM, LuciBase.py:106-145).
+
+    Buffers are allocated once and reused across calls.  ``run`` returns after the last row has landed in
+    ``host_rows``."""
+
+    def __init__(self, cfg: FitConfig, device, chunk=1 << 17, n_buffers=3):
+        self.cfg, self.dev, self.chunk, self.nb = cfg, device, int(chunk), int(n_buffers)
+        nz, K = cfg.c.nz, cfg.row_floats
+        self.copy_s, self.comp_s, self.back_s = (torch.cuda.Stream(device=device) for _ in range(3))
+        self.cube_b = [torch.empty((self.chunk, nz), dtype=torch.float32, device=device) for _ in range(self.nb)]
+        self.par_b = [torch.empty((3, self.chunk), dtype=torch.float32, device=device) for _ in range(self.nb)]
+        self.rows_b = [torch.empty((self.chunk, K), dtype=torch.float32, device=device) for _ in range(self.nb)]
+        self.stat_b = [torch.empty((self.chunk,), dtype=torch.int32, device=device) for _ in range(self.nb)]
+        self.free_ev = [None] * self.nb
+
+    def run(self, host_cube, host_par, host_rows, host_status=None):
+        """``host_cube [n, nz]``, ``host_par [3, n]`` (theta, prior velocity, prior broadening), ``host_rows [n, 7L+5]``
+        and optional ``host_status [n]`` are pinned CPU tensors."""
+        for name, t in (('host_cube', host_cube), ('host_par', host_par), ('host_rows', host_rows)):
+            if t.is_cuda or not t.is_pinned():
+                raise TypeError('%s must be a pinned CPU tensor' % name)
+        n = host_cube.shape[0]
+        for ci, lo in enumerate(range(0, n, self.chunk)):
+            hi = min(lo + self.chunk, n)
+            m, b = hi - lo, ci % self.nb
+            with torch.cuda.stream(self.copy_s):
+                if self.free_ev[b] is not None:
+                    self.copy_s.wait_event(self.free_ev[b])
+                self.cube_b[b][:m].copy_(host_cube[lo:hi], non_blocking=True)
+                self.par_b[b][:, :m].copy_(host_par[:, lo:hi], non_blocking=True)
+                ready = torch.cuda.Event()
+                ready.record(self.copy_s)
+            with torch.cuda.stream(self.comp_s):
+                self.comp_s.wait_event(ready)
+                fit_batch(self.cfg, self.cube_b[b][:m], self.par_b[b][0, :m], self.par_b[b][1, :m], self.par_b[b][2, :m],
+                          rows=self.rows_b[b][:m], status=self.stat_b[b][:m])
+                done = torch.cuda.Event()
+                done.record(self.comp_s)
+            with torch.cuda.stream(self.back_s):
+                self.back_s.wait_event(done)
+                host_rows[lo:hi].copy_(self.rows_b[b][:m], non_blocking=True)
+                if host_status is not None:
+                    host_status[lo:hi].copy_(self.stat_b[b][:m], non_blocking=True)
+                ev = torch.cuda.Event()
+                ev.record(self.back_s)
+                self.free_ev[b] = ev
+        self.back_s.synchronize()
+        return host_rows
 
 
 def unpack_rows(rows, L):

@@ -176,3 +176,33 @@ def test_size_independent_properties_on_a_large_batch():
     truth = t(sc.vel_fit_truth.reshape(-1))
     err = (a['rows'][:, 15] - truth).abs()
     assert float(err.median()) < 25.0                 # LuciSim's channel snapping: up to 24 km/s
+
+
+def test_host_cube_stream_equals_resident_path():
+    """The streamed host-memory path (chunks, three streams, reused buffers) returns exactly what one resident
+    lucifit_fit_batch call returns, including a ragged last chunk and a second pass through the same buffers."""
+    from luci_b200 import engine
+    from luci_b200.sim import SN3_LINES, SyntheticCube
+    dev = _dev()
+    sc = SyntheticCube(37, 29, model='sincgauss', resolution=5000, seed=11)
+    cube = sc.synthesize(dev).view(37 * 29, -1)
+    n, nz = cube.shape
+    v0, b0 = sc.priors()
+    t = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(dev)
+    v0f, b0f = t(v0.T.reshape(-1).copy()), t(b0.T.reshape(-1).copy())
+    theta = torch.full((n,), sc.theta, dtype=torch.float32, device=dev)
+    cfg = engine.FitConfig('sincgauss', SN3_LINES, [1] * 5, [1] * 5, sc.axis32, 'SN3', sc.delta_x, sc.n_steps, 0)
+    ref = engine.fit_batch(cfg, cube, theta, v0f, b0f)
+    host_cube = torch.empty((n, nz), dtype=torch.float32, pin_memory=True); host_cube.copy_(cube)
+    host_par = torch.empty((3, n), dtype=torch.float32, pin_memory=True)
+    host_par[0].copy_(theta); host_par[1].copy_(v0f); host_par[2].copy_(b0f)
+    host_rows = torch.zeros((n, cfg.row_floats), dtype=torch.float32, pin_memory=True)
+    host_status = torch.zeros((n,), dtype=torch.int32, pin_memory=True)
+    stream = engine.HostCubeStream(cfg, dev, chunk=200, n_buffers=3)          # 1073 spaxels -> 6 chunks, last ragged
+    for _ in range(2):
+        host_rows.zero_()
+        stream.run(host_cube, host_par, host_rows, host_status)
+        assert torch.equal(host_rows, ref['rows'].cpu())
+        assert torch.equal(host_status, ref['status'].cpu())
+    with pytest.raises(TypeError):
+        stream.run(cube, host_par, host_rows)                                  # device tensor: not a host cube

@@ -307,6 +307,12 @@ LF_CORE void lf_fold_wing(LfLineX& x)
     x.c_v2 = x.aeff * eae * l.a * l.isig * x.dsdv;
     x.c_b2 = x.aeff * eae * l.a * l.isig * x.dsdb;
 }
+struct LF_ALIGN16 LfLineV {        // compact record of one shifted variant of a line (uncertainty stage), 64 bytes
+    LfLine ln;
+    float ck, sk;      // cos, sin of the variant's phase
+    float a2, neae;    // a^2, -exp(-a^2)/erf(a)  (wing form)
+    float aeff, pad;
+};
 struct LfTieX {        // warp-uniform constants of the [NII] tie for one evaluation
     float R;
     float cRv[LF_MAX_LINES];
@@ -321,7 +327,8 @@ struct LfWork {        // pointers into the per-warp scratch (which of them are 
     float* yw;         // lm/unc/out: [nfit] data of the fit window (normalised as the stage needs)
     float* sw;         // [nfit] sin(pi xo/w)
     float* cw;         // [nfit] cos(pi xo/w)
-    LfLineX* lines;    // [L]  (unc: [13 L])
+    LfLineX* lines;    // [L]
+    LfLineV* vlines;   // unc: [13 L] shifted variants
     LfTieX* tie;
     float* gt;         // [(L+1)][LANES] unit profiles of the current chunk (unc: [13][LANES])
     float* hb;         // lm: [2][NA] normal equations (accepted / trial)
@@ -1092,27 +1099,33 @@ LF_CORE void lf_stage_unc(const LfCfg& cfg, const LfWarp<LANES>& w, const float*
     double* apd = wk.apd;
     lf_expand<MODEL, L, NV, NS, LANES>(cfg, w, sinc_w, th, apd);
     // line set-ups of all variants, built lane-parallel
-    LfLineX* lines = wk.lines;
+    LfLineV* lines = wk.vlines;
     for (int e = w.lane; e < 13 * L; e += LANES) {
         int k = e / 13, v = e % 13;
         float pp, pl;
         lf_split(apd[L + k] - cfg.x_ref, pp, pl);
         float s = (float)apd[2 * L + k] + lf_var_ds(v);
-        LfLineX x;
+        LfLineV x;
         lf_line_setup(MODEL, pp, pl - lf_var_dp(v), s, sinc_w, x.ln);
-        x.aeff = (float)apd[k];
-        x.dpdv = x.dsdv = x.dsdb = 0.0f; x.vg = x.sg = 0; x.p = x.beta = 0.0f;
+        x.aeff = (float)apd[k]; x.pad = 0.0f;
         x.ck = 1.0f; x.sk = 0.0f;
         if (MODEL != LF_GAUSSIAN) lf_phase(((double)x.ln.pp + (double)x.ln.dp) * inv_w, x.sk, x.ck);
-        lf_fold_wing(x);
+        x.a2 = x.ln.a * x.ln.a;
+        x.neae = -x.ln.ea * x.ln.ierf;
         lines[e] = x;
     }
     w.sync();
     const float iw = 1.0f / sinc_w;
     const float cont = th[D::IC];
     float gram[SLOTS];
+    int gi[SLOTS], gj[SLOTS];                            // (row, column) of the Gram entries this lane owns
 #pragma unroll
-    for (int s = 0; s < SLOTS; ++s) gram[s] = 0.0f;
+    for (int s = 0; s < SLOTS; ++s) {
+        gram[s] = 0.0f;
+        int e = s * LANES + w.lane, i = 0, rem = e < NE ? e : 0;
+        while (rem >= PF - i) { rem -= PF - i; ++i; }
+        gi[s] = i; gj[s] = i + rem;
+    }
     // per-line second-difference sums: [5][L] per lane, kept in per-warp memory (rolled line loop)
     float* sums = wk.gt + 13 * LANES;                  // [5 L][LANES]
     for (int e = 0; e < 5 * L; ++e) sums[e * LANES + w.lane] = 0.0f;
@@ -1130,7 +1143,7 @@ LF_CORE void lf_stage_unc(const LfCfg& cfg, const LfWarp<LANES>& w, const float*
         float m = cont;
 #pragma unroll 1
         for (int k = 0; k < L; ++k) {
-            const LfLineX& X = lines[13 * k];
+            const LfLineV& X = lines[13 * k];
             const float dx = lf_dx(X.ln, x);
             bool far = false;
             if (MODEL == LF_SINCGAUSS) far = w.all(lf_is_far(X.ln, dx));
@@ -1154,7 +1167,7 @@ LF_CORE void lf_stage_unc(const LfCfg& cfg, const LfWarp<LANES>& w, const float*
                 if (MODEL == LF_SINC && lf_var_ds(v) != 0.0f) {
                     gv = (lf_var_dp(v) == 0.0f) ? g0 : 0.0f;            // filled from variants 1 / 2 below
                 } else {
-                    const LfLineX& X = lines[13 * k + v];
+                    const LfLineV& X = lines[13 * k + v];
                     const float dx = lf_dx(X.ln, x);
                     float s = 0.0f, c = 1.0f;
                     if (MODEL != LF_GAUSSIAN) { s = Sx * X.ck - Cx * X.sk; c = Cx * X.ck + Sx * X.sk; }
@@ -1220,13 +1233,12 @@ LF_CORE void lf_stage_unc(const LfCfg& cfg, const LfWarp<LANES>& w, const float*
         // Gram matrix of the D vectors: entry e = (i, j), i <= j, owned by lane e % LANES
 #pragma unroll
         for (int s = 0; s < SLOTS; ++s) {
-            int e = s * LANES + w.lane;
-            if (e < NE) {
-                int i = 0, rem = e;
-                while (rem >= PF - i) { rem -= PF - i; ++i; }
-                int j = i + rem;
+            if (s * LANES + w.lane < NE) {
+                const float* ti = tile + gi[s];
+                const float* tj = tile + gj[s];
                 float acc = 0.0f;
-                for (int t = 0; t < LANES; ++t) acc += tile[t * STRIDE + i] * tile[t * STRIDE + j];
+#pragma unroll 8
+                for (int t = 0; t < LANES; ++t) acc += ti[t * STRIDE] * tj[t * STRIDE];
                 gram[s] += acc;
             }
         }
@@ -1239,11 +1251,8 @@ LF_CORE void lf_stage_unc(const LfCfg& cfg, const LfWarp<LANES>& w, const float*
     w.sync();
 #pragma unroll
     for (int s = 0; s < SLOTS; ++s) {
-        int e = s * LANES + w.lane;
-        if (e < NE) {
-            int i = 0, rem = e;
-            while (rem >= PF - i) { rem -= PF - i; ++i; }
-            int j = i + rem;
+        if (s * LANES + w.lane < NE) {
+            const int i = gi[s], j = gj[s];
             double v = (double)gram[s] / noise2;
             Hm[i * PF + j] = v; Hm[j * PF + i] = v;
         }
@@ -1331,7 +1340,7 @@ LF_CORE LfWork lf_work_at(int stage, const LfLayout& ly, unsigned char* base)
     wk.spec = reinterpret_cast<float*>(base);
     wk.yw = reinterpret_cast<float*>(base);
     wk.sortv = 0; wk.npad = ly.npad;
-    wk.sw = 0; wk.cw = 0; wk.lines = 0; wk.tie = 0; wk.gt = 0; wk.hb = 0; wk.thb = 0; wk.apd = 0; wk.tile = 0; wk.hess = 0;
+    wk.sw = 0; wk.cw = 0; wk.lines = 0; wk.vlines = 0; wk.tie = 0; wk.gt = 0; wk.hb = 0; wk.thb = 0; wk.apd = 0; wk.tile = 0; wk.hess = 0;
     if (stage == LF_STAGE_PREP) {
         wk.sortv = reinterpret_cast<float*>(base + ly.prep_sortv);
     } else if (stage == LF_STAGE_LM) {
@@ -1345,11 +1354,11 @@ LF_CORE LfWork lf_work_at(int stage, const LfLayout& ly, unsigned char* base)
     } else if (stage == LF_STAGE_UNC) {
         wk.sw = reinterpret_cast<float*>(base + ly.un_sw);
         wk.cw = reinterpret_cast<float*>(base + ly.un_cw);
-        wk.lines = reinterpret_cast<LfLineX*>(base + ly.un_lines);
+        wk.vlines = reinterpret_cast<LfLineV*>(base + ly.un_lines);
         wk.apd = reinterpret_cast<double*>(base + ly.un_apd);
         wk.gt = reinterpret_cast<float*>(base + ly.un_gt);
         wk.tile = reinterpret_cast<float*>(base + ly.un_tile);
-        wk.hess = reinterpret_cast<double*>(base + ly.un_hess);
+        wk.hess = reinterpret_cast<double*>(base + ly.un_hess);   // aliases the variant records (dead by then)
     } else {
         wk.sw = reinterpret_cast<float*>(base + ly.out_sw);
         wk.cw = reinterpret_cast<float*>(base + ly.out_cw);

@@ -77,15 +77,17 @@ static inline void lf_make_layout(int L, int P, int nz, int nfit, int ncont, int
     ly.lm_hb = (int)o; o = lf_align(o + sizeof(float) * 2 * NA, 16);
     ly.lm_thb = (int)o; o = lf_align(o + sizeof(float) * 4 * P, 16);
     ly.lm_bytes = (int)o;
-    // unc: yw | sw | cw | lines[13 L] | apd[3 L] | gt[(13 + 5 L)][lanes] | tile[lanes][PF|1] | hess
+    // unc: yw | sw | cw | variants[13 L] (later: hess) | apd[3 L] | gt[(13 + 5 L)][lanes] | tile[lanes][PF|1]
     o = win;
     ly.un_sw = (int)o; o += win;
     ly.un_cw = (int)o; o += win;
-    ly.un_lines = (int)o; o += sizeof(LfLineX) * 13 * L;
+    {   // the float64 Hessian is assembled after the sample loop, when the variant records are dead: same bytes
+        size_t rec = sizeof(LfLineV) * 13 * L, hess = sizeof(double) * (PF * PF + 2 * PF);
+        ly.un_lines = (int)o; ly.un_hess = (int)o; o = lf_align(o + (rec > hess ? rec : hess), 16);
+    }
     ly.un_apd = (int)o; o = lf_align(o + sizeof(double) * 3 * L, 16);
     ly.un_gt = (int)o; o = lf_align(o + sizeof(float) * (13 + 5 * L) * lanes, 16);
     ly.un_tile = (int)o; o = lf_align(o + sizeof(float) * lanes * (PF | 1), 16);
-    ly.un_hess = (int)o; o = lf_align(o + sizeof(double) * (PF * PF + 2 * PF), 16);
     ly.un_bytes = (int)o;
     // out: yw | sw | cw | lines[L] | apd[3 L]
     o = win;

@@ -70,6 +70,9 @@ typedef struct lucifit_config {
     int scale_mode;                           /* 1: ML-prior path scale (LuciFit.py:374-375); 0: max(spectrum) (:782) */
     int max_iter;                             /* LM iteration cap (0 -> 60) */
     double ftol;                              /* predicted relative decrease of sum r^2 that counts as converged (0 -> 1e-8) */
+    int prior_groups;                         /* 0: vel0 / broad0 hold one value per spaxel (the reference's CNN output);
+                                                 1: vel0 is [n_spaxel][NV], broad0 [n_spaxel][NS], one prior per tie group in
+                                                 order of first appearance in vel_group / sigma_group (double components) */
 } lucifit_config;
 
 /* Number of floats per spaxel in out_rows: 7 L + 5, ordered
@@ -86,7 +89,8 @@ int lucifit_workspace_bytes(const lucifit_config* cfg, int64_t n_spaxel, size_t*
  *   spaxel_index optional DEVICE int64 list (mask compaction) or NULL
  *   theta_deg    [n_spaxel] DEVICE interferometer angle of each fitted spaxel (LuciBase.py:369)
  *   vel0, broad0 [n_spaxel] DEVICE prior velocity / broadening in km/s (what the CNN writes to vel_ml / broad_ml,
- *                LuciFit.py:356-361), either may be NULL (-> 0, the reference's ML_bool=False behaviour)
+ *                LuciFit.py:356-361), either may be NULL (-> 0, the reference's ML_bool=False behaviour); with
+ *                cfg->prior_groups they are [n_spaxel][NV] / [n_spaxel][NS]
  *   bkg          [nz] DEVICE background spectrum already multiplied by binning^2, or NULL (LuciBase.py:326-330)
  *   out_rows     [n_spaxel][7L+5] DEVICE float32
  *   out_fit_sol  optional [n_spaxel][3L+1] DEVICE: fit_sol (amplitude, position cm^-1, sigma cm^-1)*L, continuum

@@ -158,8 +158,8 @@ int lucifit_fit_stages(const lucifit_config* cfg, int stages, int64_t n_spaxel, 
         a.index = spaxel_index ? (const long long*)spaxel_index + s0 : nullptr;
         a.index_base = s0;
         a.theta = theta_deg + s0;
-        a.vel0 = vel0 ? vel0 + s0 : nullptr;
-        a.broad0 = broad0 ? broad0 + s0 : nullptr;
+        a.vel0 = vel0 ? vel0 + s0 * (pl.dev.prior_groups ? pl.nv : 1) : nullptr;
+        a.broad0 = broad0 ? broad0 + s0 * (pl.dev.prior_groups ? pl.ns : 1) : nullptr;
         a.out_rows = out_rows + s0 * K;
         a.out_sol = out_fit_sol ? out_fit_sol + s0 * PF : nullptr;
         a.out_unc = out_unc ? out_unc + s0 * PF : nullptr;

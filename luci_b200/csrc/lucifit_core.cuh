@@ -55,6 +55,7 @@ struct LfCfg {                     // device-side constants of one lucifit_fit_b
     int i48, i83;                  // [NII] tie: indices of NII6548 / NII6583, -1 when off
     int sigbox_group;              // sigma group of the LAST line: 0 <= sigma <= 10 cm^-1 (LuciFit.py:539-541)
     int uncertainty, ml_scale, max_iter, n_out;
+    int prior_groups;              // 1: priors are per group ([nv] velocities, [ns] broadenings per spaxel), 0: one pair
     int state_floats;              // stride of the state record
     float ftol;
     float p0[LF_MAX_LINES];        // 1e7/lambda_k                     [cm^-1]
@@ -663,8 +664,9 @@ LF_CORE void lf_bounds(const LfCfg& cfg, const float* th, float* lo, float* hi)
 // ---------------------------------------------------------------------------------------------- stage: prep
 // Reads the spaxel's spectrum, computes everything Fit.__init__ does plus the initial vector, writes the state.
 template <int MODEL, int L, int NV, int NS, int LANES>
-LF_CORE void lf_stage_prep(const LfCfg& cfg, const LfWarp<LANES>& w, const float* gspec, float theta_deg, float vel0,
-                           float broad0, const LfWork& wk, float* state)
+LF_CORE void lf_stage_prep(const LfCfg& cfg, const LfWarp<LANES>& w, const float* gspec, float theta_deg,
+                           const float* pvel /* [nv] or [1] or null */, const float* pbroad /* [ns] or [1] or null */,
+                           const LfWork& wk, float* state)
 {
     typedef LfDims<MODEL, L, NV, NS> D;
     const int nz = cfg.nz;
@@ -714,11 +716,12 @@ LF_CORE void lf_stage_prep(const LfCfg& cfg, const LfWarp<LANES>& w, const float
     const double sinc_w = corr * cfg.axis_k;
     // initial vector (LuciFit.py:663-672, 410-423): amplitude = max over +-5 channels around the expected
     // centre minus the continuum guess; centres from the prior velocity; sigma from the prior broadening.
-    if (vel0 != vel0) vel0 = 0.0f;                     // LuciFit.py:406-409
-    if (broad0 != broad0) broad0 = 1.0f;
-    broad0 = fabsf(broad0);
+    // priors: one (velocity, broadening) pair per spaxel like the reference's CNN output, or one per tie group
+    // (cfg.prior_groups: what a double-component fit needs to leave the symmetric saddle, SURVEY hard part 7)
     float* th = state + LF_SO_TH;
     for (int k = w.lane; k < L; k += LANES) {
+        float vel0 = pvel ? pvel[cfg.prior_groups ? cfg.vg[k] : 0] : 0.0f;
+        if (vel0 != vel0) vel0 = 0.0f;                 // LuciFit.py:406-409
         double lam = cfg.line_nm[k];
         double pos = 1e7 / (((double)vel0 / 299792.0) * lam + lam);
         int ind = lf_nearest_axis(cfg.axis, nz, pos);
@@ -733,9 +736,15 @@ LF_CORE void lf_stage_prep(const LfCfg& cfg, const LfWarp<LANES>& w, const float
     }
     if (w.lane == 0) {
 #pragma unroll
-        for (int g = 0; g < NV; ++g) th[D::IV + g] = vel0;
+        for (int g = 0; g < NV; ++g) {
+            float v = pvel ? pvel[(cfg.prior_groups && g < cfg.nv) ? g : 0] : 0.0f;
+            th[D::IV + g] = (v != v) ? 0.0f : v;
+        }
 #pragma unroll
-        for (int h = 0; h < NS; ++h) th[D::IS + h] = broad0;
+        for (int h = 0; h < NS; ++h) {
+            float b = pbroad ? pbroad[(cfg.prior_groups && h < cfg.ns) ? h : 0] : 0.0f;
+            th[D::IS + h] = (b != b) ? 1.0f : fabsf(b);
+        }
         th[D::IC] = (float)cont0;
         double* sd = reinterpret_cast<double*>(state);
         sd[LF_SO_NOISE / 2] = noise; sd[LF_SO_SCALE / 2] = scale; sd[LF_SO_CORR / 2] = corr; sd[LF_SO_SINCW / 2] = sinc_w;

@@ -60,9 +60,10 @@ lf_prep_kernel(const __grid_constant__ LfLaunch a)
     const long long stride = (long long)gridDim.x * LF_PREP_WARPS;
     for (long long s = (long long)blockIdx.x * LF_PREP_WARPS + warp; s < a.n; s += stride) {
         const long long row = a.index ? a.index[s] : a.index_base + s;
+        const int pnv = a.cfg.prior_groups ? a.cfg.nv : 1, pns = a.cfg.prior_groups ? a.cfg.ns : 1;
         lf_stage_prep<MODEL, L, NG, NG, 32>(a.cfg, w, a.cube + row * (long long)a.cfg.nz, a.theta[s],
-                                            a.vel0 ? a.vel0[s] : 0.0f, a.broad0 ? a.broad0[s] : 0.0f, wk,
-                                            a.state + s * (long long)a.cfg.state_floats);
+                                            a.vel0 ? a.vel0 + s * pnv : nullptr, a.broad0 ? a.broad0 + s * pns : nullptr,
+                                            wk, a.state + s * (long long)a.cfg.state_floats);
     }
 }
 

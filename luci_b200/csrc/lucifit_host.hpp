@@ -131,6 +131,7 @@ static inline std::string lf_make_plan(const lucifit_config* c, LfPlan& pl, int 
     d.sigbox_group = d.sg[L - 1];
     d.uncertainty = c->uncertainty ? 1 : 0;
     d.ml_scale = c->scale_mode ? 1 : 0;
+    d.prior_groups = c->prior_groups ? 1 : 0;
     d.max_iter = c->max_iter > 0 ? c->max_iter : 60;
     d.ftol = c->ftol > 0 ? (float)c->ftol : 1e-8f;
     d.n_out = 7 * L + 5;

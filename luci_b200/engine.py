@@ -79,11 +79,13 @@ def fit_batch(cfg: FitConfig, cube, theta, vel0=None, broad0=None, index=None, b
     require_cuda(theta, 'theta', torch.float32)
     if theta.numel() != n:
         raise ValueError('theta must have one entry per fitted spaxel')
-    for name, t in (('vel0', vel0), ('broad0', broad0)):
+    for name, t, ng in (('vel0', vel0, cfg.n_vel_groups), ('broad0', broad0, cfg.n_sigma_groups)):
         if t is not None:
             require_cuda(t, name, torch.float32)
-            if t.numel() != n:
-                raise ValueError('%s must have one entry per fitted spaxel' % name)
+            want = n * (ng if cfg.c.prior_groups else 1)
+            if t.numel() != want:
+                raise ValueError('%s must have %s per fitted spaxel' % (name, 'one entry per tie group' if cfg.c.prior_groups
+                                                                        else 'one entry'))
     if index is not None:
         require_cuda(index, 'index', torch.int64)
     if bkg is not None:
@@ -122,13 +124,14 @@ def fit_batch(cfg: FitConfig, cube, theta, vel0=None, broad0=None, index=None, b
             for lo in range(0, n, SLICE_SPAXELS):
                 hi = min(lo + SLICE_SPAXELS, n)
                 sl = lambda t: None if t is None else t[lo:hi]
+                slp = lambda t, ng: None if t is None else t.reshape(n, -1)[lo:hi]
                 for name, bit in STAGES:
                     if bit == 4 and not cfg.c.uncertainty:
                         continue
                     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
                     e0.record()
                     check(lib.lucifit_fit_stages(cfg.byref(), bit, hi - lo, _ptr(cube), _ptr(sl(index)), _ptr(sl(theta)),
-                                                 _ptr(sl(vel0)), _ptr(sl(broad0)), _ptr(bkg), _ptr(sl(rows)), _ptr(sl(sol)),
+                                                 _ptr(slp(vel0, 0)), _ptr(slp(broad0, 0)), _ptr(bkg), _ptr(sl(rows)), _ptr(sl(sol)),
                                                  _ptr(sl(unc)), _ptr(sl(status)), _ptr(ws), C.c_size_t(ws.numel()),
                                                  _stream()))
                     e1.record()

@@ -211,12 +211,12 @@ class Luci():
 
     # --------------------------------------------------------------------------------------------------- fits
     def _make_config(self, lines, fit_function, vel_rel, sigma_rel, uncertainty_bool, nii_cons, spec_min, spec_max,
-                     obj_redshift, ml_scale):
+                     obj_redshift, ml_scale, prior_groups=False):
         return FitConfig(fit_function, lines, vel_rel, sigma_rel, self.spectrum_axis, filter=self.hdr_dict['FILTER'],
                          delta_x=self.hdr_dict['STEP'], n_steps=self.step_nb, zpd_index=self.zpd_index,
                          trans_filter=self.transmission_interpolated, uncertainty_bool=uncertainty_bool,
                          nii_cons=nii_cons, spec_min=spec_min, spec_max=spec_max, obj_redshift=obj_redshift,
-                         ml_scale=ml_scale)
+                         ml_scale=ml_scale, prior_groups=prior_groups)
 
     @staticmethod
     def _reject_unsupported(bayes_bool, absorp, initial_values, n_stoch, bkgType):
@@ -250,8 +250,15 @@ class Luci():
         if not have_prior and self.ML_bool and fit_function != 'sinc':
             warnings.warn('no prior_values given: starting every fit from velocity = broadening = 0 like the '
                           "reference's ML_bool=False path, which only works for fit_function='sinc'")
+        # priors with a trailing axis carry one value per tie group (order of first appearance in vel_rel /
+        # sigma_rel): what a double-component fit needs to start its components apart
+        per_group = have_prior and np.ndim(prior_values[0]) == 3
         cfg = self._make_config(lines, fit_function, vel_rel, sigma_rel, uncertainty_bool, nii_cons, spec_min,
-                                spec_max, obj_redshift, ml_scale=have_prior)
+                                spec_max, obj_redshift, ml_scale=have_prior, prior_groups=per_group)
+        if per_group and (np.shape(prior_values[0])[2] != cfg.n_vel_groups or np.ndim(prior_values[1]) != 3
+                          or np.shape(prior_values[1])[2] != cfg.n_sigma_groups):
+            raise Exception('per-group prior_values must be (ny, nx, %d) velocities and (ny, nx, %d) broadenings'
+                            % (cfg.n_vel_groups, cfg.n_sigma_groups))
         dev = cube3d.device
         # fitted spaxels, ordered like the output maps: (y, x) row-major
         yy, xx = np.meshgrid(np.arange(y_min, y_max), np.arange(x_min, x_max), indexing='ij')

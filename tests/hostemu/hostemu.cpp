@@ -28,7 +28,8 @@ static void run_batch(const LfPlan& pl, int64_t n, const float* cube, const int6
     for (int64_t s = 0; s < n; ++s) {
         int64_t row = index ? index[s] : s;
         const float* gspec = cube + row * (int64_t)pl.dev.nz;
-        lf_stage_prep<MODEL, L, NG, NG, 1>(pl.dev, w, gspec, theta[s], vel0 ? vel0[s] : 0.0f, broad0 ? broad0[s] : 0.0f,
+        const int pnv = pl.dev.prior_groups ? pl.nv : 1, pns = pl.dev.prior_groups ? pl.ns : 1;
+        lf_stage_prep<MODEL, L, NG, NG, 1>(pl.dev, w, gspec, theta[s], vel0 ? vel0 + s * pnv : 0, broad0 ? broad0 + s * pns : 0,
                                            lf_work_at(LF_STAGE_PREP, ly, base), state);
         lf_stage_lm<MODEL, L, NG, NG, 1>(pl.dev, w, pl.dev.xo, gspec, lf_work_at(LF_STAGE_LM, ly, base), state);
         if (pl.dev.uncertainty)

@@ -128,3 +128,33 @@ def test_unsupported_branches_raise(world):
         luci.fit_cube(SN3, 'sinc', [1] * 5, [1] * 5, 0, 2, 0, 2, initial_values=[np.zeros((2, 2)), np.ones((2, 2))])
     with pytest.raises(Exception, match='vel_rel'):
         luci.fit_cube(SN3, 'sinc', [1] * 4, [1] * 5, 0, 2, 0, 2)
+
+
+def test_double_component_fit_with_per_group_priors_and_uncertainties(tmp_path):
+    """BASELINE config 4: 5 SN3 lines + a second Halpha component (vel_rel = sigma_rel = [1,1,1,1,1,2]) with
+    uncertainties, through Luci.fit_cube with one prior per tie group; device result == CPU build of the same source."""
+    from luci_b200.luci import Luci
+    from luci_b200.sim import sim_axis
+    from tests.test_hostemu_parity import _double_component_case
+    c = _double_component_case(n=6, seed=3)
+    dev = torch.device('cuda', 0)
+    nz = c['cube'].shape[1]
+    cube = torch.from_numpy(c['cube'].reshape(3, 2, nz)).to(dev)                  # [nx=3, ny=2, nz]
+    hdr_dict = {'FILTER': 'SN3', 'STEP': c['delta_x'], 'STEPNB': c['n_steps'], 'ZPDINDEX': 0}
+    luci = Luci.from_arrays(cube, hdr_dict, str(tmp_path), 'DBL', spectrum_axis=c['axis32'], device=dev)
+    luci.interferometer_theta = np.full((3, 2), 11.96)
+    rel = [1, 1, 1, 1, 1, 2]
+    # maps are (ny, nx[, group]); spaxel s of the flat x-major list sits at x = s // 2, y = s % 2
+    v0 = c['v0'].reshape(3, 2, 2).transpose(1, 0, 2).copy()
+    b0 = c['b0'].reshape(3, 2, 2).transpose(1, 0, 2).copy()
+    vel, broad, flux, ampl = luci.fit_cube(c['lines'], 'sincgauss', rel, rel, 0, 3, 0, 2, prior_values=(v0, b0),
+                                           uncertainty_bool=True)
+    assert vel.shape == (2, 3, 6)
+    truth = c['truth'].reshape(3, 2, 4).transpose(1, 0, 2)
+    np.testing.assert_allclose(vel[:, :, 0], truth[:, :, 0], atol=3.0)
+    np.testing.assert_allclose(vel[:, :, 5], truth[:, :, 1], atol=6.0)
+    m = luci.last_fit_maps
+    assert (m['vels_errors'] > 0).all() and (m['vels_errors'] < 100).all() and (m['flux_errors'] > 0).all()
+    assert (m['vels_errors'][:, :, 5] > m['vels_errors'][:, :, 0]).all()          # the weaker component is less certain
+    with pytest.raises(Exception):
+        luci.fit_cube(c['lines'], 'sincgauss', rel, rel, 0, 3, 0, 2, prior_values=(v0[:, :, :1], b0))

@@ -226,8 +226,8 @@ class Luci():
             raise NotImplementedError('absorption templates (LuciBase.py:354-356) are out of scope')
         if len(initial_values) == 2 or (len(initial_values) >= 1 and initial_values[0] is not False):
             raise NotImplementedError('initial_values selects the freeze branch (LuciFit.py:688-709): a "next" row')
-        if n_stoch != 1:
-            raise NotImplementedError('n_stoch > 1 (random restarts, LuciFit.py:662-687) is a "next" row')
+        if int(n_stoch) < 1:
+            raise ValueError('n_stoch must be >= 1')
         if bkgType == 'pca':
             raise NotImplementedError("bkgType='pca' (LuciBase.py:331-352) is a \"next\" row")
 
@@ -241,7 +241,7 @@ class Luci():
         return h
 
     def _fit_maps(self, cube3d, lines, fit_function, vel_rel, sigma_rel, x_min, x_max, y_min, y_max, mask, bkg,
-                  bkg_scale, uncertainty_bool, nii_cons, spec_min, spec_max, obj_redshift, prior_values):
+                  bkg_scale, uncertainty_bool, nii_cons, spec_min, spec_max, obj_redshift, prior_values, n_stoch=1):
         """Shared body of fit_cube / fit_region: returns the 12 maps as numpy float32 arrays (ny', nx'[, L])."""
         L = len(lines)
         nxc, nyc, nz = cube3d.shape
@@ -279,6 +279,22 @@ class Luci():
             bkg_t = torch.from_numpy(np.asarray(bkg, dtype=np.float32) * np.float32(bkg_scale)).to(dev)
         res = engine.fit_batch(cfg, cube3d.view(nxc * nyc, nz), theta_t, v0, b0, index=index, bkg=bkg_t)
         rows = res['rows']
+        L_ = len(lines)
+        for st in range(1, int(n_stoch)):
+            # random restarts (LuciFit.py:662-687): the reference redraws every line's position from
+            # N(p, |1e7/lambda - p| / 50) and sigma from N(sigma, sigma / 10) with numpy's global generator and keeps
+            # the fit with the lowest loss; in velocity units that is v ~ N(v0, |v0| / 50), b ~ N(b0, b0 / 10) per tie
+            # group, drawn here with the same generator and compared on the chi2 each fit reports
+            if not have_prior:
+                break                                                   # all draws would equal the start (v0 = b0 = 0)
+            v_np, b_np = v0.cpu().numpy(), b0.cpu().numpy()
+            v_r = torch.from_numpy(np.random.normal(v_np, np.abs(v_np) / 50.0).astype(np.float32)).to(dev)
+            b_r = torch.from_numpy(np.random.normal(b_np, np.abs(b_np) / 10.0).astype(np.float32)).to(dev)
+            alt = engine.fit_batch(cfg, cube3d.view(nxc * nyc, nz), theta_t, v_r, b_r, index=index, bkg=bkg_t)
+            ok_alt = (alt['status'] & (1 << 16)) != 0
+            better = ok_alt & (alt['rows'][:, 7 * L_] < rows[:, 7 * L_])
+            rows = torch.where(better[:, None], alt['rows'], rows)
+            res['status'] = torch.where(better, alt['status'], res['status'])
         K = cfg.row_floats
         full = torch.zeros((nyo * nxo, K), dtype=torch.float32, device=dev)
         pos = torch.from_numpy(np.flatnonzero(sel.ravel())).to(dev)
@@ -319,7 +335,8 @@ class Luci():
         use_bkg = bkg if bkgType == 'standard' else None                # LuciBase.py:325-330 (ignored otherwise)
         scale = (binning ** 2) if (binning and use_bkg is not None) else 1.0
         m = self._fit_maps(cube_to_slice, lines, fit_function, vel_rel, sigma_rel, x_min, x_max, y_min, y_max, None,
-                           use_bkg, scale, uncertainty_bool, nii_cons, spec_min, spec_max, obj_redshift, prior_values)
+                           use_bkg, scale, uncertainty_bool, nii_cons, spec_min, spec_max, obj_redshift, prior_values,
+                           n_stoch=n_stoch)
         save_fits(self.output_dir, self.object_name, lines, m['amplitudes'], m['fluxes'], m['flux_errors'],
                   m['velocities'], m['sigmas'], m['vels_errors'], m['sigmas_errors'], m['chi2'], m['continuum'],
                   m['continuum_error'], self._cutout_header(header, x_min, y_min), binning, fit_function=fit_function)
@@ -373,7 +390,8 @@ class Luci():
         self._ensure_deep()
         # fit_region never forwards bkgType, so the reference ignores bkg here (LuciBase.py:691-705, 325)
         m = self._fit_maps(cube_to_slice, lines, fit_function, vel_rel, sigma_rel, x_min, x_max, y_min, y_max, mask,
-                           None, 1.0, uncertainty_bool, nii_cons, spec_min, spec_max, obj_redshift, prior_values)
+                           None, 1.0, uncertainty_bool, nii_cons, spec_min, spec_max, obj_redshift, prior_values,
+                           n_stoch=n_stoch)
         save_fits(self.output_dir, self.object_name, lines, m['amplitudes'], m['fluxes'], m['flux_errors'],
                   m['velocities'], m['sigmas'], m['vels_errors'], m['sigmas_errors'], m['chi2'], m['continuum'],
                   m['continuum_error'], self._cutout_header(header, x_min, y_min), binning)
@@ -387,6 +405,8 @@ class Luci():
         """``LuciBase.py:949-1046``: fit the spectrum integrated over a mask.  Returns ``(axis, sky, fit_dict)``.
         ``prior_values=(vel, broad)`` are scalars in km/s."""
         self._reject_unsupported(bayes_bool, None, initial_values, n_stoch, None)
+        if int(n_stoch) != 1:
+            raise NotImplementedError('n_stoch > 1 is implemented for the cube fits (fit_cube / fit_region) only')
         mask = torch.from_numpy(np.asarray(self._load_mask(region, False)).astype(bool)).to(self.cube_final.device)
         spec_ct = int(mask.sum().item())
         integrated = self.cube_final[mask].sum(dim=0, dtype=torch.float64)

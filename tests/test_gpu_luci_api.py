@@ -158,3 +158,12 @@ def test_double_component_fit_with_per_group_priors_and_uncertainties(tmp_path):
     assert (m['vels_errors'][:, :, 5] > m['vels_errors'][:, :, 0]).all()          # the weaker component is less certain
     with pytest.raises(Exception):
         luci.fit_cube(c['lines'], 'sincgauss', rel, rel, 0, 3, 0, 2, prior_values=(v0[:, :, :1], b0))
+    # n_stoch restarts (LuciFit.py:662-687): never worse than the single start, same seed -> same maps
+    chi1 = m['chi2'].copy()
+    np.random.seed(7)
+    luci.fit_cube(c['lines'], 'sincgauss', rel, rel, 0, 3, 0, 2, prior_values=(v0, b0), n_stoch=4)
+    chi4 = luci.last_fit_maps['chi2'].copy()
+    assert (chi4 <= chi1 * (1 + 1e-6)).all()
+    np.random.seed(7)
+    luci.fit_cube(c['lines'], 'sincgauss', rel, rel, 0, 3, 0, 2, prior_values=(v0, b0), n_stoch=4)
+    np.testing.assert_array_equal(luci.last_fit_maps['chi2'], chi4)

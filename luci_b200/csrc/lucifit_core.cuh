@@ -37,6 +37,11 @@
 #define LF_MAX_LINES 8
 #define LF_C_KMS 299792.0f        /* LuciFit.py:26 (integer km/s in the reference) */
 #define LF_MAX_CONT_WIN 256       /* samples of the continuum window handled by the clip */
+#ifndef LF_TUNE_SLACK
+#define LF_TUNE_SLACK_PRED 1e-4
+#define LF_TUNE_SLACK 4e-6
+#define LF_TUNE_REJ_CONV 1e-5
+#endif
 
 // status word: bits 0-7 accepted LM iterations, bits 8-15 model evaluations, bits 16.. flags
 enum {
@@ -821,7 +826,7 @@ LF_CORE void lf_stage_lm(const LfCfg& cfg, const LfWarp<LANES>& w, const float* 
             const bool finite = chi2t == chi2t;
             // An FP32 evaluation resolves sum r^2 to a few 1e-6 relative; once the predicted decrease is that small
             // the gradient (still accurate) is trusted and the step is taken even if chi2 appears to rise by noise.
-            const double slack = ((double)pred <= 1e-4 * chi2) ? 4e-6 * chi2 : 0.0;
+            const double slack = ((double)pred <= LF_TUNE_SLACK_PRED * chi2) ? LF_TUNE_SLACK * chi2 : 0.0;
             if (finite && chi2t <= chi2 + slack) {
                 double act = chi2 - chi2t;
                 float rho = pred > 0.0f ? (float)(act / (double)pred) : 1.0f;
@@ -837,7 +842,7 @@ LF_CORE void lf_stage_lm(const LfCfg& cfg, const LfWarp<LANES>& w, const float* 
                 // sum r^2 (relative ~1e-6) a rejection only means "converged"
                 lam *= nu; nu *= 2.0f;
                 ++tries;
-                if (finite && (double)pred <= 1e-5 * chi2) { done = true; flags |= LF_ST_CONVERGED; }
+                if (finite && (double)pred <= LF_TUNE_REJ_CONV * chi2) { done = true; flags |= LF_ST_CONVERGED; }
             }
         }
         if (accepted) {

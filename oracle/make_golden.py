@@ -45,6 +45,10 @@ CASES = {
                                  sigma_rel=[1], n=12, unc=True, broad=(25, 60), seed=108),
     'fit_sinc_noml': dict(filter='SN3', R=5000, lines=SN3, model='sinc', vel_rel=[1] * 5, sigma_rel=[1] * 5,
                           n=4, unc=False, broad=(20, 60), seed=109, noml=True),
+    # the benchmark's configuration (BASELINE.json configs[1]: nz = 841, 5-line sincgauss, ties + [NII] ratio) on a
+    # sample large enough to test the north_star's "99.9 % of spaxels" (run with --jobs 8: ~0.8 s/spaxel/core)
+    'parity_sincgauss_cfg2': dict(filter='SN3', R=5917, lines=SN3, model='sincgauss', vel_rel=[1] * 5,
+                                  sigma_rel=[1] * 5, n=1000, unc=False, broad=(25, 60), seed=110),
 }
 
 BASE_AMP = {'Halpha': 1.0, 'NII6583': 0.3, 'NII6548': 0.1, 'SII6716': 0.15, 'SII6731': 0.12, 'Hbeta': 1.0,
@@ -89,6 +93,32 @@ def build_inputs(case):
     return dict(cube=cube, axis32=np.asarray(axis, dtype=np.float32), v0=np.array(v0, np.float32),
                 b0=np.array(b0, np.float32), theta=np.full(n, theta, np.float32), n_steps=sp.n_steps,
                 delta_x=sp.delta_x)
+
+
+def _run_slice(args):
+    case, inp, lo, hi = args
+    sub = dict(inp)
+    for k in ('cube', 'v0', 'b0', 'theta'):
+        sub[k] = inp[k][lo:hi]
+    with warnings.catch_warnings():
+        warnings.simplefilter('ignore')
+        return run_reference(case, sub)
+
+
+def run_reference_parallel(case, inp, jobs):
+    """The same per-spaxel reference runs, fanned out over processes (each spaxel is independent)."""
+    import multiprocessing as mp
+    n = inp['cube'].shape[0]
+    edges = np.linspace(0, n, jobs + 1).astype(int)
+    with mp.get_context('fork').Pool(jobs) as pool:
+        parts = pool.map(_run_slice, [(case, inp, int(a), int(b)) for a, b in zip(edges[:-1], edges[1:]) if b > a])
+    out = {}
+    for k in parts[0]:
+        if k == 'ref_seconds_per_spaxel':
+            out[k] = np.array(np.mean([float(p[k]) for p in parts]))
+        else:
+            out[k] = np.concatenate([p[k] for p in parts], axis=0)
+    return out
 
 
 def run_reference(case, inp):
@@ -140,12 +170,12 @@ def run_reference(case, inp):
 _cur = {'i': 0}
 
 
-def make(name):
+def make(name, jobs=1):
     case = CASES[name]
     inp = build_inputs(case)
     with warnings.catch_warnings():
         warnings.simplefilter('ignore')
-        ref = run_reference(case, inp)
+        ref = run_reference_parallel(case, inp, jobs) if jobs > 1 else run_reference(case, inp)
     meta = dict(filter=case['filter'], model=case['model'], lines=np.array(case['lines']),
                 vel_rel=np.array(case['vel_rel']), sigma_rel=np.array(case['sigma_rel']),
                 uncertainty=np.array(case['unc']), noml=np.array(bool(case.get('noml'))),
@@ -158,9 +188,16 @@ def make(name):
 
 
 if __name__ == '__main__':
-    names = [a for a in sys.argv[1:] if a != "reductions"] or ([] if "reductions" in sys.argv[1:] else list(CASES))
+    argv = sys.argv[1:]
+    jobs = 1
+    if '--jobs' in argv:
+        jobs = int(argv[argv.index('--jobs') + 1])
+        del argv[argv.index('--jobs'):argv.index('--jobs') + 2]
+    sys.argv = sys.argv[:1] + argv
+    names = [a for a in argv if a != "reductions"] or ([] if "reductions" in argv else
+                                                       [c for c in CASES if not c.startswith('parity_')])
     for nm in names:
-        make(nm)
+        make(nm, jobs)
 
 
 # ------------------------------------------------------------------------------------------------ reductions

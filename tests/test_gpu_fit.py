@@ -206,3 +206,14 @@ def test_host_cube_stream_equals_resident_path():
         assert torch.equal(host_status, ref['status'].cpu())
     with pytest.raises(TypeError):
         stream.run(cube, host_par, host_rows)                                  # device tensor: not a host cube
+
+
+def test_cuda_large_sample_parity_config2():
+    """1000 spaxels of the benchmark configuration against the unmodified reference (north_star: 99.9 % of spaxels
+    within 0.5 km/s, 1e-3 relative broadening / flux, chi2 not worse by more than 1e-4), through the C ABI."""
+    from tests.common import check_large_sample_parity
+    from tests.test_hostemu_parity import _float64_objective_factory
+    g = load_golden('parity_sincgauss_cfg2')
+    cfg = config_from_golden(g, uncertainty=False)
+    res = _gpu_fit(cfg, g['cube'], g['theta'], g['v0'], g['b0'])
+    check_large_sample_parity(res['rows'], res['status'], g, _float64_objective_factory(g))

@@ -174,3 +174,44 @@ def test_hostemu_double_component_with_per_group_priors(hostemu):
                                  np.ascontiguousarray(c['b0'][:, 0]), want_unc=False)
     ratio = rows[:, 7 * L] / rows1[:, 7 * L]                                    # never worse, and clearly better where
     assert (ratio < 1 + 1e-4).all() and ratio.min() < 0.7                       # the shared prior stays on the saddle
+
+
+def _float64_objective_factory(g):
+    """Float64 sum of squared residuals of the normalised fit window (the quantity both optimisers minimise, up to
+    the constant noise factor) at our solution and at the reference's."""
+    import warnings
+    from oracle import luci_oracle as O
+
+    def objective(i, theta_full, scale):
+        with warnings.catch_warnings():
+            warnings.simplefilter('ignore')
+            f = O.OracleFit(g['cube'][i].astype(np.float64), g['axis32'], g['model'], g['lines'], [1] * 5, [1] * 5,
+                            theta=float(g['theta'][i]), delta_x=float(g['delta_x']), n_steps=int(g['n_steps']),
+                            zpd_index=0, filter='SN3', nii_cons=True, prior=(float(g['v0'][i]), float(g['b0'][i])))
+        th = np.array(theta_full, dtype=float).copy()
+        th[0:15:3] /= scale
+        th[-1] /= scale
+        m = O.model_sum(g['model'], f.axis_restricted, th, 5, f.sinc_width) + th[-1]
+        return float(np.sum((f.spectrum_restricted_norm - m) ** 2))
+
+    def both(i, rep):
+        from oracle import luci_oracle as O2
+        q, ours = rep['q'], np.zeros(16)
+        for k, line in enumerate(g['lines']):
+            p = 1e7 / (O2.LINE_DICT[line] * (1 + q['velocities'][i][k] / 299792.0))
+            ours[3 * k], ours[3 * k + 1], ours[3 * k + 2] = q['amplitudes'][i][k], p, p * q['sigmas'][i][k] / 299792.0
+        ours[-1] = q['continuum'][i]
+        return objective(i, ours, g['ref_scale'][i]), objective(i, g['ref_fit_sol'][i], g['ref_scale'][i])
+
+    return both
+
+
+def test_hostemu_large_sample_parity_config2(hostemu):
+    """1000 spaxels of the benchmark configuration (nz = 841, 5-line sincgauss, ties + [NII] ratio) against the
+    unmodified reference: the north_star's 99.9 % criterion."""
+    from tests.common import check_large_sample_parity
+    g = load_golden('parity_sincgauss_cfg2')
+    cfg = config_from_golden(g, uncertainty=False)
+    rows, sol, unc, st = run_hostemu(hostemu, cfg, g['cube'], g['theta'], g['v0'], g['b0'], want_unc=False)
+    rep = check_large_sample_parity(rows, st, g, _float64_objective_factory(g))
+    assert (((st >> 8) & 0xff).mean()) < 7

@@ -230,6 +230,7 @@ def main():
     from luci_b200.sim import SyntheticCube
 
     rank, world, local = ldist.init_process_group()
+    cpus = ldist.bind_to_gpu_cpus(local) if world > 1 else None       # NUMA-local pinned buffers for the e2e stream
     assert torch.cuda.is_available(), 'bench.py needs a GPU (there is no CPU fallback)'
     dev = torch.device('cuda', local)
     torch.cuda.set_device(dev)
@@ -434,7 +435,7 @@ def run_e2e(torch, engine, ldist, cfg, cube, theta, v0, b0, dev, args, world, n_
     return {'value': n_done / dt, 'unit': 'spaxels/s', 'h2d_bytes_per_step': h2d,
             'd2h_bytes_per_step': int(n_done * K * 4), 'ms_per_step': dt * 1e3,
             'h2d_gbs_achieved_per_gpu': h2d / world / dt / 1e9, 'h2d_gbs_single_copy': h2d_gbs,
-            'note': 'cube in pinned host memory, engine.HostCubeStream: %d-spaxel chunks, %d device buffers, copy / fit / '
+            'note': 'cube in pinned host memory (process bound to the GPU-local CPU cores when N > 1), engine.HostCubeStream: %d-spaxel chunks, %d device buffers, copy / fit / '
                     'copy-back on three streams; fraction of the cube streamed per step: %.2f'
                     % (stream.chunk, stream.nb, frac)}
 

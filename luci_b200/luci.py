@@ -228,8 +228,6 @@ class Luci():
             raise NotImplementedError('initial_values selects the freeze branch (LuciFit.py:688-709): a "next" row')
         if int(n_stoch) < 1:
             raise ValueError('n_stoch must be >= 1')
-        if bkgType == 'pca':
-            raise NotImplementedError("bkgType='pca' (LuciBase.py:331-352) is a \"next\" row")
 
     def _cutout_header(self, header, x_min, y_min):
         """What ``Cutout2D(...).wcs.to_header()`` changes for a rectangular cut-out: the reference pixel."""
@@ -241,8 +239,12 @@ class Luci():
         return h
 
     def _fit_maps(self, cube3d, lines, fit_function, vel_rel, sigma_rel, x_min, x_max, y_min, y_max, mask, bkg,
-                  bkg_scale, uncertainty_bool, nii_cons, spec_min, spec_max, obj_redshift, prior_values, n_stoch=1):
-        """Shared body of fit_cube / fit_region: returns the 12 maps as numpy float32 arrays (ny', nx'[, L])."""
+                  bkg_scale, uncertainty_bool, nii_cons, spec_min, spec_max, obj_redshift, prior_values, n_stoch=1,
+                  pca=None):
+        """Shared body of fit_cube / fit_region: returns the 12 maps as numpy float32 arrays (ny', nx'[, L]).
+
+        ``pca = (coefficients [n_fit_x, n_fit_y, n_comp] already summed over the bin, vectors [n_comp, nz], mean [nz])``
+        selects the reference's PCA background (LuciBase.py:331-352)."""
         L = len(lines)
         nxc, nyc, nz = cube3d.shape
         nxo, nyo = x_max - x_min, y_max - y_min
@@ -277,7 +279,27 @@ class Luci():
         bkg_t = None
         if bkg is not None:
             bkg_t = torch.from_numpy(np.asarray(bkg, dtype=np.float32) * np.float32(bkg_scale)).to(dev)
-        res = engine.fit_batch(cfg, cube3d.view(nxc * nyc, nz), theta_t, v0, b0, index=index, bkg=bkg_t)
+        cube2d = cube3d.view(nxc * nyc, nz)
+        if pca is not None:
+            # PCA background (LuciBase.py:331-352): bkg = mean + coefficients . vectors per spaxel -- the one dense
+            # contraction of the pipeline, a [n x n_comp] . [n_comp x nz] library GEMM -- scaled by the maximum of the
+            # spectrum in the filter's reference band, subtracted into a compacted copy of the fitted spectra
+            coef, vecs, mean = pca
+            coef_t = torch.from_numpy(np.ascontiguousarray(np.asarray(coef, dtype=np.float32)[xx[sel] - x_min, yy[sel] - y_min])).to(dev)
+            vecs_t = torch.from_numpy(np.ascontiguousarray(vecs, dtype=np.float32)).to(dev)
+            mean_t = torch.from_numpy(np.ascontiguousarray(mean, dtype=np.float32)).to(dev)
+            band = {'SN3': (675.0, 670.0), 'SN2': (505.0, 480.0)}.get(self.hdr_dict['FILTER'])
+            if band is None:
+                raise Exception('the PCA background is implemented for SN3 and SN2 (LuciBase.py:332-341)')
+            nm_axis = 1e7 / np.asarray(self.spectrum_axis, dtype=np.float64)
+            lo_i, hi_i = int(np.argmin(np.abs(nm_axis - band[0]))), int(np.argmin(np.abs(nm_axis - band[1])))
+            sky = cube2d[index]
+            bkg_pix = torch.addmm(mean_t[None, :].expand(sky.shape[0], nz), coef_t, vecs_t)
+            ref_band = sky[:, lo_i:hi_i]
+            scale_spec = torch.where(torch.isnan(ref_band), torch.full_like(ref_band, -float('inf')), ref_band).amax(dim=1)
+            cube2d = (sky - scale_spec[:, None] * bkg_pix).contiguous()
+            index = None
+        res = engine.fit_batch(cfg, cube2d, theta_t, v0, b0, index=index, bkg=bkg_t)
         rows = res['rows']
         L_ = len(lines)
         for st in range(1, int(n_stoch)):
@@ -290,7 +312,7 @@ class Luci():
             v_np, b_np = v0.cpu().numpy(), b0.cpu().numpy()
             v_r = torch.from_numpy(np.random.normal(v_np, np.abs(v_np) / 50.0).astype(np.float32)).to(dev)
             b_r = torch.from_numpy(np.random.normal(b_np, np.abs(b_np) / 10.0).astype(np.float32)).to(dev)
-            alt = engine.fit_batch(cfg, cube3d.view(nxc * nyc, nz), theta_t, v_r, b_r, index=index, bkg=bkg_t)
+            alt = engine.fit_batch(cfg, cube2d, theta_t, v_r, b_r, index=index, bkg=bkg_t)
             ok_alt = (alt['status'] & (1 << 16)) != 0
             better = ok_alt & (alt['rows'][:, 7 * L_] < rows[:, 7 * L_])
             rows = torch.where(better[:, None], alt['rows'], rows)
@@ -323,6 +345,7 @@ class Luci():
         self._reject_unsupported(bayes_bool, absorp, initial_values, n_stoch, bkgType)
         cube_to_slice = self.cube_final
         header = self.header
+        x0_unbinned, y0_unbinned = x_min, y_min
         if binning is not None and binning != 1:
             self.bin_cube(self.cube_final, self.header, binning, x_min, x_max, y_min, y_max)
             x_max = int((x_max - x_min) / binning)
@@ -334,9 +357,23 @@ class Luci():
         self._ensure_deep()
         use_bkg = bkg if bkgType == 'standard' else None                # LuciBase.py:325-330 (ignored otherwise)
         scale = (binning ** 2) if (binning and use_bkg is not None) else 1.0
+        pca = None
+        if bkgType == 'pca':
+            if pca_coefficient_array is None or pca_vectors is None or pca_mean is None:
+                raise Exception("bkgType='pca' needs pca_coefficient_array, pca_vectors and pca_mean")
+            coef = np.asarray(pca_coefficient_array, dtype=np.float64)
+            if binning is not None and binning != 1:                    # coefficients of a bin: nansum over it (:343-347)
+                b_ = int(binning)
+                c_ = coef[x0_unbinned:x0_unbinned + x_max * b_, y0_unbinned:y0_unbinned + y_max * b_]
+                coef = np.nansum(np.nansum(c_.reshape(x_max, b_, y_max, b_, -1), axis=3), axis=1)
+            else:
+                coef = coef[x_min:x_max, y_min:y_max]
+            pca = (coef, np.asarray(pca_vectors), np.asarray(pca_mean))
+        elif bkgType not in (None, 'standard'):
+            raise Exception('Please set bkgType to either standard or pca')
         m = self._fit_maps(cube_to_slice, lines, fit_function, vel_rel, sigma_rel, x_min, x_max, y_min, y_max, None,
                            use_bkg, scale, uncertainty_bool, nii_cons, spec_min, spec_max, obj_redshift, prior_values,
-                           n_stoch=n_stoch)
+                           n_stoch=n_stoch, pca=pca)
         save_fits(self.output_dir, self.object_name, lines, m['amplitudes'], m['fluxes'], m['flux_errors'],
                   m['velocities'], m['sigmas'], m['vels_errors'], m['sigmas_errors'], m['chi2'], m['continuum'],
                   m['continuum_error'], self._cutout_header(header, x_min, y_min), binning, fit_function=fit_function)

@@ -167,3 +167,35 @@ def test_double_component_fit_with_per_group_priors_and_uncertainties(tmp_path):
     np.random.seed(7)
     luci.fit_cube(c['lines'], 'sincgauss', rel, rel, 0, 3, 0, 2, prior_values=(v0, b0), n_stoch=4)
     np.testing.assert_array_equal(luci.last_fit_maps['chi2'], chi4)
+
+
+def test_pca_background_equals_fit_of_presubtracted_cube(world, tmp_path):
+    """bkgType='pca' (LuciBase.py:331-352): sky -= max(sky[band]) * (mean + coefficients . vectors) per spaxel, done
+    on the device; same maps as fitting a cube from which that background was subtracted on the host in float64."""
+    from luci_b200.luci import Luci
+    luci, sc, out = world
+    rng = np.random.default_rng(5)
+    cube = luci.cube_final.cpu().numpy().astype(np.float64)                      # [nx, ny, nz]
+    nx, ny, nz = cube.shape
+    n_comp = 4
+    z = np.linspace(0, 1, nz)
+    vectors = np.stack([np.sin((k + 1) * np.pi * z) * 0.02 for k in range(n_comp)])
+    mean = 0.01 + 0.005 * z
+    coef = rng.normal(0, 1, (nx, ny, n_comp))
+    nm = 1e7 / np.asarray(luci.spectrum_axis, dtype=np.float64)
+    lo, hi = int(np.argmin(np.abs(nm - 675))), int(np.argmin(np.abs(nm - 670)))
+    scale = np.nanmax(cube[:, :, lo:hi], axis=2)
+    pre = cube - scale[:, :, None] * (mean[None, None, :] + coef @ vectors)
+    v0, b0 = sc.priors()
+    args = (SN3, 'sincgauss', [1] * 5, [1] * 5, 1, 11, 2, 9)
+    pv = (v0[2:9, 1:11], b0[2:9, 1:11])
+    vel, broad, flux, ampl = luci.fit_cube(*args, prior_values=pv, bkgType='pca', pca_coefficient_array=coef,
+                                           pca_vectors=vectors, pca_mean=mean)
+    luci2 = Luci.from_arrays(torch.from_numpy(pre.astype(np.float32)).to(luci.cube_final.device), sc.hdr_dict,
+                             str(tmp_path), 'PRE', spectrum_axis=sc.axis32, device=luci.cube_final.device)
+    vel2, broad2, flux2, ampl2 = luci2.fit_cube(*args, prior_values=pv)
+    np.testing.assert_allclose(vel, vel2, atol=5e-2)
+    np.testing.assert_allclose(flux, flux2, rtol=2e-3)
+    np.testing.assert_allclose(broad, broad2, rtol=1e-3)
+    with pytest.raises(Exception):
+        luci.fit_cube(*args, prior_values=pv, bkgType='pca')                     # the PCA arrays are required

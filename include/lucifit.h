@@ -73,6 +73,10 @@ typedef struct lucifit_config {
     int prior_groups;                         /* 0: vel0 / broad0 hold one value per spaxel (the reference's CNN output);
                                                  1: vel0 is [n_spaxel][NV], broad0 [n_spaxel][NS], one prior per tie group in
                                                  order of first appearance in vel_group / sigma_group (double components) */
+    int freeze;                               /* 1: the reference's freeze branch (initial_values, LuciFit.py:159-162, 688-709):
+                                                 vel0 / broad0 are FROZEN, only amplitudes and continuum are fitted, without
+                                                 ties or boxes, continuum guess clipped at 3 sigma; sincgauss only (the
+                                                 reference's gaussian / sinc freeze paths raise IndexError) */
 } lucifit_config;
 
 /* Number of floats per spaxel in out_rows: 7 L + 5, ordered

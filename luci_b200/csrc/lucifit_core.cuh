@@ -60,6 +60,7 @@ struct LfCfg {                     // device-side constants of one lucifit_fit_b
     int i48, i83;                  // [NII] tie: indices of NII6548 / NII6583, -1 when off
     int sigbox_group;              // sigma group of the LAST line: 0 <= sigma <= 10 cm^-1 (LuciFit.py:539-541)
     int uncertainty, ml_scale, max_iter, n_out;
+    int freeze;                    // 1: velocity / broadening columns pinned at the priors, no ties, no boxes (LuciFit.py:688-709)
     int prior_groups;              // 1: priors are per group ([nv] velocities, [ns] broadenings per spaxel), 0: one pair
     int state_floats;              // stride of the state record
     float ftol;
@@ -664,6 +665,10 @@ LF_CORE void lf_bounds(const LfCfg& cfg, const float* th, float* lo, float* hi)
         hi[D::IS + h] = (h == cfg.sigbox_group) ? 10.0f * LF_C_KMS / plast : INFINITY;
     }
     lo[D::IC] = -1e-8f; hi[D::IC] = 0.99f;
+    if (cfg.freeze) {                                  // unconstrained SLSQP on amplitudes + continuum (:699-703)
+#pragma unroll
+        for (int j = 0; j < D::P; ++j) { lo[j] = -INFINITY; hi[j] = INFINITY; }
+    }
 }
 
 // ---------------------------------------------------------------------------------------------- stage: prep
@@ -713,7 +718,8 @@ LF_CORE void lf_stage_prep(const LfCfg& cfg, const LfWarp<LANES>& w, const float
         s2 = w.sum(s2);
         noise = n > 0 ? sqrt(s2 / n) / (double)smax : NAN;
     }
-    const double cont0 = lf_cont_estimate(w, spec, cfg.cont_lo, cfg.cont_hi, 1.0, wk.sortv, wk.npad) / (double)smax;
+    // sigma_level: 1 in the free fit (LuciFit.py:661), 3 in the freeze branch (:690)
+    const double cont0 = lf_cont_estimate(w, spec, cfg.cont_lo, cfg.cont_hi, cfg.freeze ? 3.0 : 1.0, wk.sortv, wk.npad) / (double)smax;
     // scale: ML-prior path max(spectrum_restricted) * max(spectrum_T) ; plain path max(spectrum_T)
     const double scale = cfg.ml_scale ? ((double)wmax / (double)smax) * (double)tmax : (double)tmax;
     const double ct = fabs(cos((double)theta_deg * 0.017453292519943295));
@@ -862,6 +868,7 @@ LF_CORE void lf_stage_lm(const LfCfg& cfg, const LfWarp<LANES>& w, const float* 
                 bool at_hi = th[j] >= hi[j] && gj >= 0.0f;
                 if (at_lo || at_hi) fixedmask |= 1u << j;
             }
+            if (cfg.freeze) fixedmask |= ((1u << D::IC) - 1u) & ~((1u << D::IV) - 1u);   // pin every v and beta column
             if (!(iters < cfg.max_iter && evals < 250)) { flags |= LF_ST_MAXITER; done = true; }
         }
         if (done) break;

@@ -132,6 +132,13 @@ static inline std::string lf_make_plan(const lucifit_config* c, LfPlan& pl, int 
     d.uncertainty = c->uncertainty ? 1 : 0;
     d.ml_scale = c->scale_mode ? 1 : 0;
     d.prior_groups = c->prior_groups ? 1 : 0;
+    d.freeze = c->freeze ? 1 : 0;
+    if (d.freeze) {
+        if (c->model != LUCIFIT_SINCGAUSS) return "freeze is defined for the sincgauss model only (the reference's gaussian / sinc freeze paths fail)";
+        if (c->uncertainty) return "freeze with uncertainty_bool is broken in the reference (LuciFit.py:713-722 on an L+1 vector) and not offered";
+        d.i48 = d.i83 = -1;                            // no constraints in the freeze branch (LuciFit.py:699-703)
+        d.ml_scale = 0;                                // scale = max(spectrum) (LuciFit.py:776-782: interpolate_spectrum is skipped)
+    }
     d.max_iter = c->max_iter > 0 ? c->max_iter : 60;
     d.ftol = c->ftol > 0 ? (float)c->ftol : 1e-8f;
     d.n_out = 7 * L + 5;

@@ -211,12 +211,12 @@ class Luci():
 
     # --------------------------------------------------------------------------------------------------- fits
     def _make_config(self, lines, fit_function, vel_rel, sigma_rel, uncertainty_bool, nii_cons, spec_min, spec_max,
-                     obj_redshift, ml_scale, prior_groups=False):
+                     obj_redshift, ml_scale, prior_groups=False, freeze=False):
         return FitConfig(fit_function, lines, vel_rel, sigma_rel, self.spectrum_axis, filter=self.hdr_dict['FILTER'],
                          delta_x=self.hdr_dict['STEP'], n_steps=self.step_nb, zpd_index=self.zpd_index,
                          trans_filter=self.transmission_interpolated, uncertainty_bool=uncertainty_bool,
                          nii_cons=nii_cons, spec_min=spec_min, spec_max=spec_max, obj_redshift=obj_redshift,
-                         ml_scale=ml_scale, prior_groups=prior_groups)
+                         ml_scale=ml_scale, prior_groups=prior_groups, freeze=freeze)
 
     @staticmethod
     def _reject_unsupported(bayes_bool, absorp, initial_values, n_stoch, bkgType):
@@ -224,8 +224,6 @@ class Luci():
             raise NotImplementedError('bayes_bool=True (emcee/dynesty MCMC, LuciFit.py:930-1015) is out of scope')
         if absorp is not None:
             raise NotImplementedError('absorption templates (LuciBase.py:354-356) are out of scope')
-        if len(initial_values) == 2 or (len(initial_values) >= 1 and initial_values[0] is not False):
-            raise NotImplementedError('initial_values selects the freeze branch (LuciFit.py:688-709): a "next" row')
         if int(n_stoch) < 1:
             raise ValueError('n_stoch must be >= 1')
 
@@ -240,7 +238,7 @@ class Luci():
 
     def _fit_maps(self, cube3d, lines, fit_function, vel_rel, sigma_rel, x_min, x_max, y_min, y_max, mask, bkg,
                   bkg_scale, uncertainty_bool, nii_cons, spec_min, spec_max, obj_redshift, prior_values, n_stoch=1,
-                  pca=None):
+                  pca=None, initial_values=(False,)):
         """Shared body of fit_cube / fit_region: returns the 12 maps as numpy float32 arrays (ny', nx'[, L]).
 
         ``pca = (coefficients [n_fit_x, n_fit_y, n_comp] already summed over the bin, vectors [n_comp, nz], mean [nz])``
@@ -248,6 +246,15 @@ class Luci():
         L = len(lines)
         nxc, nyc, nz = cube3d.shape
         nxo, nyo = x_max - x_min, y_max - y_min
+        # initial_values = [velocity map, broadening map] (ny', nx') selects the reference's freeze branch
+        # (LuciFit.py:159-162, 688-709; LuciBase.py:361-364): those values are held, amplitudes + continuum are fitted
+        freeze = len(initial_values) >= 1 and initial_values[0] is not False
+        if freeze:
+            if uncertainty_bool:
+                raise NotImplementedError('uncertainty_bool with initial_values is broken in the reference '
+                                          '(LuciFit.py:713-722 on an L+1 vector) and not offered')
+            prior_values = (np.asarray(initial_values[0], dtype=np.float32), np.asarray(initial_values[1], dtype=np.float32))
+            n_stoch = 1
         have_prior = prior_values is not None
         if not have_prior and self.ML_bool and fit_function != 'sinc':
             warnings.warn('no prior_values given: starting every fit from velocity = broadening = 0 like the '
@@ -256,7 +263,7 @@ class Luci():
         # sigma_rel): what a double-component fit needs to start its components apart
         per_group = have_prior and np.ndim(prior_values[0]) == 3
         cfg = self._make_config(lines, fit_function, vel_rel, sigma_rel, uncertainty_bool, nii_cons, spec_min,
-                                spec_max, obj_redshift, ml_scale=have_prior, prior_groups=per_group)
+                                spec_max, obj_redshift, ml_scale=have_prior, prior_groups=per_group, freeze=freeze)
         if per_group and (np.shape(prior_values[0])[2] != cfg.n_vel_groups or np.ndim(prior_values[1]) != 3
                           or np.shape(prior_values[1])[2] != cfg.n_sigma_groups):
             raise Exception('per-group prior_values must be (ny, nx, %d) velocities and (ny, nx, %d) broadenings'
@@ -373,7 +380,7 @@ class Luci():
             raise Exception('Please set bkgType to either standard or pca')
         m = self._fit_maps(cube_to_slice, lines, fit_function, vel_rel, sigma_rel, x_min, x_max, y_min, y_max, None,
                            use_bkg, scale, uncertainty_bool, nii_cons, spec_min, spec_max, obj_redshift, prior_values,
-                           n_stoch=n_stoch, pca=pca)
+                           n_stoch=n_stoch, pca=pca, initial_values=initial_values)
         save_fits(self.output_dir, self.object_name, lines, m['amplitudes'], m['fluxes'], m['flux_errors'],
                   m['velocities'], m['sigmas'], m['vels_errors'], m['sigmas_errors'], m['chi2'], m['continuum'],
                   m['continuum_error'], self._cutout_header(header, x_min, y_min), binning, fit_function=fit_function)
@@ -428,7 +435,7 @@ class Luci():
         # fit_region never forwards bkgType, so the reference ignores bkg here (LuciBase.py:691-705, 325)
         m = self._fit_maps(cube_to_slice, lines, fit_function, vel_rel, sigma_rel, x_min, x_max, y_min, y_max, mask,
                            None, 1.0, uncertainty_bool, nii_cons, spec_min, spec_max, obj_redshift, prior_values,
-                           n_stoch=n_stoch)
+                           n_stoch=n_stoch, initial_values=initial_values)
         save_fits(self.output_dir, self.object_name, lines, m['amplitudes'], m['fluxes'], m['flux_errors'],
                   m['velocities'], m['sigmas'], m['vels_errors'], m['sigmas_errors'], m['chi2'], m['continuum'],
                   m['continuum_error'], self._cutout_header(header, x_min, y_min), binning)
@@ -444,6 +451,8 @@ class Luci():
         self._reject_unsupported(bayes_bool, None, initial_values, n_stoch, None)
         if int(n_stoch) != 1:
             raise NotImplementedError('n_stoch > 1 is implemented for the cube fits (fit_cube / fit_region) only')
+        if len(initial_values) >= 1 and initial_values[0] is not False:
+            raise NotImplementedError('initial_values (freeze) is implemented for the cube fits (fit_cube / fit_region) only')
         mask = torch.from_numpy(np.asarray(self._load_mask(region, False)).astype(bool)).to(self.cube_final.device)
         spec_ct = int(mask.sum().item())
         integrated = self.cube_final[mask].sum(dim=0, dtype=torch.float64)

@@ -45,6 +45,10 @@ CASES = {
                                  sigma_rel=[1], n=12, unc=True, broad=(25, 60), seed=108),
     'fit_sinc_noml': dict(filter='SN3', R=5000, lines=SN3, model='sinc', vel_rel=[1] * 5, sigma_rel=[1] * 5,
                           n=4, unc=False, broad=(20, 60), seed=109, noml=True),
+    # the reference's freeze branch (initial_values = frozen velocity / broadening, amplitudes + continuum fitted
+    # without constraints, LuciFit.py:688-709); only sincgauss works there (gaussian / sinc raise IndexError)
+    'fit_sincgauss_freeze': dict(filter='SN3', R=5000, lines=SN3, model='sincgauss', vel_rel=[1] * 5, sigma_rel=[1] * 5,
+                                 n=16, unc=False, broad=(25, 60), seed=111, freeze=True),
     # the benchmark's configuration (BASELINE.json configs[1]: nz = 841, 5-line sincgauss, ties + [NII] ratio) on a
     # sample large enough to test the north_star's "99.9 % of spaxels" (run with --jobs 8: ~0.8 s/spaxel/core)
     'parity_sincgauss_cfg2': dict(filter='SN3', R=5917, lines=SN3, model='sincgauss', vel_rel=[1] * 5,
@@ -87,8 +91,12 @@ def build_inputs(case):
         bfit = broad * np.cos(np.deg2rad(theta)) * 299792 / 3e5
         # per velocity/sigma group priors are not expressible through the reference's CNN (one (v, b) pair per
         # spectrum), so the prior is that of the first component
-        v0.append(vfit[0] + rng.normal(0, 15))
-        b0.append(abs(bfit * (1 + rng.normal(0, 0.15))))
+        if case.get('freeze'):                       # frozen values: a previous fit's result, close to the truth
+            v0.append(vfit[0] + rng.normal(0, 3))
+            b0.append(abs(bfit * (1 + rng.normal(0, 0.05))))
+        else:
+            v0.append(vfit[0] + rng.normal(0, 15))
+            b0.append(abs(bfit * (1 + rng.normal(0, 0.15))))
     cube = np.stack(rows)
     return dict(cube=cube, axis32=np.asarray(axis, dtype=np.float32), v0=np.array(v0, np.float32),
                 b0=np.array(b0, np.float32), theta=np.full(n, theta, np.float32), n_steps=sp.n_steps,
@@ -152,7 +160,9 @@ def run_reference(case, inp):
                                 transmission_interpolated=None, interferometer_theta=theta_map,
                                 hdr_dict={'FILTER': case['filter'], 'STEP': inp['delta_x']}, step_nb=inp['n_steps'],
                                 zpd_index=0, mdn=False, ML_bool=not noml, uncertainty_bool=case['unc'],
-                                nii_cons=True, resolution=case['R'], Luci_path='/root/reference/')
+                                nii_cons=True, resolution=case['R'], Luci_path='/root/reference/',
+                                **({'initial_values': [np.array([[float(inp['v0'][i])]]), np.array([[float(inp['b0'][i])]])]}
+                                   if case.get('freeze') else {}))
             for key, lst in zip(out.keys(), res[1:]):
                 out[key].append(lst[0])
     finally:
@@ -179,6 +189,7 @@ def make(name, jobs=1):
     meta = dict(filter=case['filter'], model=case['model'], lines=np.array(case['lines']),
                 vel_rel=np.array(case['vel_rel']), sigma_rel=np.array(case['sigma_rel']),
                 uncertainty=np.array(case['unc']), noml=np.array(bool(case.get('noml'))),
+                freeze=np.array(bool(case.get('freeze'))),
                 n_steps=np.array(inp['n_steps']), delta_x=np.array(inp['delta_x']))
     os.makedirs(GOLDEN, exist_ok=True)
     path = os.path.join(GOLDEN, name + '.npz')

@@ -33,6 +33,8 @@ def load_golden(name):
 
 def config_from_golden(g, uncertainty=None, **kw):
     unc = bool(g['uncertainty']) if uncertainty is None else uncertainty
+    if 'freeze' in g and bool(g['freeze']):
+        kw.setdefault('freeze', True)
     return FitConfig(g['model'], g['lines'], [int(v) for v in g['vel_rel']], [int(v) for v in g['sigma_rel']],
                      g['axis32'], filter=g['filter'], delta_x=float(g['delta_x']), n_steps=int(g['n_steps']),
                      zpd_index=0, uncertainty_bool=unc, nii_cons=True, ml_scale=not bool(g['noml']), **kw)

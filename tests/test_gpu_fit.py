@@ -25,6 +25,15 @@ def _gpu_fit(cfg, cube, theta, v0, b0, **kw):
     return {k: v.cpu().numpy() for k, v in res.items()}
 
 
+def _gpu_fit_plain(cfg, cube, theta, v0, b0):
+    from luci_b200 import engine
+    dev = _dev()
+    t = lambda a: None if a is None else torch.from_numpy(np.ascontiguousarray(a)).to(dev)
+    res = engine.fit_batch(cfg, t(cube.astype(np.float32)), t(theta), t(v0), t(b0))
+    torch.cuda.synchronize()
+    return {k: v.cpu().numpy() for k, v in res.items()}
+
+
 @pytest.mark.parametrize('name', [c for c in FIT_CASES if c != 'fit_sincgauss_double'])
 def test_cuda_matches_reference_golden(name):
     g = load_golden(name)
@@ -217,3 +226,12 @@ def test_cuda_large_sample_parity_config2():
     cfg = config_from_golden(g, uncertainty=False)
     res = _gpu_fit(cfg, g['cube'], g['theta'], g['v0'], g['b0'])
     check_large_sample_parity(res['rows'], res['status'], g, _float64_objective_factory(g))
+
+
+def test_cuda_freeze_mode_matches_reference():
+    """The reference's freeze branch (initial_values, LuciFit.py:688-709) through the C ABI."""
+    g = load_golden('fit_sincgauss_freeze')
+    cfg = config_from_golden(g)
+    res = _gpu_fit_plain(cfg, g['cube'], g['theta'], g['v0'], g['b0'])
+    rep = parity_report(res['rows'], g, g['model'])
+    assert rep['ok'].all() and rep['dv'].max() < 1e-2 and rep['df'].max() < 1e-3, (rep['dv'], rep['df'], rep['dchi'])

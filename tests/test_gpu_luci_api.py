@@ -124,8 +124,11 @@ def test_unsupported_branches_raise(world):
     luci, sc, out = world
     with pytest.raises(NotImplementedError):
         luci.fit_cube(SN3, 'sinc', [1] * 5, [1] * 5, 0, 2, 0, 2, bayes_bool=True)
-    with pytest.raises(NotImplementedError):
+    with pytest.raises(Exception, match='freeze'):       # the reference's gaussian / sinc freeze paths raise IndexError
         luci.fit_cube(SN3, 'sinc', [1] * 5, [1] * 5, 0, 2, 0, 2, initial_values=[np.zeros((2, 2)), np.ones((2, 2))])
+    with pytest.raises(NotImplementedError):
+        luci.fit_cube(SN3, 'sincgauss', [1] * 5, [1] * 5, 0, 2, 0, 2, uncertainty_bool=True,
+                      initial_values=[np.zeros((2, 2)), np.ones((2, 2))])
     with pytest.raises(Exception, match='vel_rel'):
         luci.fit_cube(SN3, 'sinc', [1] * 4, [1] * 5, 0, 2, 0, 2)
 
@@ -199,3 +202,18 @@ def test_pca_background_equals_fit_of_presubtracted_cube(world, tmp_path):
     np.testing.assert_allclose(broad, broad2, rtol=1e-3)
     with pytest.raises(Exception):
         luci.fit_cube(*args, prior_values=pv, bkgType='pca')                     # the PCA arrays are required
+
+
+def test_freeze_mode_through_fit_cube(world):
+    """initial_values = [velocity map, broadening map]: refit of the amplitudes with the kinematics of a previous fit
+    held fixed (LuciBase.py:361-364, LuciFit.py:688-709)."""
+    luci, sc, out = world
+    v0, b0 = sc.priors()
+    pv = (v0[1:8, 2:9], b0[1:8, 2:9])
+    vel, broad, flux, ampl = luci.fit_cube(SN3, 'sincgauss', [1] * 5, [1] * 5, 2, 9, 1, 8, prior_values=pv)
+    velf, broadf, fluxf, amplf = luci.fit_cube(SN3, 'sincgauss', [1] * 5, [1] * 5, 2, 9, 1, 8,
+                                               initial_values=[vel[:, :, 0], broad[:, :, 0]])
+    np.testing.assert_allclose(velf[:, :, 0], vel[:, :, 0], atol=1e-3)           # held
+    np.testing.assert_allclose(broadf[:, :, 0], broad[:, :, 0], rtol=1e-5)
+    np.testing.assert_allclose(amplf[:, :, 0], ampl[:, :, 0], rtol=2e-2)         # Halpha barely moves
+    assert np.abs(fluxf[:, :, 1] * 3 / fluxf[:, :, 2] - 1).max() > 1e-3          # the [NII] tie is gone (no constraints)

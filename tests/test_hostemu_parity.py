@@ -215,3 +215,26 @@ def test_hostemu_large_sample_parity_config2(hostemu):
     rows, sol, unc, st = run_hostemu(hostemu, cfg, g['cube'], g['theta'], g['v0'], g['b0'], want_unc=False)
     rep = check_large_sample_parity(rows, st, g, _float64_objective_factory(g))
     assert (((st >> 8) & 0xff).mean()) < 7
+
+
+def test_hostemu_freeze_mode_matches_reference(hostemu):
+    """initial_values = frozen (velocity, broadening): amplitudes and continuum only, no ties, no boxes
+    (LuciFit.py:159-162, 688-709) against the reference's own freeze branch."""
+    g = load_golden('fit_sincgauss_freeze')
+    cfg = config_from_golden(g)
+    rows, sol, unc, st = run_hostemu(hostemu, cfg, g['cube'], g['theta'], g['v0'], g['b0'], want_unc=False)
+    rep = parity_report(rows, g, g['model'])
+    assert rep['ok'].all(), (rep['dv'], rep['db'], rep['df'], rep['dchi'])
+    assert rep['dv'].max() < 1e-2 and rep['db'].max() < 1e-5 and rep['df'].max() < 1e-3 and np.median(rep['df']) < 1e-5
+    # frozen: velocity and broadening are the inputs, the [NII] amplitudes are no longer tied 1:3
+    np.testing.assert_allclose(rep['q']['velocities'][:, 0], g['v0'], atol=1e-3)
+    np.testing.assert_allclose(rep['q']['sigmas'][:, 0], np.abs(g['b0']), rtol=1e-5)
+    assert np.abs(rep['q']['fluxes'][:, 1] * 3 / rep['q']['fluxes'][:, 2] - 1).max() > 1e-3
+    assert (((st >> 8) & 0xff) <= 4).all()                  # a linear problem: one Gauss-Newton step and its check
+    # the model and the uncertainty stage are refused exactly where the reference itself fails
+    import ctypes as C
+    from luci_b200 import _capi
+    bad = config_from_golden(g, uncertainty=True)
+    sz = C.c_size_t(0)
+    assert _capi.lib().lucifit_workspace_bytes(bad.byref(), 10, C.byref(sz)) != 0
+    assert b'freeze' in _capi.lib().lucifit_last_error()

@@ -12,7 +12,8 @@ Differences that are deliberate and documented in DESIGN.md:
     km/s, which is exactly what the CNN writes into ``vel_ml`` / ``broad_ml`` (``LuciFit.py:352-361``);
   * ``fit_entire_cube`` honours its keyword arguments and returns the ``fit_cube`` tuple (the reference drops them
     and returns ``None``, ``LuciBase.py:255``);
-  * Bayesian / PCA-background / absorption / freeze branches raise ``NotImplementedError`` (out of scope rows).
+  * the Bayesian branch (``bayes_bool``) raises ``NotImplementedError`` (out of scope); PCA background, absorption
+    template, freeze mode (``initial_values``) and ``n_stoch`` restarts are implemented for the cube fits.
 """
 import os
 import warnings
@@ -222,8 +223,6 @@ class Luci():
     def _reject_unsupported(bayes_bool, absorp, initial_values, n_stoch, bkgType):
         if bayes_bool:
             raise NotImplementedError('bayes_bool=True (emcee/dynesty MCMC, LuciFit.py:930-1015) is out of scope')
-        if absorp is not None:
-            raise NotImplementedError('absorption templates (LuciBase.py:354-356) are out of scope')
         if int(n_stoch) < 1:
             raise ValueError('n_stoch must be >= 1')
 
@@ -238,7 +237,7 @@ class Luci():
 
     def _fit_maps(self, cube3d, lines, fit_function, vel_rel, sigma_rel, x_min, x_max, y_min, y_max, mask, bkg,
                   bkg_scale, uncertainty_bool, nii_cons, spec_min, spec_max, obj_redshift, prior_values, n_stoch=1,
-                  pca=None, initial_values=(False,)):
+                  pca=None, initial_values=(False,), absorp=None):
         """Shared body of fit_cube / fit_region: returns the 12 maps as numpy float32 arrays (ny', nx'[, L]).
 
         ``pca = (coefficients [n_fit_x, n_fit_y, n_comp] already summed over the bin, vectors [n_comp, nz], mean [nz])``
@@ -305,6 +304,20 @@ class Luci():
             ref_band = sky[:, lo_i:hi_i]
             scale_spec = torch.where(torch.isnan(ref_band), torch.full_like(ref_band, -float('inf')), ref_band).amax(dim=1)
             cube2d = (sky - scale_spec[:, None] * bkg_pix).contiguous()
+            index = None
+        if absorp is not None:
+            # absorption template (LuciBase.py:354-356): sky - absorp / median(absorp) * m + m with m the median of the
+            # central half of the (background-subtracted) spectrum; applied after the background like the reference
+            sky = cube2d[index] if index is not None else cube2d
+            if bkg_t is not None:
+                sky = sky - bkg_t[None, :]
+                bkg_t = None
+            ab = torch.from_numpy(np.ascontiguousarray(absorp, dtype=np.float32)).to(dev)
+            cut = int(nz * 0.25)
+            mid = sky[:, cut:-cut]
+            # np.nanmedian averages the two middle values: quantile 0.5 with linear interpolation (chunked: size limit)
+            med = torch.cat([torch.nanquantile(mid[i:i + 16384], 0.5, dim=1) for i in range(0, mid.shape[0], 16384)])
+            cube2d = (sky - (ab / torch.nanquantile(ab, 0.5))[None, :] * med[:, None] + med[:, None]).contiguous()
             index = None
         res = engine.fit_batch(cfg, cube2d, theta_t, v0, b0, index=index, bkg=bkg_t)
         rows = res['rows']
@@ -380,7 +393,7 @@ class Luci():
             raise Exception('Please set bkgType to either standard or pca')
         m = self._fit_maps(cube_to_slice, lines, fit_function, vel_rel, sigma_rel, x_min, x_max, y_min, y_max, None,
                            use_bkg, scale, uncertainty_bool, nii_cons, spec_min, spec_max, obj_redshift, prior_values,
-                           n_stoch=n_stoch, pca=pca, initial_values=initial_values)
+                           n_stoch=n_stoch, pca=pca, initial_values=initial_values, absorp=absorp)
         save_fits(self.output_dir, self.object_name, lines, m['amplitudes'], m['fluxes'], m['flux_errors'],
                   m['velocities'], m['sigmas'], m['vels_errors'], m['sigmas_errors'], m['chi2'], m['continuum'],
                   m['continuum_error'], self._cutout_header(header, x_min, y_min), binning, fit_function=fit_function)

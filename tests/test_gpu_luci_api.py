@@ -217,3 +217,24 @@ def test_freeze_mode_through_fit_cube(world):
     np.testing.assert_allclose(broadf[:, :, 0], broad[:, :, 0], rtol=1e-5)
     np.testing.assert_allclose(amplf[:, :, 0], ampl[:, :, 0], rtol=2e-2)         # Halpha barely moves
     assert np.abs(fluxf[:, :, 1] * 3 / fluxf[:, :, 2] - 1).max() > 1e-3          # the [NII] tie is gone (no constraints)
+
+
+def test_absorption_template_equals_fit_of_corrected_cube(world, tmp_path):
+    """absorp (LuciBase.py:354-356): sky - absorp / median(absorp) * m + m, m = median of the central half."""
+    from luci_b200.luci import Luci
+    luci, sc, out = world
+    cube = luci.cube_final.cpu().numpy().astype(np.float64)
+    nx, ny, nz = cube.shape
+    absorp = 1.0 + 0.05 * np.cos(np.linspace(0, 6, nz))
+    cut = int(nz * 0.25)
+    m = np.nanmedian(cube[:, :, cut:-cut], axis=2)
+    pre = cube - (absorp / np.nanmedian(absorp))[None, None, :] * m[:, :, None] + m[:, :, None]
+    v0, b0 = sc.priors()
+    args = (SN3, 'sincgauss', [1] * 5, [1] * 5, 1, 11, 2, 9)
+    pv = (v0[2:9, 1:11], b0[2:9, 1:11])
+    vel, broad, flux, ampl = luci.fit_cube(*args, prior_values=pv, absorp=absorp)
+    luci2 = Luci.from_arrays(torch.from_numpy(pre.astype(np.float32)).to(luci.cube_final.device), sc.hdr_dict,
+                             str(tmp_path), 'ABS', spectrum_axis=sc.axis32, device=luci.cube_final.device)
+    vel2, broad2, flux2, ampl2 = luci2.fit_cube(*args, prior_values=pv)
+    np.testing.assert_allclose(vel, vel2, atol=5e-2)
+    np.testing.assert_allclose(flux, flux2, rtol=2e-3)

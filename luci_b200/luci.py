@@ -504,3 +504,87 @@ class Luci():
         fit_dict['fit_vector'] = plot_vector(cfg, fit_dict['fit_sol'], theta, self.cube_final.device)
         sky = integrated.cpu().numpy()
         return np.asarray(self.spectrum_axis), sky, fit_dict
+
+    def fit_wvt(self, lines, fit_function, vel_rel, sigma_rel, bkg=None, bayes_bool=False, uncertainty_bool=False,
+                n_threads=1, initial_values=[False], n_stoch=1, stn_target=10, bin_map=None, prior_values=None,
+                nii_cons=True, mean=False):
+        """``LuciBase.py:1383-1467``: fit the integrated spectrum of every bin of a tessellation and paint each bin's
+        result onto its pixels.  Returns ``(velocities, broadenings, flux, chi2, header)`` like the reference.
+
+        The reference loops over ``<output_dir>/Numpy_Voronoi_Bins/bool_bin_map_<i>.npy`` and calls
+        ``fit_spectrum_region`` once per bin (9.5 h for 16 789 bins, docs/source/example_wvt.rst:116).  Here the bins
+        are one segmented reduction of the cube followed by ONE ``lucifit_fit_batch`` call.  ``bin_map`` (int
+        ``(nx, ny)``, -1 = unbinned pixel) may be passed directly instead of the ``.npy`` files; the tessellation
+        itself (``create_wvt``, LuciWVT.py) is out of scope.  ``prior_values=(vel_map, broad_map)`` ``(ny, nx)`` are
+        reduced to one prior per bin by the median over its pixels.  Every bin is fitted with the interferometer angle
+        the reference's ``fit_spectrum_region`` uses (LuciBase.py:1035: the last pixel of the cube).
+
+        Two defects of the reference loop are not reproduced: its maps are ``(ny, nx)`` but indexed ``[x, y]``
+        (IndexError off the square part of the detector, LuciBase.py:1449-1459) and the continuum map is overwritten
+        with the continuum error (:1456-1457)."""
+        self._reject_unsupported(bayes_bool, None, [False], 1, None)
+        if int(n_stoch) != 1 or (len(initial_values) >= 1 and initial_values[0] is not False):
+            raise NotImplementedError('fit_wvt: n_stoch > 1 / initial_values are implemented for fit_cube / fit_region only')
+        nx, ny, nz = self.cube_final.shape
+        dev = self.cube_final.device
+        if bin_map is None:
+            folder = os.path.join(self.output_dir, 'Numpy_Voronoi_Bins')
+            bin_map = np.full((nx, ny), -1, dtype=np.int64)
+            for b in range(len(os.listdir(folder))):
+                bin_map[np.load(os.path.join(folder, 'bool_bin_map_%i.npy' % b)).astype(bool)] = b
+        bin_map = np.asarray(bin_map, dtype=np.int64)
+        if bin_map.shape != (nx, ny):
+            raise ValueError('bin_map must be (nx, ny) = %s' % ((nx, ny),))
+        n_bins = int(bin_map.max()) + 1
+        if n_bins < 1:
+            raise ValueError('bin_map holds no bins')
+        flat = torch.from_numpy(bin_map.reshape(-1)).to(dev)
+        inside = flat >= 0
+        # segmented reduction: integrated spectrum of every bin (nansum like extract_spectrum_region, float64 sums)
+        sums = torch.zeros((n_bins, nz), dtype=torch.float64, device=dev)
+        rows = self.cube_final.view(nx * ny, nz)
+        for lo in range(0, nx * ny, 1 << 18):                      # bounded temporaries
+            hi = min(lo + (1 << 18), nx * ny)
+            sel = inside[lo:hi]
+            if bool(sel.any()):
+                sums.index_add_(0, flat[lo:hi][sel], torch.nan_to_num(rows[lo:hi][sel].to(torch.float64), nan=0.0))
+        counts = torch.bincount(flat[inside], minlength=n_bins).to(torch.float64)
+        if mean:
+            sums = sums / counts.clamp(min=1.0)[:, None]
+        if bkg is not None:
+            sums = sums - torch.from_numpy(np.asarray(bkg, dtype=np.float64)).to(dev)[None, :] * counts[:, None]
+        theta = float(self.interferometer_theta[nx - 1, ny - 1])
+        have_prior = prior_values is not None
+        cfg = self._make_config(lines, fit_function, vel_rel, sigma_rel, uncertainty_bool, nii_cons, None, None, 0.0,
+                                ml_scale=have_prior)
+        th = torch.full((n_bins,), theta, dtype=torch.float32, device=dev)
+        v0 = b0 = None
+        if have_prior:
+            pv = np.asarray(prior_values[0], dtype=np.float64).T.reshape(-1)     # (ny, nx) -> x-major like bin_map
+            pb = np.asarray(prior_values[1], dtype=np.float64).T.reshape(-1)
+            order = np.argsort(bin_map.reshape(-1), kind='stable')
+            keys = bin_map.reshape(-1)[order]
+            first = np.searchsorted(keys, np.arange(n_bins), side='left')
+            last = np.searchsorted(keys, np.arange(n_bins), side='right')
+            med = lambda a: np.array([np.median(a[order[f:l]]) if l > f else 0.0 for f, l in zip(first, last)], np.float32)
+            v0, b0 = torch.from_numpy(med(pv)).to(dev), torch.from_numpy(med(pb)).to(dev)
+        res = engine.fit_batch(cfg, sums.to(torch.float32).contiguous(), th, v0, b0)
+        self.last_fit_summary = engine.status_summary(res['status'])
+        L, K = len(lines), cfg.row_floats
+        # paint: pixel (x, y) of bin b gets row b; unbinned pixels stay 0
+        full = torch.zeros((nx * ny, K), dtype=torch.float32, device=dev)
+        full[inside] = res['rows'][flat[inside]]
+        full = full.view(nx, ny, K).permute(1, 0, 2).contiguous().cpu().numpy()      # (ny, nx, K) like every other map
+        m = {}
+        for i, name in enumerate(engine.ROW_FIELDS):
+            m[name] = np.ascontiguousarray(full[:, :, i * L:(i + 1) * L])
+        for i, name in enumerate(engine.ROW_SCALARS):
+            m[name] = np.ascontiguousarray(full[:, :, 7 * L + i])
+        m['bin_rows'] = res['rows'].cpu().numpy()
+        self._ensure_deep()
+        header = self._cutout_header(self.header, 0, 0)
+        save_fits(self.output_dir, self.object_name, lines, m['amplitudes'], m['fluxes'], m['flux_errors'],
+                  m['velocities'], m['sigmas'], m['vels_errors'], m['sigmas_errors'], m['chi2'], m['continuum'],
+                  m['continuum_error'], header, binning=1, suffix='_wvt_%i' % stn_target)
+        self.last_fit_maps = m
+        return m['velocities'], m['sigmas'], m['fluxes'], m['chi2'], header

@@ -238,3 +238,41 @@ def test_absorption_template_equals_fit_of_corrected_cube(world, tmp_path):
     vel2, broad2, flux2, ampl2 = luci2.fit_cube(*args, prior_values=pv)
     np.testing.assert_allclose(vel, vel2, atol=5e-2)
     np.testing.assert_allclose(flux, flux2, rtol=2e-3)
+
+
+def test_fit_wvt_bins_equal_fit_spectrum_region(world):
+    """fit_wvt: one segmented reduction + one batch call == the reference's per-bin fit_spectrum_region loop
+    (LuciBase.py:1383-1467), painted onto the bins' pixels; bins can come from the .npy files the reference writes."""
+    luci, sc, out = world
+    nx, ny = luci.cube_final.shape[:2]
+    bin_map = np.full((nx, ny), -1, dtype=np.int64)
+    b = 0
+    for x0 in range(0, nx - 1, 3):
+        for y0 in range(0, ny - 1, 2):
+            bin_map[x0:x0 + 3, y0:y0 + 2] = b
+            b += 1
+    bin_map[0, 0] = -1                                                     # an unbinned pixel
+    n_bins = b
+    v0, b0 = sc.priors()
+    vel, broad, flux, chi2, hdr = luci.fit_wvt(SN3, 'sincgauss', [1] * 5, [1] * 5, bin_map=bin_map,
+                                               prior_values=(v0, b0), uncertainty_bool=True)
+    assert vel.shape == (ny, nx, 5) and chi2.shape == (ny, nx)
+    assert (vel[0, 0] == 0).all()                                           # unbinned pixel untouched
+    for k in (0, n_bins // 2, n_bins - 1):
+        mask = bin_map == k
+        xs, ys = np.nonzero(mask)
+        pv = (float(np.median(v0.T[mask])), float(np.median(b0.T[mask])))
+        axis, sky, d = luci.fit_spectrum_region(SN3, 'sincgauss', [1] * 5, [1] * 5, mask, prior_values=pv,
+                                                uncertainty_bool=True)
+        for x, y in zip(xs, ys):
+            np.testing.assert_allclose(vel[y, x], d['velocities'], atol=2e-3)
+            np.testing.assert_allclose(flux[y, x], d['fluxes'], rtol=1e-4)
+            np.testing.assert_allclose(chi2[y, x], d['chi2'], rtol=1e-4)
+    assert os.path.exists(os.path.join(out, 'Luci_outputs', 'Velocity', 'OBJ_wvt_10_1_Halpha_velocity.fits'))
+    # the same bins from the reference's on-disk layout
+    folder = os.path.join(luci.output_dir, 'Numpy_Voronoi_Bins')
+    os.makedirs(folder, exist_ok=True)
+    for k in range(n_bins):
+        np.save(os.path.join(folder, 'bool_bin_map_%i.npy' % k), bin_map == k)
+    vel2 = luci.fit_wvt(SN3, 'sincgauss', [1] * 5, [1] * 5, prior_values=(v0, b0), uncertainty_bool=True)[0]
+    np.testing.assert_array_equal(vel, vel2)

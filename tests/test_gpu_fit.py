@@ -235,3 +235,31 @@ def test_cuda_freeze_mode_matches_reference():
     res = _gpu_fit_plain(cfg, g['cube'], g['theta'], g['v0'], g['b0'])
     rep = parity_report(res['rows'], g, g['model'])
     assert rep['ok'].all() and rep['dv'].max() < 1e-2 and rep['df'].max() < 1e-3, (rep['dv'], rep['df'], rep['dchi'])
+
+
+def test_largest_instantiated_systems_launch_and_converge():
+    """The biggest pre-instantiated normal equations (8 lines x 2 groups: 13 unknowns; 6 lines x 6 groups: 19 unknowns)
+    need most of the register file; they must still launch, converge and agree with the CPU build of the same source."""
+    from luci_b200 import engine
+    from tests.test_hostemu_parity import _double_component_case
+    c = _double_component_case(n=4, seed=9)
+    dev = _dev()
+    t = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(dev)
+    lines8 = ['Halpha', 'NII6548', 'NII6583', 'SII6716', 'SII6731', 'Halpha', 'NII6583', 'SII6716']
+    rel8 = [1, 1, 1, 1, 1, 2, 2, 2]
+    cfg8 = engine.FitConfig('sincgauss', lines8, rel8, rel8, c['axis32'], 'SN3', c['delta_x'], c['n_steps'], 0,
+                            uncertainty_bool=True, prior_groups=True)
+    r8 = engine.fit_batch(cfg8, t(c['cube']), t(c['theta']), t(c['v0']), t(c['b0']), want_unc=True)
+    st = r8['status'].cpu().numpy()
+    assert ((st >> 16) & 3 != 0).all() and torch.isfinite(r8['rows'][:, :8]).all()
+    vel = r8['rows'][:, 24:32].cpu().numpy()
+    np.testing.assert_allclose(vel[:, 0], c['truth'][:, 0], atol=5.0)
+    np.testing.assert_allclose(vel[:, 5], c['truth'][:, 1], atol=15.0)
+    lines6 = ['Halpha', 'NII6548', 'NII6583', 'SII6716', 'SII6731', 'Halpha']
+    rel6 = [1, 2, 3, 4, 5, 6]
+    cfg6 = engine.FitConfig('gaussian', lines6, rel6, rel6, c['axis32'], 'SN3', c['delta_x'], c['n_steps'], 0,
+                            nii_cons=False, prior_groups=True)
+    v6 = np.stack([c['v0'][:, 0]] * 5 + [c['v0'][:, 1]], axis=1).copy()
+    b6 = np.stack([c['b0'][:, 0]] * 5 + [c['b0'][:, 1]], axis=1).copy()
+    r6 = engine.fit_batch(cfg6, t(c['cube']), t(c['theta']), t(v6), t(b6))
+    assert ((r6['status'].cpu().numpy() >> 16) & 3 != 0).all() and torch.isfinite(r6['rows'][:, :6]).all()

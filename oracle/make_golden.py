@@ -45,6 +45,10 @@ CASES = {
                                  sigma_rel=[1], n=12, unc=True, broad=(25, 60), seed=108),
     'fit_sinc_noml': dict(filter='SN3', R=5000, lines=SN3, model='sinc', vel_rel=[1] * 5, sigma_rel=[1] * 5,
                           n=4, unc=False, broad=(20, 60), seed=109, noml=True),
+    # transmission curve (LuciFit.py:124-125, 197-207): divides the spectrum where T > 0.5 AFTER the normalisation, so
+    # it moves the scale and the chi2 but not the optimum
+    'fit_sincgauss_trans': dict(filter='SN3', R=5000, lines=SN3, model='sincgauss', vel_rel=[1] * 5, sigma_rel=[1] * 5,
+                                n=8, unc=True, broad=(25, 60), seed=112, trans=True),
     # the reference's freeze branch (initial_values = frozen velocity / broadening, amplitudes + continuum fitted
     # without constraints, LuciFit.py:688-709); only sincgauss works there (gaussian / sinc raise IndexError)
     'fit_sincgauss_freeze': dict(filter='SN3', R=5000, lines=SN3, model='sincgauss', vel_rel=[1] * 5, sigma_rel=[1] * 5,
@@ -98,7 +102,11 @@ def build_inputs(case):
             v0.append(vfit[0] + rng.normal(0, 15))
             b0.append(abs(bfit * (1 + rng.normal(0, 0.15))))
     cube = np.stack(rows)
-    return dict(cube=cube, axis32=np.asarray(axis, dtype=np.float32), v0=np.array(v0, np.float32),
+    extra = {}
+    if case.get('trans'):                             # smooth band-pass: 0.3 at the edges (below the 0.5 cut), 0.95 inside
+        z = np.linspace(-1, 1, cube.shape[1])
+        extra['trans'] = 0.3 + 0.65 * np.exp(-(z / 0.8) ** 8)
+    return dict(**extra, cube=cube, axis32=np.asarray(axis, dtype=np.float32), v0=np.array(v0, np.float32),
                 b0=np.array(b0, np.float32), theta=np.full(n, theta, np.float32), n_steps=sp.n_steps,
                 delta_x=sp.delta_x)
 
@@ -157,7 +165,7 @@ def run_reference(case, inp):
             theta_map = np.full((1, 1), float(inp['theta'][i]))
             res = Luci.fit_calc(0, 0, 1, 0, case['model'], lines, case['vel_rel'], case['sigma_rel'],
                                 cube_slice=cube_slice, spectrum_axis=inp['axis32'], wavenumbers_syn=wsyn,
-                                transmission_interpolated=None, interferometer_theta=theta_map,
+                                transmission_interpolated=inp.get('trans'), interferometer_theta=theta_map,
                                 hdr_dict={'FILTER': case['filter'], 'STEP': inp['delta_x']}, step_nb=inp['n_steps'],
                                 zpd_index=0, mdn=False, ML_bool=not noml, uncertainty_bool=case['unc'],
                                 nii_cons=True, resolution=case['R'], Luci_path='/root/reference/',
@@ -193,6 +201,8 @@ def make(name, jobs=1):
                 n_steps=np.array(inp['n_steps']), delta_x=np.array(inp['delta_x']))
     os.makedirs(GOLDEN, exist_ok=True)
     path = os.path.join(GOLDEN, name + '.npz')
+    if 'trans' in inp:
+        meta['trans'] = inp['trans']
     np.savez_compressed(path, cube=inp['cube'], axis32=inp['axis32'], v0=inp['v0'], b0=inp['b0'], theta=inp['theta'],
                         **meta, **ref)
     print('%s: n=%d  %.2f s/spaxel (reference) -> %s' % (name, case['n'], float(ref['ref_seconds_per_spaxel']), path))

@@ -16,7 +16,8 @@ TOL_REL = 1e-3
 TOL_CHI2 = 1e-4
 
 FIT_CASES = ['fit_sincgauss_sn3', 'fit_gaussian_sn3', 'fit_sinc_sn3', 'fit_gaussian_sn2', 'fit_gaussian_sn1',
-             'fit_sincgauss_groups', 'fit_sincgauss_double', 'fit_sincgauss_single', 'fit_sinc_noml']
+             'fit_sincgauss_groups', 'fit_sincgauss_double', 'fit_sincgauss_single', 'fit_sinc_noml',
+             'fit_sincgauss_trans']
 
 
 def load_golden(name):
@@ -35,6 +36,8 @@ def config_from_golden(g, uncertainty=None, **kw):
     unc = bool(g['uncertainty']) if uncertainty is None else uncertainty
     if 'freeze' in g and bool(g['freeze']):
         kw.setdefault('freeze', True)
+    if 'trans' in g:
+        kw.setdefault('trans_filter', g['trans'])
     return FitConfig(g['model'], g['lines'], [int(v) for v in g['vel_rel']], [int(v) for v in g['sigma_rel']],
                      g['axis32'], filter=g['filter'], delta_x=float(g['delta_x']), n_steps=int(g['n_steps']),
                      zpd_index=0, uncertainty_bool=unc, nii_cons=True, ml_scale=not bool(g['noml']), **kw)

@@ -37,11 +37,15 @@
 #define LF_MAX_LINES 8
 #define LF_C_KMS 299792.0f        /* LuciFit.py:26 (integer km/s in the reference) */
 #define LF_MAX_CONT_WIN 256       /* samples of the continuum window handled by the clip */
-#ifndef LF_TUNE_SLACK
-#define LF_TUNE_SLACK_PRED 1e-4
-#define LF_TUNE_SLACK 4e-6
-#define LF_TUNE_REJ_CONV 1e-5
+#ifndef LF_LM_LAM0
+#define LF_LM_LAM0 1e-3f
+#define LF_LM_DEC (1.0f / 3.0f)
+#define LF_LM_LAMREJ 0.0f
 #endif
+/* LM acceptance / stopping constants (tuned on tests/golden/parity_sincgauss_cfg2.npz: 1000 reference fits) */
+#define LF_TUNE_SLACK_PRED 1e-4   /* below this predicted relative decrease an FP32-noise-sized rise of sum r^2 is accepted */
+#define LF_TUNE_SLACK 4e-6        /* ... of at most this relative size */
+#define LF_TUNE_REJ_CONV 1e-5     /* a rejected step predicted to gain less than this means converged */
 
 // status word: bits 0-7 accepted LM iterations, bits 8-15 model evaluations, bits 16.. flags
 enum {
@@ -814,7 +818,7 @@ LF_CORE void lf_stage_lm(const LfCfg& cfg, const LfWarp<LANES>& w, const float* 
     }
     w.sync();
     int evals = 0, iters = 0, flags = 0, tries = 0;
-    float lam = 1e-3f, nu = 2.0f, pred = 0.0f;
+    float lam = LF_LM_LAM0, nu = 2.0f, pred = 0.0f;
     double chi2 = 0.0;
     const double ftol = (double)cfg.ftol;
     bool first = true, done = false;
@@ -837,7 +841,7 @@ LF_CORE void lf_stage_lm(const LfCfg& cfg, const LfWarp<LANES>& w, const float* 
                 double act = chi2 - chi2t;
                 float rho = pred > 0.0f ? (float)(act / (double)pred) : 1.0f;
                 float f = 1.0f - (2.0f * rho - 1.0f) * (2.0f * rho - 1.0f) * (2.0f * rho - 1.0f);
-                lam *= fmaxf(1.0f / 3.0f, f);
+                lam *= fmaxf(LF_LM_DEC, f);
                 lam = fmaxf(lam, 1e-7f);
                 nu = 2.0f;
                 accepted = true;
@@ -846,7 +850,7 @@ LF_CORE void lf_stage_lm(const LfCfg& cfg, const LfWarp<LANES>& w, const float* 
             } else {
                 // rejected: keep the accepted system and increase the damping; inside the FP32 noise floor of
                 // sum r^2 (relative ~1e-6) a rejection only means "converged"
-                lam *= nu; nu *= 2.0f;
+                lam = fmaxf(lam * nu, LF_LM_LAMREJ); nu *= 2.0f;
                 ++tries;
                 if (finite && (double)pred <= LF_TUNE_REJ_CONV * chi2) { done = true; flags |= LF_ST_CONVERGED; }
             }

@@ -42,4 +42,6 @@ def hostemu():
     lib.hostemu_fit_batch.restype = C.c_int
     lib.hostemu_profile.argtypes = [C.c_int, C.c_float, C.c_float, C.c_float, C.c_int, vp, vp, vp, vp]
     lib.hostemu_faddeeva.argtypes = [C.c_int, vp, vp, vp, vp]
+    lib.hostemu_eval.argtypes = [C.POINTER(lucifit_config), vp, C.c_float, vp, vp, vp]
+    lib.hostemu_eval.restype = C.c_int
     return lib

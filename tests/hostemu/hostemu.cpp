@@ -84,3 +84,40 @@ extern "C" void hostemu_faddeeva(int n, const float* x, const float* y, float* w
 {
     for (int i = 0; i < n; ++i) lf_faddeeva(x[i], y[i], wr[i], wi[i]);
 }
+
+// Debug/test entry: sum r^2, J^T r and J^T J of the LM objective at an arbitrary reduced parameter vector `th`
+// (layout [A | v | beta | continuum] of the (L, bucket) instance) for spectrum 0 of `cube`.
+template <int MODEL, int L, int NG>
+static void run_eval(const LfPlan& pl, const float* gspec, float theta, const float* th_in, double* chi2, float* hg)
+{
+    typedef LfDims<MODEL, L, NG, NG> D;
+    LfWarp<1> w;
+    const LfLayout& ly = pl.ly;
+    size_t bytes = ly.prep_bytes > ly.lm_bytes ? ly.prep_bytes : ly.lm_bytes;
+    std::vector<unsigned char> buf(bytes + 64);
+    unsigned char* base = buf.data();
+    base += (16 - ((uintptr_t)base & 15)) & 15;
+    std::vector<double> state_d(pl.dev.state_floats / 2 + 1);
+    float* state = reinterpret_cast<float*>(state_d.data());
+    float v0 = 0.f, b0 = 30.f;
+    lf_stage_prep<MODEL, L, NG, NG, 1>(pl.dev, w, gspec, theta, &v0, &b0, lf_work_at(LF_STAGE_PREP, ly, base), state);
+    LfWork wk = lf_work_at(LF_STAGE_LM, ly, base);
+    const double sinc_w_d = reinterpret_cast<const double*>(state)[LF_SO_SINCW / 2];
+    lf_stage_window<MODEL, 1>(pl.dev, w, pl.dev.xo, gspec, state[LF_SO_INVW], false, sinc_w_d, wk);
+    float* th = wk.thb;
+    for (int j = 0; j < D::P; ++j) th[j] = th_in[j];
+    lf_setup_lines<MODEL, L, NG, NG, 1>(pl.dev, w, th, (float)sinc_w_d, 1.0 / sinc_w_d, wk.lines, wk.tie);
+    lf_eval<MODEL, L, NG, NG, 1>(pl.dev, w, pl.dev.xo, wk, pl.dev.fit_hi - pl.dev.fit_lo, (float)sinc_w_d, th[D::IC], *chi2, wk.hb);
+    for (int e = 0; e < D::NA; ++e) hg[e] = wk.hb[e];
+}
+
+extern "C" int hostemu_eval(const lucifit_config* cfg, const float* gspec, float theta, const float* th, double* chi2, float* hg)
+{
+    LfPlan pl;
+    std::string err = lf_make_plan(cfg, pl, 1);
+    if (!err.empty()) return -1;
+    pl.dev.axis = pl.axis.data(); pl.dev.xo = pl.xo.data(); pl.dev.trans = 0; pl.dev.bkg = 0;
+    if (pl.L == 5 && pl.nv_t == 1 && cfg->model == 2) { run_eval<2, 5, 1>(pl, gspec, theta, th, chi2, hg); return 0; }
+    if (pl.L == 5 && pl.nv_t == 1 && cfg->model == 0) { run_eval<0, 5, 1>(pl, gspec, theta, th, chi2, hg); return 0; }
+    return -2;
+}

@@ -238,3 +238,37 @@ def test_hostemu_freeze_mode_matches_reference(hostemu):
     sz = C.c_size_t(0)
     assert _capi.lib().lucifit_workspace_bytes(bad.byref(), 10, C.byref(sz)) != 0
     assert b'freeze' in _capi.lib().lucifit_last_error()
+
+
+@pytest.mark.parametrize('name', ['parity_sincgauss_cfg2', 'fit_gaussian_sn3'])
+def test_analytic_gradient_matches_finite_differences(hostemu, name):
+    """J^T r of the tie-eliminated model (analytic partials, [NII] ratio chain rule, folded wing path) equals the
+    central finite difference of the evaluated sum of squares in every free parameter, off the optimum."""
+    import ctypes as C
+    from tests.common import ptr
+    g = load_golden(name)
+    cfg = config_from_golden(g, uncertainty=False)
+    L, P, NH = 5, 8, 36
+    for i in (0, 1):
+        spec = np.ascontiguousarray(g['cube'][i], dtype=np.float32)
+        scale = float(g['ref_scale'][i])
+        th = np.zeros(P, np.float32)
+        th[:L] = g['ref_amplitudes'][i] / scale
+        th[5], th[6], th[7] = g['ref_velocities'][i][0] + 3.0, g['ref_sigmas'][i][0] * 1.05, g['ref_continuum'][i] / scale
+        th[0] *= 0.97
+
+        def ev(t):
+            t = np.ascontiguousarray(t, dtype=np.float32)
+            chi, hg = C.c_double(0), np.zeros(NH + P, np.float32)
+            assert hostemu.hostemu_eval(cfg.byref(), ptr(spec), C.c_float(float(g['theta'][i])), ptr(t), C.byref(chi), ptr(hg)) == 0
+            return chi.value, hg
+
+        _, hg = ev(th)
+        for j, h in zip(range(P), [1e-3] * 5 + [0.05, 0.05, 1e-3]):
+            if j == 1:
+                assert hg[NH + j] == 0.0                     # the tied [NII]6548 column is dead
+                continue
+            tp, tm = th.copy(), th.copy()
+            tp[j] += h; tm[j] -= h
+            fd = -(ev(tp)[0] - ev(tm)[0]) / (2.0 * (float(tp[j]) - float(tm[j])))      # -1/2 d(sum r^2)/d theta_j
+            np.testing.assert_allclose(hg[NH + j], fd, rtol=3e-2, atol=2e-6 * abs(hg[NH:]).max(), err_msg='%s param %d' % (name, j))

@@ -37,6 +37,7 @@
 #define LF_MAX_LINES 8
 #define LF_C_KMS 299792.0f        /* LuciFit.py:26 (integer km/s in the reference) */
 #define LF_MAX_CONT_WIN 256       /* samples of the continuum window handled by the clip */
+#define LF_PREP_MLP 9             /* loads in flight per lane while the prep stage reads a spectrum */
 #ifndef LF_LM_LAM0
 #define LF_LM_LAM0 1e-3f
 #define LF_LM_DEC (1.0f / 3.0f)
@@ -688,16 +689,27 @@ LF_CORE void lf_stage_prep(const LfCfg& cfg, const LfWarp<LANES>& w, const float
     float smax = -INFINITY, wmax = -INFINITY, tmax = -INFINITY;
     int nan_ct = 0;
     w.sync();
-    for (int i = w.lane; i < nz; i += LANES) {
-        float s = gspec[i];
-        if (cfg.bkg) s -= cfg.bkg[i];
-        spec[i] = s;
-        nan_ct += (s != s);
-        smax = fmaxf(smax, s);
-        if (i >= cfg.fit_lo && i < cfg.fit_hi) wmax = fmaxf(wmax, s);
-        float st = s;
-        if (cfg.trans) { float t = cfg.trans[i]; if (t > 0.5f) st = s / t; }
-        tmax = fmaxf(tmax, st);
+    // the spectrum is read once from HBM: LF_PREP_MLP independent loads per lane are issued before the first one is
+    // consumed, otherwise the stage sits on DRAM latency (this loop is the only global traffic of the stage)
+    for (int i0 = w.lane; i0 < nz; i0 += LANES * LF_PREP_MLP) {
+        float q[LF_PREP_MLP];
+#pragma unroll
+        for (int j = 0; j < LF_PREP_MLP; ++j) { const int i = i0 + j * LANES; q[j] = i < nz ? gspec[i] : 0.0f; }
+#pragma unroll
+        for (int j = 0; j < LF_PREP_MLP; ++j) {
+            const int i = i0 + j * LANES;
+            if (i < nz) {
+                float s = q[j];
+                if (cfg.bkg) s -= cfg.bkg[i];
+                spec[i] = s;
+                nan_ct += (s != s);
+                smax = fmaxf(smax, s);
+                if (i >= cfg.fit_lo && i < cfg.fit_hi) wmax = fmaxf(wmax, s);
+                float st = s;
+                if (cfg.trans) { float t = cfg.trans[i]; if (t > 0.5f) st = s / t; }
+                tmax = fmaxf(tmax, st);
+            }
+        }
     }
     smax = w.max(smax); wmax = w.max(wmax); tmax = w.max(tmax);
     nan_ct = w.sum(nan_ct);
@@ -1044,22 +1056,32 @@ LF_CORE void lf_stage_out(const LfCfg& cfg, const LfWarp<LANES>& w, const float*
         double flux, ferr;
         if (MODEL == LF_GAUSSIAN) {
             flux = (1.20671 / FWHM_COEFF) * SQ2PI * Ak * s;
-            ferr = flux * sqrt((uA / Ak) * (uA / Ak) + (us / s) * (us / s));
         } else if (MODEL == LF_SINC) {
             flux = PI * sqrt(PI) * Ak * sinc_w_d;
-            ferr = flux * sqrt((uA / Ak) * (uA / Ak) + (us / s) * (us / s));
         } else {
-            double c0 = 1.4142135623730951 * sinc_w_d;
-            double ef = erf(s / c0);
-            flux = (1.20671 / (PI * FWHM_COEFF)) * Ak * (SQ2PI * s / ef);
-            double t = ef - (2.0 * PI) / (sqrt(PI) * c0) * exp(-s * s / (c0 * c0));
-            ferr = flux * sqrt((uA / Ak) * (uA / Ak) + (us / s) * (us / s) * t * t);
+            flux = (1.20671 / (PI * FWHM_COEFF)) * Ak * (SQ2PI * s / erf(s / (1.4142135623730951 * sinc_w_d)));
         }
         double lam = cfg.line_nm[k];
         double v = 299792.0 * ((1e7 / pk - lam) / lam);                         // LuciFitParameters.py:34-36
-        double verr = 299792.0 * up * (1e7 / (lam * pk * pk));                  // :57
         double broad = pk > 0 ? fabs(299792.0 * s / pk) : 0.0;                  // :82-88
-        double berr = (pk > 0 && s > 0) ? (299792.0 * s / pk) * sqrt((us / s) * (us / s) + (up / pk) * (up / pk)) : 0.0;
+        double verr, berr;
+        if (unc) {
+            if (MODEL == LF_SINCGAUSS) {
+                double c0 = 1.4142135623730951 * sinc_w_d;
+                double t = erf(s / c0) - (2.0 * PI) / (sqrt(PI) * c0) * exp(-s * s / (c0 * c0));
+                ferr = flux * sqrt((uA / Ak) * (uA / Ak) + (us / s) * (us / s) * t * t);
+            } else {
+                ferr = flux * sqrt((uA / Ak) * (uA / Ak) + (us / s) * (us / s));
+            }
+            verr = 299792.0 * up * (1e7 / (lam * pk * pk));                     // :57
+            berr = (pk > 0 && s > 0) ? (299792.0 * s / pk) * sqrt((us / s) * (us / s) + (up / pk) * (up / pk)) : 0.0;
+        } else {
+            // uncertainty_bool = False: every 1-sigma input is 0 and the expressions above reduce to 0 -- or to the
+            // 0/0 = NaN the reference produces when an amplitude or a width collapsed to 0 (kept: same maps)
+            ferr = (Ak == 0.0 || s == 0.0 || flux != flux) ? NAN : flux * 0.0;
+            verr = 0.0;
+            berr = 0.0;
+        }
         out_row[k] = (float)Ak; out_row[L + k] = (float)flux; out_row[2 * L + k] = (float)ferr;
         out_row[3 * L + k] = (float)v; out_row[4 * L + k] = (float)verr;
         out_row[5 * L + k] = (float)broad; out_row[6 * L + k] = (float)berr;

@@ -357,11 +357,12 @@ def main():
             pass
         for name, fn in (('deep_image', lambda: engine.deep_image(cube)),
                          ('snr_map_method1', lambda: engine.snr_map(cube, 1, flo, fhi, nlo, nhi)),
-                         ('snr1_plus_deep_fused', lambda: engine.snr_map(cube, 1, flo, fhi, nlo, nhi, with_deep=True))):
-            for _ in range(3):
+                         ('snr1_plus_deep_fused', lambda: engine.snr_map(cube, 1, flo, fhi, nlo, nhi, with_deep=True)),
+                         ('snr_map_method2', lambda: engine.snr_map(cube, 2, flo, fhi, nlo, nhi))):
+            for _ in range(3 if name != 'snr_map_method2' else 1):
                 fn()
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            reps = 10
+            reps = 10 if name != 'snr_map_method2' else 2
             torch.cuda.synchronize(); e0.record()
             for _ in range(reps):
                 fn()

@@ -192,7 +192,7 @@ LF_CORE void lf_sort(const LfWarp<LANES>& w, float* v, int npad)
     for (int k = 2; k <= npad; k <<= 1) {
         for (int j = k >> 1; j > 0; j >>= 1) {
             for (int t = w.lane; t < (npad >> 1); t += LANES) {
-                int i = 2 * j * (t / j) + (t % j);
+                int i = 2 * (t & ~(j - 1)) + (t & (j - 1));       // j is a power of two: no division
                 int l = i + j;
                 bool up = (i & k) == 0;
                 float a = v[i], b = v[l];

@@ -283,44 +283,43 @@ lf_reduce_tma_kernel(const float* __restrict__ cube, long long n_tiles, int nz, 
 
 // SNR method 2: flux-window sum minus n * min(sigma_clip(sky, sigma=1, maxiters=10)), over std of the noise
 // window (LuciBase.py:1144-1157, 1167-1169).  sigma_clip: centre = median, spread = population std.
-// The spectrum lives in shared memory; the median comes from a bisection on the value range (counting pass per
-// step) refined to the exact order statistics.
-__device__ float warp_select_kth(const float* v, const unsigned char* alive, int n, int k, int lane)
+// The finite samples are sorted ONCE in shared memory (bitonic, padded with +inf): a clip keeps the values inside an
+// interval, so the survivors are always a contiguous range [a, a+m) of the sorted spectrum -- the median is an index,
+// the new range two binary searches, the clipped minimum is v[a].
+__device__ __forceinline__ void warp_bitonic_sort(float* v, int npad, int lane)
 {
-    // k-th smallest (0-based) among alive entries: radix-free bisection on float keys
-    // map floats to order-preserving uints
-    unsigned lo = 0u, hi = 0xffffffffu;
-    auto key = [](float f) { unsigned u = __float_as_uint(f); return (u & 0x80000000u) ? ~u : (u | 0x80000000u); };
-    while (lo < hi) {
-        unsigned mid = lo + ((hi - lo) >> 1);
-        int c = 0;
-        for (int i = lane; i < n; i += 32) if (alive[i] && key(v[i]) <= mid) ++c;
-        c = __reduce_add_sync(0xffffffffu, c);
-        if (c >= k + 1) hi = mid; else lo = mid + 1;
+    for (int k = 2; k <= npad; k <<= 1) {
+        for (int lj = 31 - __clz(k >> 1); lj >= 0; --lj) {               // partner distance j = 1 << lj
+            const int j = 1 << lj;
+            for (int t = lane; t < (npad >> 1); t += 32) {
+                const int i = ((t >> lj) << (lj + 1)) | (t & (j - 1)), l = i + j;   // i has bit lj clear
+                const bool up = (i & k) == 0;
+                const float a = v[i], b = v[l];
+                const float lo = fminf(a, b), hi = fmaxf(a, b);
+                v[i] = up ? lo : hi; v[l] = up ? hi : lo;
+            }
+            __syncwarp();
+        }
     }
-    unsigned u = (lo & 0x80000000u) ? (lo & 0x7fffffffu) : ~lo;
-    return __uint_as_float(u);
 }
 
 __global__ void __launch_bounds__(RED_WARPS * 32)
-lf_snr2_kernel(const float* __restrict__ cube, long long n_spaxel, int nz, long long n_live, int flo, int fhi,
+lf_snr2_kernel(const float* __restrict__ cube, long long n_spaxel, int nz, int npad, long long n_live, int flo, int fhi,
                int nlo, int nhi, float* __restrict__ snr, float* __restrict__ deep)
 {
     extern __shared__ __align__(16) unsigned char smem2[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int nzp = (nz + 15) & ~15;
-    float* v = reinterpret_cast<float*>(smem2) + (size_t)warp * nzp;
-    unsigned char* alive = smem2 + (size_t)RED_WARPS * nzp * sizeof(float) + (size_t)warp * nzp;
+    float* v = reinterpret_cast<float*>(smem2) + (size_t)warp * npad;
     const long long stride = (long long)gridDim.x * RED_WARPS;
     for (long long s = (long long)blockIdx.x * RED_WARPS + warp; s < n_spaxel; s += stride) {
         const float* row = cube + s * (long long)nz;
         float sum = 0.f, fsum = 0.f; double n1 = 0.0, n2 = 0.0; int ncnt = 0, m = 0;
         float allmin = INFINITY;
-        for (int z = lane; z < nz; z += 32) {
-            float x = __ldcs(row + z);
-            v[z] = x;
-            bool fin = (x == x) && fabsf(x) != INFINITY;
-            alive[z] = fin ? 1 : 0;
+        __syncwarp();
+        for (int z = lane; z < npad; z += 32) {
+            float x = z < nz ? __ldcs(row + z) : NAN;
+            const bool fin = (x == x) && fabsf(x) != INFINITY;
+            v[z] = fin ? x : INFINITY;                                    // non-finite samples sort to the end
             m += fin;
             if (x == x) { sum += x; allmin = fminf(allmin, x); if (z >= flo && z < fhi) fsum += x;
                           if (z >= nlo && z < nhi) { n1 += x; n2 += (double)x * x; ++ncnt; } }
@@ -333,32 +332,28 @@ lf_snr2_kernel(const float* __restrict__ cube, long long n_spaxel, int nz, long 
             ncnt += __shfl_xor_sync(0xffffffffu, ncnt, o); m += __shfl_xor_sync(0xffffffffu, m, o);
             allmin = fminf(allmin, __shfl_xor_sync(0xffffffffu, allmin, o));
         }
-        // sigma_clip(sky, sigma=1, maxiters=10): median / population std of the survivors
+        warp_bitonic_sort(v, npad, lane);
+        // sigma_clip(sky, sigma=1, maxiters=10): median / population std of the survivors v[a .. a+m)
+        int a = 0;
         for (int it = 0; it < 10 && m > 0; ++it) {
-            double med;
-            if (m & 1) med = warp_select_kth(v, alive, nz, m / 2, lane);
-            else med = 0.5 * ((double)warp_select_kth(v, alive, nz, m / 2 - 1, lane) + (double)warp_select_kth(v, alive, nz, m / 2, lane));
+            const double med = (m & 1) ? (double)v[a + m / 2] : 0.5 * ((double)v[a + m / 2 - 1] + (double)v[a + m / 2]);
             double s1 = 0.0, s2 = 0.0;
-            for (int z = lane; z < nz; z += 32) if (alive[z]) { double d = (double)v[z] - med; s1 += d; s2 += d * d; }
+            for (int z = a + lane; z < a + m; z += 32) { double d = (double)v[z] - med; s1 += d; s2 += d * d; }
 #pragma unroll
             for (int o = 16; o > 0; o >>= 1) { s1 += __shfl_xor_sync(0xffffffffu, s1, o); s2 += __shfl_xor_sync(0xffffffffu, s2, o); }
-            double mu = s1 / m;
-            double sd = sqrt(fmax(s2 / m - mu * mu, 0.0));
-            double lo_b = med - sd, hi_b = med + sd;
-            int removed = 0;
-            for (int z = lane; z < nz; z += 32)
-                if (alive[z] && !((double)v[z] >= lo_b && (double)v[z] <= hi_b)) { alive[z] = 0; ++removed; }
-            removed = __reduce_add_sync(0xffffffffu, removed);
-            __syncwarp();
-            m -= removed;
+            const double mu = s1 / m;
+            const double sd = sqrt(fmax(s2 / m - mu * mu, 0.0));
+            const double lo_b = med - sd, hi_b = med + sd;
+            // survivors: lo_b <= v <= hi_b, a contiguous sub-range (binary searches, every lane the same)
+            int l0 = a, l1 = a + m;                                       // first index with v >= lo_b
+            while (l0 < l1) { int mid = (l0 + l1) >> 1; if ((double)v[mid] >= lo_b) l1 = mid; else l0 = mid + 1; }
+            int h0 = l0, h1 = a + m;                                      // first index with v > hi_b
+            while (h0 < h1) { int mid = (h0 + h1) >> 1; if ((double)v[mid] > hi_b) h1 = mid; else h0 = mid + 1; }
+            const int removed = m - (h0 - l0);
+            a = l0; m = h0 - l0;
             if (removed == 0) break;
         }
-        float cmin = INFINITY;
-        for (int z = lane; z < nz; z += 32) if (alive[z]) cmin = fminf(cmin, v[z]);
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) cmin = fminf(cmin, __shfl_xor_sync(0xffffffffu, cmin, o));
-        if (m <= 0) cmin = allmin;                                        // LuciBase.py:1151-1152
-        __syncwarp();
+        const float cmin = m > 0 ? v[a] : allmin;                         // LuciBase.py:1151-1152
         if (lane == 0) {
             if (deep) deep[s] = s < n_live ? sum : 0.0f;
             double mu = ncnt > 0 ? n1 / ncnt : 0.0;
@@ -494,8 +489,10 @@ extern "C" cudaError_t lf_run_reduce(int mode, const float* cube, long long n_sp
 {
     long long want = (n_spaxel + RED_WARPS - 1) / RED_WARPS;
     if (mode == 2) {
-        const int nzp = (nz + 15) & ~15;
-        size_t smem = (size_t)RED_WARPS * nzp * (sizeof(float) + 1);
+        int npad = 32;
+        while (npad < nz) npad <<= 1;
+        size_t smem = (size_t)RED_WARPS * npad * sizeof(float);
+        if (smem > 200 * 1024) return cudaErrorInvalidValue;      // spectra longer than 6400 samples
         cudaError_t e = cudaFuncSetAttribute(lf_snr2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
         int occ = 1;
@@ -503,7 +500,7 @@ extern "C" cudaError_t lf_run_reduce(int mode, const float* cube, long long n_sp
         if (occ < 1) return cudaErrorLaunchOutOfResources;
         long long cap = (long long)sm_count * occ;
         int grid = (int)(want < cap ? want : cap); if (grid < 1) grid = 1;
-        lf_snr2_kernel<<<grid, RED_WARPS * 32, smem, stream>>>(cube, n_spaxel, nz, n_live, flo, fhi, nlo, nhi, snr, deep);
+        lf_snr2_kernel<<<grid, RED_WARPS * 32, smem, stream>>>(cube, n_spaxel, nz, npad, n_live, flo, fhi, nlo, nhi, snr, deep);
         return cudaGetLastError();
     }
     // TMA-staged form for the whole tiles of RED_TILE_ROWS spaxels when the cube is 16-byte aligned and a stage ring

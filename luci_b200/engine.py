@@ -53,7 +53,10 @@ _workspaces = {}
 
 
 def workspace_for(device, nbytes):
-    ws = _workspaces.setdefault(str(device), Workspace())
+    """One workspace per (device, stream): the fit keeps per-spaxel state in it between its stage kernels, so two
+    streams fitting at the same time must not share it."""
+    key = (str(device), int(torch.cuda.current_stream(device).cuda_stream))
+    ws = _workspaces.setdefault(key, Workspace())
     return ws.get(nbytes, device)
 
 

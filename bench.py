@@ -371,6 +371,22 @@ def main():
             gbs = cube.numel() * 4 / (ms * 1e-3) / 1e9
             red[name] = {'ms': ms, 'achieved': gbs, 'peak': hbm_peak, 'unit': 'GB/s', 'frac': gbs / hbm_peak,
                          'bound': 'hbm'}
+        # 2x2 spatial binning of the slab (bin_cube_function, LuciUtility.py:319-355): reads the cube, writes a quarter
+        nxl = (nx_local // 2) * 2
+        if nxl >= 2:
+            c3 = cube.view(nx_local, args.ny, args.nz)
+            fnb = lambda: engine.bin_cube(c3, 2, 0, nxl, 0, (args.ny // 2) * 2)
+            for _ in range(2):
+                fnb()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            torch.cuda.synchronize(); e0.record()
+            for _ in range(5):
+                fnb()
+            e1.record(); e1.synchronize()
+            ms = e0.elapsed_time(e1) / 5
+            gbs = 1.25 * nxl * ((args.ny // 2) * 2) * args.nz * 4 / (ms * 1e-3) / 1e9
+            red['bin_cube_2x2'] = {'ms': ms, 'achieved': gbs, 'peak': hbm_peak, 'unit': 'GB/s', 'frac': gbs / hbm_peak,
+                                   'bound': 'hbm'}
         line['roofline_reductions'] = red
 
     # --- end to end: cube in pinned host memory, streamed in chunks through the C ABI

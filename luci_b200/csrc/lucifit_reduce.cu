@@ -364,22 +364,38 @@ lf_snr2_kernel(const float* __restrict__ cube, long long n_spaxel, int nz, int n
     }
 }
 
-// b x b nansum binning: one thread per (output spaxel, 4 z samples)
-__global__ void lf_bin_kernel(const float* __restrict__ cube, int ny, int nz, int b, int x0, int y0, int nxb,
-                              int nyb, float* __restrict__ out)
+// b x b nansum binning (bin_cube_function, LUCI/LuciUtility.py:332-341): one warp per OUTPUT spaxel walks the
+// spectral axis (coalesced, no per-element index divisions), four output samples per lane in flight; the b*b input
+// rows of a bin are read exactly once.
+template <int B>                                        // B > 0: compile-time bin size (all B*B rows' loads in flight)
+__global__ void __launch_bounds__(RED_WARPS * 32)
+lf_bin_kernel(const float* __restrict__ cube, int ny, int nz, int b_rt, int x0, int y0, int nxb, int nyb,
+              float* __restrict__ out)
 {
-    long long total = (long long)nxb * nyb * nz;
-    for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (long long)gridDim.x * blockDim.x) {
-        int z = (int)(t % nz);
-        long long sp = t / nz;
-        int j = (int)(sp % nyb), i = (int)(sp / nyb);
-        float acc = 0.0f;
-        for (int di = 0; di < b; ++di)
-            for (int dj = 0; dj < b; ++dj) {
-                float v = cube[((long long)(x0 + i * b + di) * ny + (y0 + j * b + dj)) * nz + z];
-                if (v == v) acc += v;
-            }
-        out[t] = acc;
+    const int b = B > 0 ? B : b_rt;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const long long n_out = (long long)nxb * nyb;
+    const long long stride = (long long)gridDim.x * RED_WARPS;
+    for (long long sp = (long long)blockIdx.x * RED_WARPS + warp; sp < n_out; sp += stride) {
+        const int j = (int)(sp % nyb), i = (int)(sp / nyb);
+        const float* base = cube + ((long long)(x0 + i * b) * ny + (y0 + j * b)) * nz;
+        float* orow = out + sp * (long long)nz;
+        for (int z0 = lane; z0 < nz; z0 += 128) {
+            float acc[4] = {0.0f, 0.0f, 0.0f, 0.0f};
+#pragma unroll
+            for (int di = 0; di < b; ++di)
+#pragma unroll
+                for (int dj = 0; dj < b; ++dj) {
+                    const float* r = base + ((long long)di * ny + dj) * nz;
+                    float q[4];
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) { const int z = z0 + 32 * u; q[u] = z < nz ? __ldcs(r + z) : 0.0f; }
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) acc[u] += (q[u] == q[u]) ? q[u] : 0.0f;
+                }
+#pragma unroll
+            for (int u = 0; u < 4; ++u) { const int z = z0 + 32 * u; if (z < nz) orow[z] = acc[u]; }
+        }
     }
 }
 
@@ -550,11 +566,15 @@ extern "C" cudaError_t lf_run_reduce(int mode, const float* cube, long long n_sp
 extern "C" cudaError_t lf_run_bin(const float* cube, int ny, int nz, int b, int x0, int y0, int nxb, int nyb,
                                   float* out, int sm_count, cudaStream_t stream)
 {
-    long long total = (long long)nxb * nyb * nz;
-    long long want = (total + 255) / 256;
-    long long cap = (long long)sm_count * 16;
+    long long want = ((long long)nxb * nyb + RED_WARPS - 1) / RED_WARPS;
+    int occ = 1;
+    if (b == 2) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, lf_bin_kernel<2>, RED_WARPS * 32, 0);
+    else cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, lf_bin_kernel<0>, RED_WARPS * 32, 0);
+    if (occ < 1) occ = 1;
+    long long cap = (long long)sm_count * occ;
     int grid = (int)(want < cap ? want : cap); if (grid < 1) grid = 1;
-    lf_bin_kernel<<<grid, 256, 0, stream>>>(cube, ny, nz, b, x0, y0, nxb, nyb, out);
+    if (b == 2) lf_bin_kernel<2><<<grid, RED_WARPS * 32, 0, stream>>>(cube, ny, nz, b, x0, y0, nxb, nyb, out);
+    else lf_bin_kernel<0><<<grid, RED_WARPS * 32, 0, stream>>>(cube, ny, nz, b, x0, y0, nxb, nyb, out);
     return cudaGetLastError();
 }
 

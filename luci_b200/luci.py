@@ -473,9 +473,18 @@ class Luci():
             integrated = integrated / spec_ct
         if bkg is not None:
             integrated = integrated - torch.from_numpy(np.asarray(bkg, dtype=np.float64)).to(integrated.device) * spec_ct
-        sky32 = integrated.to(torch.float32).view(1, -1).contiguous()
         # the reference passes the angle of the LAST pixel of its double loop (LuciBase.py:1035)
         theta = float(self.interferometer_theta[self.cube_final.shape[0] - 1, self.cube_final.shape[1] - 1])
+        fit_dict = self._fit_one_spectrum(integrated, theta, lines, fit_function, vel_rel, sigma_rel, uncertainty_bool,
+                                          nii_cons, spec_min, spec_max, obj_redshift, prior_values)
+        sky = integrated.cpu().numpy()
+        return np.asarray(self.spectrum_axis), sky, fit_dict
+
+    def _fit_one_spectrum(self, spectrum, theta, lines, fit_function, vel_rel, sigma_rel, uncertainty_bool, nii_cons,
+                          spec_min, spec_max, obj_redshift, prior_values):
+        """One spectrum (device tensor ``[nz]``) through ``lucifit_fit_batch``; returns the dictionary of
+        ``Fit.fit`` (``LuciFit.py:824-834``).  Shared by fit_spectrum_region / fit_pixel."""
+        sky32 = spectrum.to(torch.float32).view(1, -1).contiguous()
         have_prior = prior_values is not None
         cfg = self._make_config(lines, fit_function, vel_rel, sigma_rel, uncertainty_bool, nii_cons, spec_min, spec_max,
                                 obj_redshift, ml_scale=have_prior)
@@ -502,8 +511,91 @@ class Luci():
         fit_dict['scale'] = None
         from .host_ops import plot_vector
         fit_dict['fit_vector'] = plot_vector(cfg, fit_dict['fit_sol'], theta, self.cube_final.device)
-        sky = integrated.cpu().numpy()
-        return np.asarray(self.spectrum_axis), sky, fit_dict
+        return fit_dict
+
+    def fit_pixel(self, lines, fit_function, vel_rel, sigma_rel, pixel_x, pixel_y, binning=None, bkg=None, absorp=None,
+                  bayes_bool=False, bayes_method='emcee', uncertainty_bool=False, nii_cons=True, spec_min=None,
+                  spec_max=None, obj_redshift=0.0, n_stoch=1, bkgType='standard', pca_coefficient_array=None,
+                  pca_vectors=None, pca_mean=None, prior_values=None):
+        """``LuciBase.py:724-838``: fit one pixel, or with ``binning`` the nansum of the ``2 binning`` square
+        ``[pixel - binning, pixel + binning)`` around it.  Returns ``(axis, sky, fit_dict)``.
+
+        Like the reference the background is scaled by ``binning ** 2`` (``:769``), which makes ``bkg`` usable only
+        together with ``binning`` there (``None ** 2`` raises); here ``binning=None`` subtracts the plain background.
+        The reference subtracts in place from a view of ``cube_final`` (``:767-769``), altering the cube; that side
+        effect is not reproduced.  ``prior_values=(vel, broad)`` are scalars in km/s."""
+        self._reject_unsupported(bayes_bool, absorp, [False], n_stoch, bkgType)
+        if int(n_stoch) != 1:
+            raise NotImplementedError('n_stoch > 1 is implemented for the cube fits (fit_cube / fit_region) only')
+        if absorp is not None:
+            raise NotImplementedError('absorp is implemented for fit_cube only')
+        b = int(binning) if (binning is not None and binning != 1) else 0
+        if b:
+            box = self.cube_final[max(pixel_x - b, 0):pixel_x + b, max(pixel_y - b, 0):pixel_y + b, :]
+            sky = torch.nan_to_num(box.to(torch.float64), nan=0.0).sum(dim=(0, 1))
+        else:
+            sky = self.cube_final[pixel_x, pixel_y, :].to(torch.float64)
+        if bkgType == 'standard':
+            if bkg is not None:
+                scale = float(binning) ** 2 if binning is not None else 1.0
+                sky = sky - torch.from_numpy(np.asarray(bkg, dtype=np.float64)).to(sky.device) * scale
+        elif bkgType == 'pca':
+            if pca_coefficient_array is None or pca_vectors is None or pca_mean is None:
+                raise Exception("bkgType='pca' needs pca_coefficient_array, pca_vectors and pca_mean")
+            band = {'SN3': (675.0, 670.0), 'SN2': (505.0, 480.0)}.get(self.hdr_dict['FILTER'])
+            if band is None:
+                raise Exception('the PCA background is implemented for SN3 and SN2 (LuciBase.py:774-783)')
+            nm_axis = 1e7 / np.asarray(self.spectrum_axis, dtype=np.float64)
+            lo_i, hi_i = int(np.argmin(np.abs(nm_axis - band[0]))), int(np.argmin(np.abs(nm_axis - band[1])))
+            coef = np.asarray(pca_coefficient_array, dtype=np.float64)
+            if b:                                                       # coefficients of the box: nansum (:784-788)
+                c = np.nansum(coef[max(pixel_x - b, 0):pixel_x + b, max(pixel_y - b, 0):pixel_y + b, :], axis=(0, 1))
+            else:
+                c = coef[pixel_x, pixel_y]                              # (the reference names an undefined x_pix here, :790)
+            bkg_pix = np.asarray(pca_mean, dtype=np.float64) + c @ np.asarray(pca_vectors, dtype=np.float64)
+            ref_band = sky[lo_i:hi_i]
+            scale_spec = ref_band[~torch.isnan(ref_band)].max()
+            sky = sky - scale_spec * torch.from_numpy(bkg_pix).to(sky.device)
+        else:
+            raise Exception('Please set bkgType to either standard or pca')
+        if bool(torch.isnan(sky).any()):
+            raise NotImplementedError('fit_pixel: NaN channels (the reference drops them, LuciBase.py:801-803) are not '
+                                      'supported; spectra with NaNs are returned as zeros by the cube fits')
+        theta = float(self.interferometer_theta[pixel_x, pixel_y])
+        fit_dict = self._fit_one_spectrum(sky, theta, lines, fit_function, vel_rel, sigma_rel, uncertainty_bool, nii_cons,
+                                          spec_min, spec_max, obj_redshift, prior_values)
+        return np.asarray(self.spectrum_axis), sky.cpu().numpy(), fit_dict
+
+    def extract_spectrum(self, x_min, x_max, y_min, y_max, bkg=None, binning=None, mean=False):
+        """``LuciBase.py:844-893``: spectrum summed over a rectangle (NaN channels skipped), ``mean`` divides by the
+        reference's ``spec_ct`` -- which it increments only ONCE (``:887-889``), so ``mean=True`` returns the plain sum
+        there; with ``strict_reference=False`` the mean over the summed spectra is returned instead.  The background
+        is subtracted from every summed spectrum (times ``binning ** 2`` when binned, ``:882-886``)."""
+        cube = self.cube_final
+        if binning is not None and binning != 1:
+            self.bin_cube(self.cube_final, self.header, binning, x_min, x_max, y_min, y_max)
+            x_max = int((x_max - x_min) / binning)
+            y_max = int((y_max - y_min) / binning)
+            x_min = y_min = 0
+            cube = self.cube_binned
+        box = cube[x_min:x_max, y_min:y_max, :]
+        n_spec = box.shape[0] * box.shape[1]
+        integrated = torch.nan_to_num(box.to(torch.float64), nan=0.0).sum(dim=(0, 1))
+        if bkg is not None:
+            scale = float(binning) ** 2 if binning else 1.0
+            integrated = integrated - torch.from_numpy(np.asarray(bkg, dtype=np.float64)).to(integrated.device) * (scale * n_spec)
+        if mean and not self.strict_reference:
+            integrated = integrated / max(n_spec, 1)
+        return np.asarray(self.spectrum_axis), integrated.cpu().numpy()
+
+    def extract_spectrum_region(self, region, mean=False):
+        """``LuciBase.py:895-947``: spectrum summed (or averaged) over a boolean mask / ``.npy`` mask."""
+        mask = torch.from_numpy(np.asarray(self._load_mask(region, False)).astype(bool)).to(self.cube_final.device)
+        spec_ct = int(mask.sum().item())
+        integrated = self.cube_final[mask].sum(dim=0, dtype=torch.float64)
+        if mean:
+            integrated = integrated / spec_ct
+        return np.asarray(self.spectrum_axis), integrated.cpu().numpy()
 
     def fit_wvt(self, lines, fit_function, vel_rel, sigma_rel, bkg=None, bayes_bool=False, uncertainty_bool=False,
                 n_threads=1, initial_values=[False], n_stoch=1, stn_target=10, bin_map=None, prior_values=None,

@@ -276,3 +276,58 @@ def test_fit_wvt_bins_equal_fit_spectrum_region(world):
         np.save(os.path.join(folder, 'bool_bin_map_%i.npy' % k), bin_map == k)
     vel2 = luci.fit_wvt(SN3, 'sincgauss', [1] * 5, [1] * 5, prior_values=(v0, b0), uncertainty_bool=True)[0]
     np.testing.assert_array_equal(vel, vel2)
+
+
+def test_fit_pixel_matches_fit_cube_and_binned_box(world):
+    """fit_pixel (LuciBase.py:724-838): a single pixel equals the same spaxel of fit_cube; with binning the spectrum is
+    the nansum of the [pixel - b, pixel + b) box."""
+    luci, sc, out = world
+    v0, b0 = sc.priors()
+    x, y = 5, 4
+    axis, sky, fd = luci.fit_pixel(SN3, 'sincgauss', [1] * 5, [1] * 5, x, y, prior_values=(v0[y, x], b0[y, x]),
+                                   uncertainty_bool=True)
+    host = luci.cube_final.cpu().numpy()
+    np.testing.assert_array_equal(sky.astype(np.float32), host[x, y])
+    assert axis.shape == sky.shape
+    velc, broadc, fluxc, amplc = luci.fit_cube(SN3, 'sincgauss', [1] * 5, [1] * 5, x, x + 1, y, y + 1,
+                                               prior_values=(v0[y:y + 1, x:x + 1], b0[y:y + 1, x:x + 1]),
+                                               uncertainty_bool=True)
+    np.testing.assert_array_equal(np.float32(fd['velocities']), velc[0, 0])
+    np.testing.assert_array_equal(np.float32(fd['fluxes']), fluxc[0, 0])
+    assert set(fd) >= {'fit_sol', 'fit_uncertainties', 'amplitudes', 'fluxes', 'flux_errors', 'chi2', 'velocities',
+                       'sigmas', 'vels_errors', 'sigmas_errors', 'axis_step', 'corr', 'continuum', 'continuum_error',
+                       'scale', 'vel_ml', 'broad_ml', 'fit_vector', 'fit_axis'}
+    assert fd['fit_vector'].shape == axis.shape and fd['fit_sol'].shape == (16,)
+    # binned box with a background: sky = nansum(box) - bkg * binning^2 (LuciBase.py:762-769)
+    bkg = np.full(host.shape[2], 0.01e-17)
+    _, sky2, fd2 = luci.fit_pixel(SN3, 'sincgauss', [1] * 5, [1] * 5, x, y, binning=2, bkg=bkg,
+                                  prior_values=(v0[y, x], b0[y, x]))
+    np.testing.assert_allclose(sky2, host[x - 2:x + 2, y - 2:y + 2].astype(np.float64).sum(axis=(0, 1)) - bkg * 4, rtol=1e-12)
+    assert 8.0 < fd2['amplitudes'][0] / 1e-17 < 20.0 and fd2['chi2'] > 0
+
+
+def test_extract_spectrum_and_region(world):
+    """extract_spectrum / extract_spectrum_region (LuciBase.py:844-947)."""
+    luci, sc, out = world
+    host = luci.cube_final.cpu().numpy().astype(np.float64)
+    axis, spec = luci.extract_spectrum(2, 6, 1, 5)
+    np.testing.assert_allclose(spec, host[2:6, 1:5].sum(axis=(0, 1)), rtol=1e-12)
+    np.testing.assert_array_equal(axis, luci.spectrum_axis)
+    bkg = np.full(host.shape[2], 0.02e-17)
+    _, specb = luci.extract_spectrum(2, 6, 1, 5, bkg=bkg)
+    np.testing.assert_allclose(specb, host[2:6, 1:5].sum(axis=(0, 1)) - 16 * bkg, rtol=1e-12)
+    # mean=True: the reference divides by a counter it increments once (LuciBase.py:887-889)
+    _, specm = luci.extract_spectrum(2, 6, 1, 5, mean=True)
+    np.testing.assert_allclose(specm, spec, rtol=1e-12)
+    luci.strict_reference = False
+    try:
+        _, specm = luci.extract_spectrum(2, 6, 1, 5, mean=True)
+        np.testing.assert_allclose(specm, spec / 16, rtol=1e-12)
+    finally:
+        luci.strict_reference = True
+    _, spec2 = luci.extract_spectrum(0, 12, 0, 10, binning=2)
+    np.testing.assert_allclose(spec2, host.sum(axis=(0, 1)), rtol=1e-5)
+    mask = np.zeros((12, 10), bool)
+    mask[1:4, 2:9] = True
+    _, specr = luci.extract_spectrum_region(mask, mean=True)
+    np.testing.assert_allclose(specr, host[1:4, 2:9].sum(axis=(0, 1)) / 21, rtol=1e-12)

@@ -5,18 +5,28 @@
 #include <cuda_runtime.h>
 #include "lucifit_core.cuh"
 
-#define LF_PREP_WARPS 8
-#ifndef LF_LM_WARPS
-#define LF_LM_WARPS 4
+// Warps per CTA.  Measured on the benchmark cube (B200, 1 M spaxels): consecutive spaxels go to consecutive warps of a
+// CTA, and larger CTAs keep neighbouring spaxels (neighbouring DRAM pages) on one SM -- the LM kernel runs 57.1 / 54.7 /
+// 52.5 ms with 4 / 8 / 16 warps per CTA at the same 16 resident warps per SM, the prep kernel 3.71 -> 3.32 ms from 8 to
+// 16, the output kernel is best at 8.
+#ifndef LF_PREP_WARPS
+#define LF_PREP_WARPS 16
 #endif
-// Resident CTAs per SM the LM kernel is compiled for (register cap), by size of the normal equations: up to 8
-// unknowns (44 accumulators) fit 96 registers without spilling; larger systems get the registers they need.
+// The LM kernel keeps ONE resident CTA per SM and sizes it by the normal equations: up to 8 unknowns (44 accumulators)
+// fit the 128 registers that 16 warps leave per thread; larger systems get 12 or 8 warps and the registers they need.
+#ifndef LF_LM_WARPS_SMALL
+#define LF_LM_WARPS_SMALL 16
+#endif
 #ifndef LF_LM_MINB_SMALL
-#define LF_LM_MINB_SMALL 4
+#define LF_LM_MINB_SMALL 1
 #endif
-template <int NA> struct LfLmBlocks { enum { V = NA <= 44 ? LF_LM_MINB_SMALL : NA <= 77 ? 3 : 2 }; };
+template <int NA> struct LfLmBlocks {
+    enum { W = NA <= 44 ? LF_LM_WARPS_SMALL : NA <= 77 ? 12 : 8, V = NA <= 44 ? LF_LM_MINB_SMALL : 1 };
+};
 #define LF_UNC_WARPS 4
+#ifndef LF_OUT_WARPS
 #define LF_OUT_WARPS 8
+#endif
 
 struct LfLaunch {
     LfCfg cfg;
@@ -68,16 +78,17 @@ lf_prep_kernel(const __grid_constant__ LfLaunch a)
 }
 
 template <int MODEL, int L, int NG>
-__global__ void __launch_bounds__(LF_LM_WARPS * 32, (LfLmBlocks<LfDims<MODEL, L, NG, NG>::NA>::V))
+__global__ void __launch_bounds__((LfLmBlocks<LfDims<MODEL, L, NG, NG>::NA>::W) * 32, (LfLmBlocks<LfDims<MODEL, L, NG, NG>::NA>::V))
 lf_lm_kernel(const __grid_constant__ LfLaunch a)
 {
     extern __shared__ __align__(16) unsigned char lf_smem[];
+    constexpr int WARPS = LfLmBlocks<LfDims<MODEL, L, NG, NG>::NA>::W;
     const float* xo_s = lf_stage_xo(a, lf_smem);
     const int warp = threadIdx.x >> 5;
     LfWork wk = lf_work_at(LF_STAGE_LM, a.ly, lf_smem + a.xo_bytes + (size_t)warp * a.ly.lm_bytes);
     LfWarp<32> w;
-    const long long stride = (long long)gridDim.x * LF_LM_WARPS;
-    for (long long s = (long long)blockIdx.x * LF_LM_WARPS + warp; s < a.n; s += stride) {
+    const long long stride = (long long)gridDim.x * WARPS;
+    for (long long s = (long long)blockIdx.x * WARPS + warp; s < a.n; s += stride) {
         const long long row = a.index ? a.index[s] : a.index_base + s;
         lf_stage_lm<MODEL, L, NG, NG, 32>(a.cfg, w, xo_s, a.cube + row * (long long)a.cfg.nz, wk,
                                           a.state + s * (long long)a.cfg.state_floats);
@@ -149,7 +160,8 @@ cudaError_t lf_launch(const LfLaunch& a, int stages)
         if (e != cudaSuccess) return e;
     }
     if (stages & 2) {
-        e = lf_launch_one(lf_lm_kernel<MODEL, L, NG>, a, LF_LM_WARPS, (size_t)a.xo_bytes + (size_t)LF_LM_WARPS * a.ly.lm_bytes);
+        constexpr int LMW = LfLmBlocks<LfDims<MODEL, L, NG, NG>::NA>::W;
+        e = lf_launch_one(lf_lm_kernel<MODEL, L, NG>, a, LMW, (size_t)a.xo_bytes + (size_t)LMW * a.ly.lm_bytes);
         if (e != cudaSuccess) return e;
     }
     if ((stages & 4) && a.unc_ws) {

@@ -125,6 +125,17 @@ int lucifit_fit_stages(const lucifit_config* cfg, int stages, int64_t n_spaxel, 
                        const float* bkg, float* out_rows, float* out_fit_sol, float* out_unc, int32_t* out_status,
                        void* workspace, size_t workspace_bytes, void* stream);
 
+/* Initial velocity / broadening (km/s) of n_spaxel spectra, measured from the data: what the reference obtains from
+ * its Keras CNN (Fit.estimate_priors_ML, LUCI/LuciFit.py:335-362, consumed by line_vals_estimate :382-430) and feeds
+ * to the optimiser as vel_ml / broad_ml.  Velocity: matched filter of the continuum-subtracted fit window against
+ * the expected centres of cfg's lines over the grid v_min, v_min + v_step, ... <= v_max (at most 512 points),
+ * refined by a parabola; broadening: FWHM of the strongest line with the instrumental sinc width removed.
+ * Uses cfg->model, line_nm, axis, fit_lo / fit_hi, step_nm, n_steps, zpd_index.  cube / spaxel_index / theta_deg / bkg
+ * as in lucifit_fit_batch; vel0, broad0: [n_spaxel] DEVICE outputs, directly usable as its vel0 / broad0. */
+int lucifit_estimate_prior(const lucifit_config* cfg, int64_t n_spaxel, const float* cube, const int64_t* spaxel_index,
+                           const float* theta_deg, const float* bkg, double v_min, double v_max, double v_step,
+                           float* vel0, float* broad0, void* stream);
+
 /* Deep image: deep[s] = nansum_z cube[s][z] for s < n_spaxel - n_zero_tail, 0 for the rest
  * (create_deep_image leaves the trailing nx mod 10 x-rows zero, LuciBase.py:173-177). */
 int lucifit_deep_image(const float* cube, int64_t n_spaxel, int nz, int64_t n_zero_tail, float* deep,

@@ -42,8 +42,8 @@ class lucifit_config(C.Structure):
 
 
 EXPORTS = ['lucifit_row_floats', 'lucifit_workspace_bytes', 'lucifit_fit_batch', 'lucifit_fit_stages', 'lucifit_deep_image',
-           'lucifit_snr_map', 'lucifit_bin_cube', 'lucifit_sim_cube', 'lucifit_peak_probe', 'lucifit_last_error',
-           'lucifit_version']
+           'lucifit_snr_map', 'lucifit_bin_cube', 'lucifit_sim_cube', 'lucifit_peak_probe', 'lucifit_estimate_prior',
+           'lucifit_last_error', 'lucifit_version']
 
 _lib = None
 
@@ -70,6 +70,8 @@ def declare(lib):
     lib.lucifit_sim_cube.restype = C.c_int
     lib.lucifit_peak_probe.argtypes = [C.c_int, C.c_int, C.c_int, vp, vp]
     lib.lucifit_peak_probe.restype = C.c_int
+    lib.lucifit_estimate_prior.argtypes = [cfgp, i64, vp, vp, vp, vp, C.c_double, C.c_double, C.c_double, vp, vp, vp]
+    lib.lucifit_estimate_prior.restype = C.c_int
     lib.lucifit_last_error.argtypes = []
     lib.lucifit_last_error.restype = C.c_char_p
     lib.lucifit_version.argtypes = []

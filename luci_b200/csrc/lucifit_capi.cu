@@ -4,6 +4,7 @@
 
 #include "lucifit_host.hpp"
 #include "lucifit_fit_kernel.cuh"
+#include "lucifit_prior.cuh"
 
 static thread_local std::string g_err;
 static int fail(int code, const std::string& msg) { g_err = msg; return code; }
@@ -54,6 +55,8 @@ extern "C" cudaError_t lf_run_bin(const float* cube, int ny, int nz, int b, int 
                                   float* out, int sm_count, cudaStream_t stream);
 extern "C" cudaError_t lf_run_sim(const LfSimArgs* a, int sm_count, cudaStream_t stream);
 extern "C" cudaError_t lf_run_peak(int mode, int iters, int blocks, float* out, cudaStream_t stream);
+extern "C" cudaError_t lf_run_prior(const LfPriorCfg* c, long long n, const float* cube, const long long* index,
+                                    const float* theta, float* vel, float* broad, int sm_count, cudaStream_t stream);
 
 static int sm_count_of_current_device(int* out)
 {
@@ -231,6 +234,23 @@ int lucifit_sim_cube(const lucifit_config* cfg, int64_t n_spaxel, const float* a
     int sm = 0; int rc = sm_count_of_current_device(&sm); if (rc) return rc;
     e = lf_run_sim(&a, sm, st);
     if (e != cudaSuccess) return cuda_fail(e, "launch lf_sim_kernel");
+    return 0;
+}
+
+int lucifit_estimate_prior(const lucifit_config* cfg, int64_t n_spaxel, const float* cube, const int64_t* spaxel_index,
+                           const float* theta_deg, const float* bkg, double v_min, double v_max, double v_step,
+                           float* vel0, float* broad0, void* stream)
+{
+    LfPriorCfg pc;
+    std::string err = lf_make_prior_cfg(cfg, v_min, v_max, v_step, pc);
+    if (!err.empty()) return fail(LUCIFIT_EINVAL, err);
+    if (n_spaxel < 0) return fail(LUCIFIT_EINVAL, "n_spaxel < 0");
+    if (n_spaxel == 0) return 0;
+    if (!cube || !theta_deg || !vel0 || !broad0) return fail(LUCIFIT_EINVAL, "cube, theta_deg, vel0 and broad0 are required");
+    pc.bkg = bkg;
+    int sm = 0; int rc = sm_count_of_current_device(&sm); if (rc) return rc;
+    cudaError_t e = lf_run_prior(&pc, n_spaxel, cube, (const long long*)spaxel_index, theta_deg, vel0, broad0, sm, (cudaStream_t)stream);
+    if (e != cudaSuccess) return cuda_fail(e, "launch lf_prior_kernel");
     return 0;
 }
 

@@ -10,6 +10,7 @@
 
 #include "../../include/lucifit.h"
 #include "lucifit_core.cuh"
+#include "lucifit_prior.cuh"
 
 struct LfPlan {
     LfCfg dev;                 // pointers filled by the caller once the tables are placed
@@ -172,5 +173,37 @@ static inline std::string lf_make_plan(const lucifit_config* c, LfPlan& pl, int 
     d.state_floats = (int)lf_align((size_t)LF_SO_TH + P, 2);
     pl.state_bytes = sizeof(float) * d.state_floats + (d.uncertainty ? sizeof(double) * (3 * (size_t)L + 1) : 0);
     lf_make_layout(L, P, c->nz, pl.nfit, pl.ncont, lanes, pl.ly);
+    return "";
+}
+
+// Constants of lucifit_estimate_prior from the public config (velocity grid in km/s).  Returns "" on success.
+static inline std::string lf_make_prior_cfg(const lucifit_config* c, double v_min, double v_max, double v_step, LfPriorCfg& pc)
+{
+    if (!c) return "config is NULL";
+    if (c->model < 0 || c->model > 2) return "model must be 0 (gaussian), 1 (sinc) or 2 (sincgauss)";
+    const int L = c->n_lines;
+    if (L < 1 || L > LF_MAX_LINES) return "n_lines must be in [1, 8]";
+    if (c->nz < 8 || !c->axis) return "axis missing or nz < 8";
+    if (!(c->fit_lo >= 0 && c->fit_hi <= c->nz && c->fit_hi - c->fit_lo >= 8)) return "fit window must hold at least 8 samples";
+    if (!(c->step_nm > 0) || !(c->n_steps - c->zpd_index > 0)) return "STEP and (STEPNB - ZPDINDEX) must be positive";
+    if (!(v_step > 0) || !(v_max >= v_min)) return "velocity grid needs v_step > 0 and v_max >= v_min";
+    const double nv = floor((v_max - v_min) / v_step + 0.5) + 1.0;
+    if (nv > LF_PRIOR_MAX_GRID) return "velocity grid has more than 512 points";
+    memset(&pc, 0, sizeof(pc));
+    pc.model = c->model; pc.L = L; pc.nz = c->nz; pc.fit_lo = c->fit_lo; pc.nfit = c->fit_hi - c->fit_lo;
+    if (pc.nfit > 4096) return "fit window too long for the prior estimator's shared-memory layout";
+    pc.nv = (int)nv; pc.v_min = (float)v_min; pc.v_step = (float)v_step;
+    pc.inv_vmax = (float)(1.0 / fmax(fmax(fabs(v_min), fabs(v_max)), 1.0));
+    const double x_ref = c->axis[c->fit_lo];
+    for (int i = c->fit_lo + 1; i < c->fit_hi; ++i)
+        if (!(c->axis[i] > c->axis[i - 1])) return "axis must be strictly increasing (cm^-1)";
+    for (int k = 0; k < L; ++k) {
+        if (!(c->line_nm[k] > 0)) return "line_nm must be positive";
+        pc.p0[k] = (float)(1e7 / c->line_nm[k]);
+        pc.p0_off[k] = (float)(1e7 / c->line_nm[k] - x_ref);
+    }
+    pc.chan = (float)((c->axis[c->fit_hi - 1] - x_ref) / (double)(pc.nfit - 1));
+    pc.axis_k = 1e7 / (2.0 * c->step_nm * (c->n_steps - c->zpd_index));
+    pc.bkg = nullptr;
     return "";
 }

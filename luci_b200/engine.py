@@ -215,6 +215,37 @@ def unpack_rows(rows, L):
     return out
 
 
+PRIOR_V_RANGE = (-500.0, 500.0)    # km/s: the velocity range the reference's CNN was trained on
+PRIOR_V_STEP = 6.0                 # km/s (1/8 of an R = 5000 SN3 channel)
+
+
+def estimate_prior(cfg: FitConfig, cube, theta, index=None, bkg=None, v_range=PRIOR_V_RANGE, v_step=PRIOR_V_STEP):
+    """``lucifit_estimate_prior``: (velocity, broadening) in km/s of every fitted spaxel, measured from the spectra
+    (matched filter + line width) -- the stand-in for the reference's CNN prior (LuciFit.py:335-362).  Arguments as
+    :func:`fit_batch`; returns two float32 device tensors ``[n]`` usable as its ``vel0`` / ``broad0``."""
+    lib = _capi.lib()
+    require_cuda(cube, 'cube', torch.float32)
+    dev = cube.device
+    if cube.dim() != 2 or cube.shape[1] != cfg.c.nz:
+        raise ValueError('cube must be [n_rows, nz=%d]' % cfg.c.nz)
+    n = int(index.numel()) if index is not None else int(cube.shape[0])
+    require_cuda(theta, 'theta', torch.float32)
+    if theta.numel() != n:
+        raise ValueError('theta must have one entry per fitted spaxel')
+    if index is not None:
+        require_cuda(index, 'index', torch.int64)
+    if bkg is not None:
+        require_cuda(bkg, 'bkg', torch.float32)
+    vel = torch.empty((n,), dtype=torch.float32, device=dev)
+    broad = torch.empty((n,), dtype=torch.float32, device=dev)
+    with torch.cuda.device(dev):
+        check(lib.lucifit_estimate_prior(cfg.byref(), n, _ptr(cube), _ptr(index), _ptr(theta), _ptr(bkg),
+                                         float(v_range[0]), float(v_range[1]), float(v_step), _ptr(vel), _ptr(broad),
+                                         _stream()))
+    launch_counter['n'] += 1 if n > 0 else 0
+    return vel, broad
+
+
 def deep_image(cube2d, n_zero_tail=0):
     """``cube2d [n_spaxel, nz]`` -> ``deep [n_spaxel]`` (nansum over z); the last ``n_zero_tail`` entries are 0."""
     lib = _capi.lib()

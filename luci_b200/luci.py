@@ -9,7 +9,9 @@ cube.  The cube lives in HBM as float32 ``[x, y, z]`` (z contiguous), exactly th
 Differences that are deliberate and documented in DESIGN.md:
   * ``Luci.from_arrays(...)`` builds the object from in-memory arrays (h5py/astropy are optional here).
   * the CNN prior of the reference (TensorFlow, out of scope) enters as ``prior_values=(vel_map, broad_map)`` in
-    km/s, which is exactly what the CNN writes into ``vel_ml`` / ``broad_ml`` (``LuciFit.py:352-361``);
+    km/s, which is exactly what the CNN writes into ``vel_ml`` / ``broad_ml`` (``LuciFit.py:352-361``); without
+    ``prior_values`` and with ``ML_bool=True`` the two numbers are measured from each spectrum on the device
+    (``engine.estimate_prior`` -> ``lucifit_estimate_prior``: matched-filter velocity, line-width broadening);
   * ``fit_entire_cube`` honours its keyword arguments and returns the ``fit_cube`` tuple (the reference drops them
     and returns ``None``, ``LuciBase.py:255``);
   * the Bayesian branch (``bayes_bool``) raises ``NotImplementedError`` (out of scope); PCA background, absorption
@@ -255,14 +257,19 @@ class Luci():
             prior_values = (np.asarray(initial_values[0], dtype=np.float32), np.asarray(initial_values[1], dtype=np.float32))
             n_stoch = 1
         have_prior = prior_values is not None
-        if not have_prior and self.ML_bool and fit_function != 'sinc':
-            warnings.warn('no prior_values given: starting every fit from velocity = broadening = 0 like the '
-                          "reference's ML_bool=False path, which only works for fit_function='sinc'")
+        # ML_bool=True without explicit priors: the reference asks its CNN (LuciFit.py:776-780); here the same two numbers
+        # per spaxel are measured on the device (engine.estimate_prior).  ML_bool=False starts at velocity =
+        # broadening = 0 like the reference, which only works for fit_function='sinc' (SURVEY fact 0.4).
+        auto_prior = (not have_prior) and bool(self.ML_bool)
+        if not have_prior and not auto_prior and fit_function != 'sinc':
+            warnings.warn('ML_bool=False and no prior_values: every fit starts from velocity = broadening = 0 like the '
+                          "reference, which only works for fit_function='sinc'")
         # priors with a trailing axis carry one value per tie group (order of first appearance in vel_rel /
         # sigma_rel): what a double-component fit needs to start its components apart
         per_group = have_prior and np.ndim(prior_values[0]) == 3
         cfg = self._make_config(lines, fit_function, vel_rel, sigma_rel, uncertainty_bool, nii_cons, spec_min,
-                                spec_max, obj_redshift, ml_scale=have_prior, prior_groups=per_group, freeze=freeze)
+                                spec_max, obj_redshift, ml_scale=have_prior or auto_prior, prior_groups=per_group,
+                                freeze=freeze)
         if per_group and (np.shape(prior_values[0])[2] != cfg.n_vel_groups or np.ndim(prior_values[1]) != 3
                           or np.shape(prior_values[1])[2] != cfg.n_sigma_groups):
             raise Exception('per-group prior_values must be (ny, nx, %d) velocities and (ny, nx, %d) broadenings'
@@ -319,6 +326,10 @@ class Luci():
             med = torch.cat([torch.nanquantile(mid[i:i + 16384], 0.5, dim=1) for i in range(0, mid.shape[0], 16384)])
             cube2d = (sky - (ab / torch.nanquantile(ab, 0.5))[None, :] * med[:, None] + med[:, None]).contiguous()
             index = None
+        if auto_prior:
+            v0, b0 = engine.estimate_prior(cfg, cube2d, theta_t, index=index, bkg=bkg_t)
+            have_prior = True
+        self.last_prior = (v0, b0)
         res = engine.fit_batch(cfg, cube2d, theta_t, v0, b0, index=index, bkg=bkg_t)
         rows = res['rows']
         L_ = len(lines)
@@ -486,12 +497,17 @@ class Luci():
         ``Fit.fit`` (``LuciFit.py:824-834``).  Shared by fit_spectrum_region / fit_pixel."""
         sky32 = spectrum.to(torch.float32).view(1, -1).contiguous()
         have_prior = prior_values is not None
+        auto_prior = (not have_prior) and bool(self.ML_bool)
         cfg = self._make_config(lines, fit_function, vel_rel, sigma_rel, uncertainty_bool, nii_cons, spec_min, spec_max,
-                                obj_redshift, ml_scale=have_prior)
+                                obj_redshift, ml_scale=have_prior or auto_prior)
         dev = sky32.device
         th = torch.tensor([theta], dtype=torch.float32, device=dev)
         v0 = torch.tensor([float(prior_values[0])], dtype=torch.float32, device=dev) if have_prior else None
         b0 = torch.tensor([float(prior_values[1])], dtype=torch.float32, device=dev) if have_prior else None
+        if auto_prior:                                          # the reference's CNN prior, measured on the device
+            v0, b0 = engine.estimate_prior(cfg, sky32, th)
+            prior_values = (float(v0[0].item()), float(b0[0].item()))
+            have_prior = True
         res = engine.fit_batch(cfg, sky32, th, v0, b0, want_sol=True, want_unc=True)
         L = len(lines)
         row = res['rows'][0].cpu().numpy()
@@ -647,8 +663,9 @@ class Luci():
             sums = sums - torch.from_numpy(np.asarray(bkg, dtype=np.float64)).to(dev)[None, :] * counts[:, None]
         theta = float(self.interferometer_theta[nx - 1, ny - 1])
         have_prior = prior_values is not None
+        auto_prior = (not have_prior) and bool(self.ML_bool)
         cfg = self._make_config(lines, fit_function, vel_rel, sigma_rel, uncertainty_bool, nii_cons, None, None, 0.0,
-                                ml_scale=have_prior)
+                                ml_scale=have_prior or auto_prior)
         th = torch.full((n_bins,), theta, dtype=torch.float32, device=dev)
         v0 = b0 = None
         if have_prior:
@@ -660,7 +677,10 @@ class Luci():
             last = np.searchsorted(keys, np.arange(n_bins), side='right')
             med = lambda a: np.array([np.median(a[order[f:l]]) if l > f else 0.0 for f, l in zip(first, last)], np.float32)
             v0, b0 = torch.from_numpy(med(pv)).to(dev), torch.from_numpy(med(pb)).to(dev)
-        res = engine.fit_batch(cfg, sums.to(torch.float32).contiguous(), th, v0, b0)
+        sums32 = sums.to(torch.float32).contiguous()
+        if auto_prior:
+            v0, b0 = engine.estimate_prior(cfg, sums32, th)
+        res = engine.fit_batch(cfg, sums32, th, v0, b0)
         self.last_fit_summary = engine.status_summary(res['status'])
         L, K = len(lines), cfg.row_floats
         # paint: pixel (x, y) of bin b gets row b; unbinned pixels stay 0

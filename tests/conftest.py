@@ -32,7 +32,7 @@ def hostemu():
     so = os.path.join(here, '_build', 'libhostemu.so')
     srcs = [os.path.join(here, 'hostemu.cpp')] + [os.path.join(ROOT, 'luci_b200', 'csrc', f) for f in
                                                     ('lucifit_core.cuh', 'lucifit_math.cuh', 'lucifit_host.hpp',
-                                                     'lucifit_instances.h')]
+                                                     'lucifit_instances.h', 'lucifit_prior.cuh')]
     if not os.path.exists(so) or any(os.path.getmtime(s) > os.path.getmtime(so) for s in srcs):
         os.makedirs(os.path.dirname(so), exist_ok=True)
         subprocess.check_call(['g++', '-O2', '-std=c++17', '-shared', '-fPIC', '-o', so, srcs[0]])
@@ -44,4 +44,6 @@ def hostemu():
     lib.hostemu_faddeeva.argtypes = [C.c_int, vp, vp, vp, vp]
     lib.hostemu_eval.argtypes = [C.POINTER(lucifit_config), vp, C.c_float, vp, vp, vp]
     lib.hostemu_eval.restype = C.c_int
+    lib.hostemu_estimate_prior.argtypes = [C.POINTER(lucifit_config), C.c_int64, vp, vp, vp, C.c_double, C.c_double, C.c_double, vp, vp]
+    lib.hostemu_estimate_prior.restype = C.c_int
     return lib

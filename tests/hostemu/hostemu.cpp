@@ -121,3 +121,18 @@ extern "C" int hostemu_eval(const lucifit_config* cfg, const float* gspec, float
     if (pl.L == 5 && pl.nv_t == 1 && cfg->model == 0) { run_eval<0, 5, 1>(pl, gspec, theta, th, chi2, hg); return 0; }
     return -2;
 }
+
+// The prior estimator (lucifit_prior.cuh) with LANES = 1.
+extern "C" int hostemu_estimate_prior(const lucifit_config* cfg, int64_t n, const float* cube, const float* theta,
+                                      const float* bkg, double v_min, double v_max, double v_step, float* vel, float* broad)
+{
+    LfPriorCfg pc;
+    std::string err = lf_make_prior_cfg(cfg, v_min, v_max, v_step, pc);
+    if (!err.empty()) { fprintf(stderr, "hostemu: %s\n", err.c_str()); return -1; }
+    pc.bkg = bkg;
+    std::vector<float> z(pc.nfit), sm(pc.nfit), score(pc.nv);
+    LfWarp<1> w;
+    for (int64_t s = 0; s < n; ++s)
+        lf_estimate_prior<1>(pc, w, cube + s * (int64_t)pc.nz, theta[s], z.data(), sm.data(), score.data(), vel + s, broad + s);
+    return 0;
+}

@@ -77,6 +77,10 @@ typedef struct lucifit_config {
                                                  vel0 / broad0 are FROZEN, only amplitudes and continuum are fitted, without
                                                  ties or boxes, continuum guess clipped at 3 sigma; sincgauss only (the
                                                  reference's gaussian / sinc freeze paths raise IndexError) */
+    int no_prior_refine;                      /* 0 (default): the prep stage moves the prior velocity to the maximum of a matched
+                                                 filter within +-36 km/s of it before the optimiser starts (fewer iterations,
+                                                 same optimum; skipped with prior_groups / freeze / several velocity groups);
+                                                 1: start exactly at vel0 */
 } lucifit_config;
 
 /* Number of floats per spaxel in out_rows: 7 L + 5, ordered

@@ -37,7 +37,7 @@ class lucifit_config(C.Structure):
         ('step_nm', C.c_double), ('n_steps', C.c_double), ('zpd_index', C.c_double),
         ('transmission', C.POINTER(C.c_double)),
         ('uncertainty', C.c_int), ('scale_mode', C.c_int), ('max_iter', C.c_int), ('ftol', C.c_double),
-        ('prior_groups', C.c_int), ('freeze', C.c_int),
+        ('prior_groups', C.c_int), ('freeze', C.c_int), ('no_prior_refine', C.c_int),
     ]
 
 
@@ -110,7 +110,8 @@ class FitConfig:
 
     def __init__(self, model_type, lines, vel_rel, sigma_rel, axis, filter='SN3', delta_x=2943, n_steps=842,
                  zpd_index=169, trans_filter=None, uncertainty_bool=False, nii_cons=True, spec_min=None,
-                 spec_max=None, obj_redshift=0.0, ml_scale=True, max_iter=0, ftol=0.0, prior_groups=False, freeze=False):
+                 spec_max=None, obj_redshift=0.0, ml_scale=True, max_iter=0, ftol=0.0, prior_groups=False, freeze=False,
+                 refine_prior=True):
         if model_type not in MODEL_CODE:
             raise Exception('Please submit a fitting function name in the available list: \n {}'.format(
                 ['gaussian', 'sinc', 'sincgauss', 'gauss']))
@@ -159,6 +160,7 @@ class FitConfig:
         c.ftol = float(ftol)
         c.prior_groups = int(bool(prior_groups))
         c.freeze = int(bool(freeze))
+        c.no_prior_refine = int(not refine_prior)
         # dense group order (first appearance), as the library numbers the tie groups
         self.n_vel_groups = len(dict.fromkeys(int(v) for v in vel_rel))
         self.n_sigma_groups = len(dict.fromkeys(int(v) for v in sigma_rel))

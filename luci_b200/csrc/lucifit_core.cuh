@@ -38,6 +38,8 @@
 #define LF_C_KMS 299792.0f        /* LuciFit.py:26 (integer km/s in the reference) */
 #define LF_MAX_CONT_WIN 256       /* samples of the continuum window handled by the clip */
 #define LF_PREP_MLP 9             /* loads in flight per lane while the prep stage reads a spectrum */
+#define LF_REFINE_HALF 6          /* prior-velocity refinement: grid of 2*6+1 points ... */
+#define LF_REFINE_STEP 6.0f        /* ... 6 km/s apart (+-36 km/s around the prior) */
 #ifndef LF_LM_LAM0
 #define LF_LM_LAM0 1e-3f
 #define LF_LM_DEC (1.0f / 3.0f)
@@ -68,6 +70,8 @@ struct LfCfg {                     // device-side constants of one lucifit_fit_b
     int freeze;                    // 1: velocity / broadening columns pinned at the priors, no ties, no boxes (LuciFit.py:688-709)
     int prior_groups;              // 1: priors are per group ([nv] velocities, [ns] broadenings per spaxel), 0: one pair
     int state_floats;              // stride of the state record
+    int refine_prior;              // 1: matched-filter refinement of the prior velocity in the prep stage
+    float ichan;                   // 1 / mean channel width of the fit window [1/cm^-1]
     float ftol;
     float p0[LF_MAX_LINES];        // 1e7/lambda_k                     [cm^-1]
     float p0_off[LF_MAX_LINES];    // 1e7/lambda_k - x_ref             [cm^-1]
@@ -761,12 +765,60 @@ LF_CORE void lf_stage_prep(const LfCfg& cfg, const LfWarp<LANES>& w, const float
         }
         th[k] = (float)((double)amp / (double)smax - cont0);
     }
+    // Start of the velocity: the prior (one value for all lines) is moved to the maximum of a matched filter within
+    // +-LF_REFINE_HALF steps of LF_REFINE_STEP km/s around it -- sum over the lines of the squared positive part of the
+    // smoothed, continuum-subtracted spectrum at the expected centres (lucifit_prior.cuh: the same score on a local
+    // grid).  A CNN-like prior is good to ~15 km/s, the filter to ~1 km/s; the optimum does not depend on the start,
+    // the number of LM iterations does.
+    float v_refined = 0.0f;
+    bool refined = false;
+    if (cfg.refine_prior && pvel && NV == 1 && !cfg.prior_groups && !cfg.freeze) {
+        float vc = pvel[0];
+        if (vc != vc) vc = 0.0f;
+        const float contr = (float)(cont0 * (double)smax);
+        float sc = -INFINITY;
+        const int iv = w.lane;
+        if (iv <= 2 * LF_REFINE_HALF || LANES == 1) {
+            for (int j = (LANES == 1 ? 0 : iv); j <= (LANES == 1 ? 2 * LF_REFINE_HALF : iv); ++j) {
+                const float vt = (vc + (float)(j - LF_REFINE_HALF) * LF_REFINE_STEP) * (1.0f / LF_C_KMS);
+                const float shift = vt / (1.0f + vt);
+                float acc = 0.0f;
+                for (int k = 0; k < L; ++k) {
+                    const float t = (cfg.p0_off[k] - cfg.p0[k] * shift) * cfg.ichan;
+                    const int i = cfg.fit_lo + (int)floorf(t);
+                    if (i < 1 || i + 2 >= nz) continue;
+                    const float f = t - floorf(t);
+                    const float a = 0.25f * spec[i - 1] + 0.5f * spec[i] + 0.25f * spec[i + 1];
+                    const float b = 0.25f * spec[i] + 0.5f * spec[i + 1] + 0.25f * spec[i + 2];
+                    const float val = fmaxf(a + f * (b - a) - contr, 0.0f);
+                    acc += val * val;
+                }
+                if (LANES == 1) wk.sortv[j] = acc; else sc = acc;
+            }
+        }
+        if (LANES != 1) { if (iv <= 2 * LF_REFINE_HALF) wk.sortv[iv] = sc; }
+        w.sync();
+        int jb = 0;
+        for (int j = 1; j <= 2 * LF_REFINE_HALF; ++j) if (wk.sortv[j] > wk.sortv[jb]) jb = j;
+        if (wk.sortv[jb] > 0.0f) {
+            float dv = (float)(jb - LF_REFINE_HALF) * LF_REFINE_STEP;
+            if (jb > 0 && jb < 2 * LF_REFINE_HALF) {
+                const float a = wk.sortv[jb - 1], b = wk.sortv[jb], d = wk.sortv[jb + 1];
+                const float den = a - 2.0f * b + d;
+                if (den < 0.0f) dv += LF_REFINE_STEP * fminf(fmaxf(0.5f * (a - d) / den, -0.5f), 0.5f);
+                v_refined = vc + dv;
+                refined = true;                                  // an interior maximum only: at the edge keep the prior
+            }
+        }
+        w.sync();
+    }
     if (w.lane == 0) {
 #pragma unroll
         for (int g = 0; g < NV; ++g) {
             float v = pvel ? pvel[(cfg.prior_groups && g < cfg.nv) ? g : 0] : 0.0f;
             th[D::IV + g] = (v != v) ? 0.0f : v;
         }
+        if (refined) th[D::IV] = v_refined;
 #pragma unroll
         for (int h = 0; h < NS; ++h) {
             float b = pbroad ? pbroad[(cfg.prior_groups && h < cfg.ns) ? h : 0] : 0.0f;

@@ -140,6 +140,7 @@ static inline std::string lf_make_plan(const lucifit_config* c, LfPlan& pl, int 
         d.i48 = d.i83 = -1;                            // no constraints in the freeze branch (LuciFit.py:699-703)
         d.ml_scale = 0;                                // scale = max(spectrum) (LuciFit.py:776-782: interpolate_spectrum is skipped)
     }
+    d.refine_prior = c->no_prior_refine ? 0 : 1;
     d.max_iter = c->max_iter > 0 ? c->max_iter : 60;
     d.ftol = c->ftol > 0 ? (float)c->ftol : 1e-8f;
     d.n_out = 7 * L + 5;
@@ -157,6 +158,7 @@ static inline std::string lf_make_plan(const lucifit_config* c, LfPlan& pl, int 
     }
     d.axis_k = 1e7 / (2.0 * c->step_nm * (c->n_steps - c->zpd_index));
     pl.nfit = c->fit_hi - c->fit_lo;
+    d.ichan = (float)((double)(pl.nfit - 1) / (pl.axis[c->fit_hi - 1] - d.x_ref));
     pl.ncont = c->cont_hi - c->cont_lo;
     pl.xo.resize(pl.nfit);
     for (int n = 0; n < pl.nfit; ++n) pl.xo[n] = (float)(pl.axis[c->fit_lo + n] - d.x_ref);

@@ -156,6 +156,10 @@ int lucifit_snr_map(const float* cube, int64_t n_spaxel, int nz, int method, int
 int lucifit_bin_cube(const float* cube, int nx, int ny, int nz, int b, int x0, int x1, int y0, int y1,
                      float* binned, void* stream);
 
+/* Cube ingest, in place: the clamp rules Luci.read_in_cube applies to every HDF5 quadrant (LuciBase.py:123-129) --
+ * non-finite samples, samples < lo (-1e-16) and samples > hi (1e-9) become `fill` (1e-22).  cube: n_values DEVICE floats. */
+int lucifit_sanitize_cube(float* cube, int64_t n_values, float lo, float hi, float fill, void* stream);
+
 /* Synthetic LuciSim-style cube written straight into HBM (benchmark input; LUCI/LuciSim.py:159-203):
  * spectrum[s][z] = flux_scale * (continuum + sum_k amp[s][k] * profile(axis[z]; centre snapped to the axis,
  * sigma from broad[s][k]) + noise_sigma[s] * noise[s][z]) where noise is caller-provided N(0,1) draws (or NULL;

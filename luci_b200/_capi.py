@@ -43,7 +43,7 @@ class lucifit_config(C.Structure):
 
 EXPORTS = ['lucifit_row_floats', 'lucifit_workspace_bytes', 'lucifit_fit_batch', 'lucifit_fit_stages', 'lucifit_deep_image',
            'lucifit_snr_map', 'lucifit_bin_cube', 'lucifit_sim_cube', 'lucifit_peak_probe', 'lucifit_estimate_prior',
-           'lucifit_last_error', 'lucifit_version']
+           'lucifit_sanitize_cube', 'lucifit_last_error', 'lucifit_version']
 
 _lib = None
 
@@ -72,6 +72,8 @@ def declare(lib):
     lib.lucifit_peak_probe.restype = C.c_int
     lib.lucifit_estimate_prior.argtypes = [cfgp, i64, vp, vp, vp, vp, C.c_double, C.c_double, C.c_double, vp, vp, vp]
     lib.lucifit_estimate_prior.restype = C.c_int
+    lib.lucifit_sanitize_cube.argtypes = [vp, i64, C.c_float, C.c_float, C.c_float, vp]
+    lib.lucifit_sanitize_cube.restype = C.c_int
     lib.lucifit_last_error.argtypes = []
     lib.lucifit_last_error.restype = C.c_char_p
     lib.lucifit_version.argtypes = []

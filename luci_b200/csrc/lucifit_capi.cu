@@ -55,6 +55,7 @@ extern "C" cudaError_t lf_run_bin(const float* cube, int ny, int nz, int b, int 
                                   float* out, int sm_count, cudaStream_t stream);
 extern "C" cudaError_t lf_run_sim(const LfSimArgs* a, int sm_count, cudaStream_t stream);
 extern "C" cudaError_t lf_run_peak(int mode, int iters, int blocks, float* out, cudaStream_t stream);
+extern "C" cudaError_t lf_run_sanitize(float* cube, long long n, float lo, float hi, float fill, int sm_count, cudaStream_t stream);
 extern "C" cudaError_t lf_run_prior(const LfPriorCfg* c, long long n, const float* cube, const long long* index,
                                     const float* theta, float* vel, float* broad, int sm_count, cudaStream_t stream);
 
@@ -251,6 +252,17 @@ int lucifit_estimate_prior(const lucifit_config* cfg, int64_t n_spaxel, const fl
     int sm = 0; int rc = sm_count_of_current_device(&sm); if (rc) return rc;
     cudaError_t e = lf_run_prior(&pc, n_spaxel, cube, (const long long*)spaxel_index, theta_deg, vel0, broad0, sm, (cudaStream_t)stream);
     if (e != cudaSuccess) return cuda_fail(e, "launch lf_prior_kernel");
+    return 0;
+}
+
+int lucifit_sanitize_cube(float* cube, int64_t n_values, float lo, float hi, float fill, void* stream)
+{
+    if (n_values < 0 || (!cube && n_values > 0)) return fail(LUCIFIT_EINVAL, "bad argument");
+    if (!(lo <= hi)) return fail(LUCIFIT_EINVAL, "lo must not exceed hi");
+    if (n_values == 0) return 0;
+    int sm = 0; int rc = sm_count_of_current_device(&sm); if (rc) return rc;
+    cudaError_t e = lf_run_sanitize(cube, n_values, lo, hi, fill, sm, (cudaStream_t)stream);
+    if (e != cudaSuccess) return cuda_fail(e, "launch lf_sanitize_kernel");
     return 0;
 }
 

@@ -588,3 +588,34 @@ extern "C" cudaError_t lf_run_sim(const LfSimArgs* a, int sm_count, cudaStream_t
     else lf_sim_kernel<2><<<grid, RED_WARPS * 32, 0, stream>>>(*a);
     return cudaGetLastError();
 }
+
+// ------------------------------------------------------------------------------------------------ cube ingest
+// Clamp rules of Luci.read_in_cube (LuciBase.py:123-129): non-finite samples, fluxes below `lo` (-1e-16) and above
+// `hi` (1e-9) are replaced by `fill` (1e-22), in place.  One 16-byte load and store per thread and step; the scalar
+// head / tail covers buffers that are not 16-byte aligned (views into a larger cube).
+__global__ void __launch_bounds__(256) lf_sanitize_kernel(float* __restrict__ cube, long long n, float lo, float hi, float fill)
+{
+    const long long head = (long long)(((16 - ((uintptr_t)cube & 15)) & 15) / 4);
+    const long long h = head < n ? head : n;
+    const long long n4 = (n - h) / 4;
+    float4* v = reinterpret_cast<float4*>(cube + h);
+    const long long stride = (long long)gridDim.x * blockDim.x, t0 = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    auto fix = [=](float x) { return (isfinite(x) && x >= lo && x <= hi) ? x : fill; };
+    for (long long i = t0; i < n4; i += stride) {
+        float4 q = v[i];
+        q.x = fix(q.x); q.y = fix(q.y); q.z = fix(q.z); q.w = fix(q.w);
+        v[i] = q;
+    }
+    if (t0 < h) cube[t0] = fix(cube[t0]);
+    const long long tail = h + 4 * n4 + t0;
+    if (tail < n) cube[tail] = fix(cube[tail]);
+}
+
+extern "C" cudaError_t lf_run_sanitize(float* cube, long long n, float lo, float hi, float fill, int sm_count, cudaStream_t stream)
+{
+    long long want = (n / 4 + 255) / 256;
+    long long cap = (long long)sm_count * 8;
+    int grid = (int)(want < cap ? want : cap); if (grid < 1) grid = 1;
+    lf_sanitize_kernel<<<grid, 256, 0, stream>>>(cube, n, lo, hi, fill);
+    return cudaGetLastError();
+}

@@ -286,6 +286,16 @@ def bin_cube(cube3d, binning, x_min, x_max, y_min, y_max):
     return out
 
 
+def sanitize_cube(cube, lo=-1e-16, hi=1e-9, fill=1e-22):
+    """In-place clamp of ``Luci.read_in_cube`` (LuciBase.py:123-129) on a contiguous float32 device tensor."""
+    lib = _capi.lib()
+    require_cuda(cube, 'cube', torch.float32)
+    with torch.cuda.device(cube.device):
+        check(lib.lucifit_sanitize_cube(_ptr(cube), cube.numel(), float(lo), float(hi), float(fill), _stream()))
+    launch_counter['n'] += 1 if cube.numel() > 0 else 0
+    return cube
+
+
 def sim_cube(cfg: FitConfig, amp, vel, broad, theta, noise_sigma=None, noise=None, continuum=0.0, flux_scale=1.0,
              out=None):
     """LuciSim-style synthetic spectra written on the device (LuciSim.py:159-203).  ``amp [n, L]``, ``vel``,

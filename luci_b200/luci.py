@@ -52,8 +52,9 @@ def spectrum_axis_func(hdr_dict, redshift):
 class Luci():
     def __init__(self, Luci_path, cube_path, output_dir, object_name, redshift, resolution, ML_bool=True, mdn=False,
                  device=None):
-        """Reference signature (``LuciBase.py:51``).  Reading the ORBS HDF5 cube needs ``h5py`` (optional here);
-        use :meth:`from_arrays` for in-memory data."""
+        """Reference signature (``LuciBase.py:51``): reads ``<cube_path>.hdf5`` (needs ``h5py``, see
+        :mod:`luci_b200.hdf5io`); use :meth:`from_arrays` for in-memory data.  The reference spectrum of the CNN
+        (``wavenumbers_syn``, ``LuciBase.py:98-99``) is not read: the CNN prior is replaced (see ``prior_values``)."""
         self._init_common(Luci_path, output_dir, object_name, redshift, resolution, ML_bool, mdn, device)
         self.cube_path = cube_path
         self.read_in_cube()
@@ -140,12 +141,24 @@ class Luci():
         return out
 
     def read_in_cube(self):
-        """``LuciBase.py:106-145`` -- needs h5py; the clamp rules of :123-129 are applied on the device."""
-        try:
-            import h5py
-        except ImportError as exc:
-            raise ImportError('h5py is not installed: build the object with Luci.from_arrays(...)') from exc
-        raise NotImplementedError('HDF5 ingest is a "next" row (SURVEY 8f-2); use Luci.from_arrays')
+        """``LuciBase.py:106-145``: HDF5 quadrants -> ``cube_final[x, y, z]`` (float32, in HBM, clamp rules of
+        :123-129 applied by one device pass), header -> ``hdr_dict`` / WCS ``header``, calibration map ->
+        ``interferometer_theta``; then the transmission curve of the filter (``:100-101``).  Needs ``h5py``."""
+        from . import hdf5io
+        if self.device is None:
+            raise RuntimeError('luci_b200 needs a CUDA device: there is no CPU path')
+        print('Reading in data...')
+        file = hdf5io.open_hdf5(self.cube_path)
+        self.cube_final = hdf5io.read_cube(file, self.device)
+        self.hdr_dict = hdf5io.header_dict(file)
+        self.header = hdf5io.wcs_header(self.hdr_dict)
+        self.interferometer_theta = hdf5io.interferometer_angles(file, self.hdr_dict)
+        self.spectrum_axis, self.spectrum_axis_unshifted = spectrum_axis_func(self.hdr_dict, self.redshift)
+        if self.hdr_dict['FILTER'] in ('C4', 'C2', 'C1'):
+            self.spectrum_axis = self.spectrum_axis_unshifted          # LuciBase.py:96-97
+        if self.Luci_path is not None:
+            self.transmission_interpolated = hdf5io.read_in_transmission(self.Luci_path, self.hdr_dict,
+                                                                         self.spectrum_axis_unshifted)
 
     # -------------------------------------------------------------------------------------------- reductions
     def create_deep_image(self, output_name=None, binning=None):

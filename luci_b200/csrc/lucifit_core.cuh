@@ -459,16 +459,25 @@ template <int N, int LANES> struct LfReduceScatter<N, 0, LANES> {
 };
 
 // Wing of the sincgauss profile (|z|^2 >= LF_W_R2_ASY, exp(-b^2) = 0): T = Re[e^{-i phi} w(z)], z = -b + i a, from the
-// three-term asymptotic series, split as w = (i/sqrt pi)/z + w2 (T2 is the w2 part); g = -exp(-a^2)/erf(a) T.
-LF_CORE void lf_wing_terms(float b, float a, float r2, float s, float c, float& T, float& T2, float& w1r, float& w1i)
+// three-term asymptotic series w = (i/sqrt pi) (1/z) (1 + 1/(2 z^2) + 3/(4 z^4)), split as w = (i/sqrt pi)/z + w2
+// (T2 is the w2 part); g = -exp(-a^2)/erf(a) T.  With 1/z = conj(z)/|z|^2 every power of 1/z is a power of conj(z)
+// times a power of inv = 1/|z|^2, so all the complex products are formed from b, a, s, c BEFORE the reciprocal is
+// needed (they overlap the MUFU latency) and only a short chain depends on it:
+//   A1 = c a - s b,  A2 = s a + c b                (e^{-i phi} conj(z): T1 = inv A1 / sqrt pi)
+//   P = conj(z)^2 = (b^2 - a^2, 2ab),  Q = P^2,    B1 = (P.A)/2,  B2 = 3 (Q.A)/4   with X.A = Xr A1 + Xi A2
+//   T2 = inv^3 (B1 + inv^2 B2) / sqrt pi,  T = inv A1 / sqrt pi + T2,  E2 = inv A2 / sqrt pi
+// E2 serves the b-derivative: (1/sqrt pi)(c Re(1/z) + s Im(1/z)) = -E2.
+LF_CORE void lf_wing_terms(float b, float a, float bb, float a2, float r2, float s, float c, float& T, float& T2, float& E2)
 {
     const float inv = LF_RCP(r2);
-    w1r = -b * inv; w1i = -a * inv;                                                    // 1/z
-    const float sr = w1r * w1r - w1i * w1i, si = 2.0f * w1r * w1i;                     // 1/z^2
-    const float fr = 0.5f * sr * (1.0f + 1.5f * sr) - 0.75f * si * si, fi = 0.5f * si + 1.5f * sr * si;
-    const float qr = w1r * fr - w1i * fi, qi = w1r * fi + w1i * fr;                    // w2 = (i/sqrt pi) q
-    T2 = LF_ISQRTPI_F * (s * qr - c * qi);
-    T = LF_ISQRTPI_F * (s * w1r - c * w1i) + T2;
+    const float A1 = c * a - s * b, A2 = s * a + c * b;
+    const float Pr = bb - a2, Pi = 2.0f * a * b;
+    const float Qr = Pr * Pr - Pi * Pi, Qi = 2.0f * Pr * Pi;
+    const float B1 = 0.5f * (Pr * A1 + Pi * A2), B2 = 0.75f * (Qr * A1 + Qi * A2);
+    const float v = inv * inv, iv = LF_ISQRTPI_F * inv;
+    T2 = (iv * v) * (B1 + v * B2);
+    T = iv * A1 + T2;
+    E2 = iv * A2;
 }
 
 // One pass over the fit window: chi2 = sum r^2, and (into dst[NA], per-warp memory) H = J^T J packed upper
@@ -520,9 +529,9 @@ LF_CORE void lf_eval(const LfCfg& cfg, const LfWarp<LANES>& w, const float* xo, 
                 if (wing) {
                     // the whole chunk is in the asymptotic region of w(z) and exp(-b^2) = 0: the wing formulas of
                     // lf_profile_sc with every per-line factor pre-multiplied (lf_fold_wing)
-                    float T, T2, w1r, w1i;
-                    lf_wing_terms(b, X.ln.a, r2, s, c, T, T2, w1r, w1i);
-                    const float Tb = (LF_2ISQRTPI_F * X.ln.a) * (c * w1r + s * w1i) - 2.0f * b * T2;
+                    float T, T2, E2;
+                    lf_wing_terms(b, X.ln.a, b * b, X.a2, r2, s, c, T, T2, E2);
+                    const float Tb = -(2.0f * X.ln.a) * E2 - 2.0f * b * T2;
                     const float U = X.c_q * T - (X.c_ia2 * r2) * T2;
                     g = X.neae * T;
                     m += X.c_m * T;
@@ -1082,8 +1091,8 @@ LF_CORE void lf_stage_out(const LfCfg& cfg, const LfWarp<LANES>& w, const float*
                 const float b = dx * X.ln.is2s;
                 const float r2 = b * b + X.a2;
                 if (w.all(b * b >= 40.0f && r2 >= LF_W_R2_ASY)) {      // whole chunk in the wing of this line
-                    float T, T2, w1r, w1i;
-                    lf_wing_terms(b, X.ln.a, r2, s, c, T, T2, w1r, w1i);
+                    float T, T2, E2;
+                    lf_wing_terms(b, X.ln.a, b * b, X.a2, r2, s, c, T, T2, E2);
                     m += X.c_m * T;
                     continue;
                 }
@@ -1276,8 +1285,8 @@ LF_CORE void lf_stage_unc(const LfCfg& cfg, const LfWarp<LANES>& w, const float*
                         const float r2 = b * b + X.a2;
                         wing = w.all(b * b >= 40.0f && r2 >= LF_W_R2_ASY);
                         if (wing) {                                 // value-only wing form (see lf_eval)
-                            float T, T2, w1r, w1i;
-                            lf_wing_terms(b, X.ln.a, r2, s, c, T, T2, w1r, w1i);
+                            float T, T2, E2;
+                            lf_wing_terms(b, X.ln.a, b * b, X.a2, r2, s, c, T, T2, E2);
                             gv = X.neae * T;
                         }
                     }

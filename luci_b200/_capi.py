@@ -113,12 +113,15 @@ class FitConfig:
     def __init__(self, model_type, lines, vel_rel, sigma_rel, axis, filter='SN3', delta_x=2943, n_steps=842,
                  zpd_index=169, trans_filter=None, uncertainty_bool=False, nii_cons=True, spec_min=None,
                  spec_max=None, obj_redshift=0.0, ml_scale=True, max_iter=0, ftol=0.0, prior_groups=False, freeze=False,
-                 refine_prior=True):
+                 refine_prior=True, extra_lines=None):
         if model_type not in MODEL_CODE:
             raise Exception('Please submit a fitting function name in the available list: \n {}'.format(
                 ['gaussian', 'sinc', 'sincgauss', 'gauss']))
-        if not set(lines).issubset(LINE_DICT):
-            raise Exception('Please submit a line name in the available list: \n {}'.format(LINE_DICT.keys()))
+        line_dict = dict(LINE_DICT)
+        if extra_lines:                       # e.g. the sky lines of Luci.skyline_calibration: {name: wavelength in nm}
+            line_dict.update(extra_lines)
+        if not set(lines).issubset(line_dict):
+            raise Exception('Please submit a line name in the available list: \n {}'.format(line_dict.keys()))
         if len(vel_rel) != len(lines):
             raise Exception("The argument vel_rel has %i arguments, but it should have %i arguments" % (
                 len(vel_rel), len(lines)))
@@ -141,7 +144,7 @@ class FitConfig:
         c.model = MODEL_CODE[model_type]
         c.n_lines = self.L
         for k, line in enumerate(lines):
-            c.line_nm[k] = LINE_DICT[line]
+            c.line_nm[k] = line_dict[line]
             c.vel_group[k] = int(vel_rel[k])
             c.sigma_group[k] = int(sigma_rel[k])
         c.nii6548_idx = c.nii6583_idx = -1

@@ -257,6 +257,7 @@ LF_CORE double lf_cont_estimate(const LfWarp<LANES>& w, const float* spec, int l
     w.sync();
     lf_sort(w, sv, npad);
     int a = 0, m = n;
+#pragma unroll 1
     for (int it = 0; it < 3 && m > 0; ++it) {
         const double med = lf_sorted_median(sv, a, m);
         int i0 = 0;

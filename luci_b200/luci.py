@@ -30,6 +30,9 @@ from .constants import LINE_DICT, snr_windows
 from .fitsio import read_fits, save_fits, write_fits
 
 
+SKYLINE_V0 = 80.0          # km/s: the reference's initial guess for the sky-line velocity (LuciFit.py:859)
+
+
 def check_luci_path(Luci_path):
     if Luci_path is not None and not Luci_path.endswith('/'):
         Luci_path += '/'
@@ -625,6 +628,73 @@ class Luci():
         if mean:
             integrated = integrated / spec_ct
         return np.asarray(self.spectrum_axis), integrated.cpu().numpy()
+
+    def skyline_calibration(self, Luci_path, n_grid, bin_size=30):
+        """``LuciBase.py:1205-1284``: velocity offset of the OH sky line(s) of ``<Luci_path>/Data/sky_lines.dat``
+        (6498.729 Angstrom) on an ``n_grid x n_grid`` set of regions, fitted with a sinc started at 80 km/s
+        (``Fit.fit(sky_line=True)``, ``LuciFit.py:837-928``).  Returns ``(velocity, fit_vector, sky, vel_grid,
+        vel_uncertainty_grid, spectrum_axis)`` like the reference (the first three belong to the last region) and
+        writes ``velocity_correction.fits``.
+
+        The reference fits the regions one after the other; here their spectra are one gathered reduction and ONE
+        ``lucifit_fit_batch`` call.  Region spectra: the reference adds ``cube_final[x_c + i, y_c + i]`` ``bin_size``
+        times for ``i < bin_size`` (its inner index ``j`` is unused, ``:1254-1256``), i.e. ``bin_size`` times the
+        diagonal of the box; ``strict_reference=False`` sums the full ``bin_size x bin_size`` box instead.  Every line
+        of the file gets its own free position like in the reference (no velocity tie, ``LuciFit.py:866``); the
+        returned velocity is that of the first line."""
+        import csv
+        with open(str(Luci_path).rstrip('/') + '/Data/sky_lines.dat') as fh:
+            rows = [r for r in csv.reader(fh) if r and not r[0].startswith('#')]
+        names = [c.strip() for c in rows[0]]
+        waves_nm = [float(r[names.index('Wavelength')]) / 10.0 for r in rows[1:]]      # Angstrom -> nm (:1229)
+        if not 1 <= len(waves_nm) <= 8:
+            raise NotImplementedError('skyline_calibration: 1 to 8 sky lines per fit are supported')
+        sky_lines = {'OH_%i' % k: w for k, w in enumerate(waves_nm)}
+        nx, ny, nz = self.cube_final.shape
+        x_min, y_min = 200, 200                                                        # :1236-1241
+        x_max, y_max = nx - x_min, ny - y_min
+        x_step, y_step = int((x_max - x_min) / n_grid), int((y_max - y_min) / n_grid)
+        dev = self.cube_final.device
+        centres = [(x_min + int(0.5 * x_step * (xg + 1)), y_min + int(0.5 * y_step * (yg + 1)))
+                   for xg in range(n_grid) for yg in range(n_grid)]
+        flat = self.cube_final.view(nx * ny, nz)
+        if self.strict_reference:
+            offs = torch.arange(bin_size, device=dev) * (ny + 1)                       # (x_c + i, y_c + i)
+            scale = float(bin_size)
+        else:
+            ii, jj = torch.meshgrid(torch.arange(bin_size, device=dev), torch.arange(bin_size, device=dev), indexing='ij')
+            offs = (ii * ny + jj).reshape(-1)
+            scale = 1.0
+        base = torch.tensor([xc * ny + yc for xc, yc in centres], dtype=torch.int64, device=dev)
+        spectra = flat[(base[:, None] + offs[None, :]).reshape(-1)].view(len(centres), offs.numel(), nz)
+        spectra = (spectra.sum(dim=1, dtype=torch.float64) * scale)
+        theta = np.array([self.interferometer_theta[xc, yc] for xc, yc in centres], dtype=np.float32)
+        L = len(waves_nm)
+        cfg = FitConfig('sinc', list(sky_lines), list(range(1, L + 1)), [1] * L, self.spectrum_axis,
+                        filter=self.hdr_dict['FILTER'], delta_x=self.hdr_dict['STEP'], n_steps=self.step_nb,
+                        zpd_index=self.zpd_index, trans_filter=self.transmission_interpolated, uncertainty_bool=True,
+                        nii_cons=False, ml_scale=False, prior_groups=L > 1, extra_lines=sky_lines)
+        n = len(centres)
+        # The reference starts every position at 80 km/s (:859) and lets SLSQP walk; the sinc objective has a local
+        # minimum per side lobe, so the start is first moved to the maximum of the matched filter within +-200 km/s of
+        # that guess (lucifit_estimate_prior) -- the same optimum, reached from inside its basin.
+        spectra32 = spectra.to(torch.float32).contiguous()
+        theta_t = torch.from_numpy(theta).to(dev)
+        v_start, _ = engine.estimate_prior(cfg, spectra32, theta_t, v_range=(SKYLINE_V0 - 200.0, SKYLINE_V0 + 200.0))
+        v0 = v_start.repeat_interleave(L).contiguous() if L > 1 else v_start
+        b0 = torch.zeros((n * L,), dtype=torch.float32, device=dev)
+        res = engine.fit_batch(cfg, spectra32, theta_t, v0, b0, want_sol=True)
+        q = engine.unpack_rows(res['rows'].cpu().numpy(), L)
+        vel_grid = q['velocities'][:, 0].astype(np.float64).reshape(n_grid, n_grid)
+        # the sky-line branch inverts the Hessian itself (LuciFit.py:873-876), the regular fit half of it (:718): its
+        # 1-sigma errors are smaller by sqrt(2)
+        vel_uncertainty_grid = (q['vels_errors'][:, 0].astype(np.float64) / np.sqrt(2.0)).reshape(n_grid, n_grid)
+        write_fits(self.output_dir + '/velocity_correction.fits', vel_grid, self.header)
+        from .host_ops import plot_vector
+        fit_vector = plot_vector(cfg, res['fit_sol'][-1].cpu().numpy().astype(np.float64), float(theta[-1]), dev)
+        self.last_fit_summary = engine.status_summary(res['status'])
+        return (float(vel_grid[-1, -1]), fit_vector, spectra[-1].cpu().numpy(), vel_grid, vel_uncertainty_grid,
+                np.asarray(self.spectrum_axis))
 
     def fit_wvt(self, lines, fit_function, vel_rel, sigma_rel, bkg=None, bayes_bool=False, uncertainty_bool=False,
                 n_threads=1, initial_values=[False], n_stoch=1, stn_target=10, bin_map=None, prior_values=None,

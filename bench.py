@@ -367,6 +367,22 @@ def main():
     except Exception as exc:                                     # reported, never fatal for the headline number
         line['auto_prior'] = {'error': repr(exc)}
 
+    # --- second row of SURVEY 8(d): the same cube with uncertainty_bool=True (adds the FD-stencil Hessian stage)
+    if not args.uncertainty:
+        try:
+            cfg_u = FitConfig(model, LINES, [1] * 5, [1] * 5, sc.axis32, 'SN3', sc.delta_x, sc.n_steps, 0,
+                              uncertainty_bool=True, nii_cons=True)
+            engine.fit_batch(cfg_u, cube, theta, v0, b0)
+            barrier()
+            st_u = engine.fit_batch(cfg_u, cube, theta, v0, b0, time_stages=True)['stage_ms']
+            tot_u = ldist.max_over_ranks(float(sum(st_u.values())), dev)
+            line['with_uncertainties'] = {'ms_per_step': tot_u, 'spaxels_per_s': n_total / (tot_u * 1e-3),
+                                          'stage_ms': {k: float(v) for k, v in st_u.items()},
+                                          'note': 'uncertainty_bool=True: lf_unc_kernel added (LuciFit.py:713-722, LuciUtility.py:409-434); '
+                                                  'sum of the stage kernels timed with CUDA events, no gather'}
+        except Exception as exc:
+            line['with_uncertainties'] = {'error': repr(exc)}
+
     # --- reductions (config 5): deep image + SNR map over the same cube, HBM-bound
     if not args.no_reductions:
         red = {}

@@ -292,9 +292,7 @@ def main():
     mean_E = sum_evals / max(n_fit_total, 1)
     nfit = cfg.c.fit_hi - cfg.c.fit_lo
     L, P_red = 5, 7                                                # 4 free amplitudes + v + beta + continuum
-    W = mean_E * nfit * (L * F_MODEL[model] + P_red * (P_red + 3)) + mean_E * P_red ** 3 / 3.0
-    if unc:
-        W += 24 * L * nfit * (F_MODEL[model] / 2.0) + (3 * L + 1) ** 3
+    W = mean_E * nfit * (L * F_MODEL[model] + P_red * (P_red + 3)) + mean_E * P_red ** 3 / 3.0      # lf_lm_kernel only
     # the dominant kernel (lf_lm_kernel) timed alone: the same pipeline stage by stage with CUDA events around every
     # launch on the launching stream (engine.fit_batch(time_stages=True) -> lucifit_fit_stages)
     barrier()

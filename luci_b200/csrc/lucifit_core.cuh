@@ -97,6 +97,7 @@ template <> struct LfWarp<1> {
     int sum(int v) const { return v; }
     bool all(bool p) const { return p; }
     bool any(bool p) const { return p; }
+    int first_true(bool p) const { return p ? 0 : -1; }      // lowest lane whose predicate holds, -1 if none
     float xchg(float v, int) const { return v; }
     void argmin(double& v, int& i) const {}
     void sync() const {}
@@ -124,6 +125,7 @@ template <> struct LfWarp<32> {
     }
     __device__ bool all(bool p) const { return __all_sync(0xffffffffu, p); }
     __device__ bool any(bool p) const { return __any_sync(0xffffffffu, p); }
+    __device__ int first_true(bool p) const { return __ffs((int)__ballot_sync(0xffffffffu, p)) - 1; }
     __device__ float xchg(float v, int o) const { return __shfl_xor_sync(0xffffffffu, v, o); }
     __device__ void argmin(double& v, int& i) const {   // smallest v, ties -> smallest index (np.argmin)
 #pragma unroll
@@ -1204,7 +1206,10 @@ LF_CORE void lf_stage_unc(const LfCfg& cfg, const LfWarp<LANES>& w, const float*
     const float* th = state + LF_SO_TH;
     const float dl = 0.1f;
     const int nfit = cfg.fit_hi - cfg.fit_lo;
-    lf_stage_window<MODEL, LANES>(cfg, w, xo, gspec, state[LF_SO_INVW], false, sinc_w_d, wk);
+    // The sample loop below visits every chunk of the window ONCE, so the data and the phase of a chunk are formed when
+    // the chunk is reached (the next chunk's data are requested one chunk ahead) instead of being staged for the whole
+    // window: 3 nfit floats of per-warp shared memory less, which is what limits the resident warps of this stage.
+    const float invw_norm = state[LF_SO_INVW];
     double* apd = wk.apd;
     lf_expand<MODEL, L, NV, NS, LANES>(cfg, w, sinc_w, th, apd);
     // line set-ups of all variants, built lane-parallel
@@ -1240,13 +1245,24 @@ LF_CORE void lf_stage_unc(const LfCfg& cfg, const LfWarp<LANES>& w, const float*
     for (int e = 0; e < 5 * L; ++e) sums[e * LANES + w.lane] = 0.0f;
     float* tile = wk.tile;
     float* gvt = wk.gt;                                // [13][LANES]
+    float y_ahead = 0.0f;
+    if (w.lane < nfit) {
+        const int i = cfg.fit_lo + w.lane;
+        y_ahead = gspec[i];
+        if (cfg.bkg) y_ahead -= cfg.bkg[i];
+    }
     for (int n0 = 0; n0 < nfit; n0 += LANES) {
         const int n = n0 + w.lane;
         const bool live = n < nfit;
         const float x = live ? xo[n] : 0.0f;
-        const float yn = live ? wk.yw[n] : 0.0f;
+        const float yn = live ? y_ahead * invw_norm : 0.0f;
+        if (n + LANES < nfit) {
+            const int i = cfg.fit_lo + n + LANES;
+            y_ahead = gspec[i];
+            if (cfg.bkg) y_ahead -= cfg.bkg[i];
+        }
         float Sx = 0.0f, Cx = 1.0f;
-        if (MODEL != LF_GAUSSIAN && live) { Sx = wk.sw[n]; Cx = wk.cw[n]; }
+        if (MODEL != LF_GAUSSIAN && live) lf_phase((double)x * inv_w, Sx, Cx);
         float* trow = tile + w.lane * STRIDE;
         // pass 1: model value at the solution (residual r0) and the unit profiles g0
         float m = cont;

@@ -23,7 +23,13 @@
 template <int NA> struct LfLmBlocks {
     enum { W = NA <= 44 ? LF_LM_WARPS_SMALL : NA <= 77 ? 12 : 8, V = NA <= 44 ? LF_LM_MINB_SMALL : 1 };
 };
-#define LF_UNC_WARPS 4
+// The uncertainty kernel is bound by its per-warp shared memory (13 L variant records, the variant / sum tiles):
+// one CTA per SM with as many warps as fit 227 KB -- 16 up to 6 lines, 12 beyond (96.2 / 91.9 / 89.6 / 91.3 ms per 2^20
+// spaxels with 4 / 8 / 16 / 18 warps per CTA for the 5-line sincgauss).
+#ifndef LF_UNC_WARPS
+#define LF_UNC_WARPS 16
+#endif
+template <int L> struct LfUncWarps { enum { W = L <= 6 ? LF_UNC_WARPS : (LF_UNC_WARPS < 12 ? LF_UNC_WARPS : 12) }; };
 #ifndef LF_OUT_WARPS
 #define LF_OUT_WARPS 8
 #endif
@@ -96,16 +102,17 @@ lf_lm_kernel(const __grid_constant__ LfLaunch a)
 }
 
 template <int MODEL, int L, int NG>
-__global__ void __launch_bounds__(LF_UNC_WARPS * 32)
+__global__ void __launch_bounds__(LfUncWarps<L>::W * 32, 1)
 lf_unc_kernel(const __grid_constant__ LfLaunch a)
 {
     extern __shared__ __align__(16) unsigned char lf_smem[];
+    constexpr int WARPS = LfUncWarps<L>::W;
     const float* xo_s = lf_stage_xo(a, lf_smem);
     const int warp = threadIdx.x >> 5;
     LfWork wk = lf_work_at(LF_STAGE_UNC, a.ly, lf_smem + a.xo_bytes + (size_t)warp * a.ly.un_bytes);
     LfWarp<32> w;
-    const long long stride = (long long)gridDim.x * LF_UNC_WARPS;
-    for (long long s = (long long)blockIdx.x * LF_UNC_WARPS + warp; s < a.n; s += stride) {
+    const long long stride = (long long)gridDim.x * WARPS;
+    for (long long s = (long long)blockIdx.x * WARPS + warp; s < a.n; s += stride) {
         const long long row = a.index ? a.index[s] : a.index_base + s;
         lf_stage_unc<MODEL, L, NG, NG, 32>(a.cfg, w, xo_s, a.cube + row * (long long)a.cfg.nz, wk,
                                            a.state + s * (long long)a.cfg.state_floats, a.unc_ws + s * (3 * L + 1));
@@ -165,7 +172,7 @@ cudaError_t lf_launch(const LfLaunch& a, int stages)
         if (e != cudaSuccess) return e;
     }
     if ((stages & 4) && a.unc_ws) {
-        e = lf_launch_one(lf_unc_kernel<MODEL, L, NG>, a, LF_UNC_WARPS, (size_t)a.xo_bytes + (size_t)LF_UNC_WARPS * a.ly.un_bytes);
+        e = lf_launch_one(lf_unc_kernel<MODEL, L, NG>, a, LfUncWarps<L>::W, (size_t)a.xo_bytes + (size_t)LfUncWarps<L>::W * a.ly.un_bytes);
         if (e != cudaSuccess) return e;
     }
     if (stages & 8)

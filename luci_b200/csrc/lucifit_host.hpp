@@ -78,10 +78,10 @@ static inline void lf_make_layout(int L, int P, int nz, int nfit, int ncont, int
     ly.lm_hb = (int)o; o = lf_align(o + sizeof(float) * 2 * NA, 16);
     ly.lm_thb = (int)o; o = lf_align(o + sizeof(float) * 4 * P, 16);
     ly.lm_bytes = (int)o;
-    // unc: yw | sw | cw | variants[13 L] (later: hess) | apd[3 L] | gt[(13 + 5 L)][lanes] | tile[lanes][PF|1]
-    o = win;
-    ly.un_sw = (int)o; o += win;
-    ly.un_cw = (int)o; o += win;
+    // unc: variants[13 L] (later: hess) | apd[3 L] | gt[(13 + 5 L)][lanes] | tile[lanes][PF|1]   (no staged window:
+    // the stage forms data and phase chunk by chunk)
+    o = 0;
+    ly.un_sw = 0; ly.un_cw = 0;
     {   // the float64 Hessian is assembled after the sample loop, when the variant records are dead: same bytes
         size_t rec = sizeof(LfLineV) * 13 * L, hess = sizeof(double) * (PF * PF + 2 * PF);
         ly.un_lines = (int)o; ly.un_hess = (int)o; o = lf_align(o + (rec > hess ? rec : hess), 16);

@@ -117,35 +117,47 @@ LF_CORE void lf_estimate_prior(const LfPriorCfg& c, const LfWarp<LANES>& w, cons
         const float den = a - 2.0f * b + d;
         if (den < 0.0f) v += c.v_step * fminf(fmaxf(0.5f * (a - d) / den, -0.5f), 0.5f);
     }
-    // ---- broadening: FWHM of the strongest line at that velocity (lane 0; a few dozen samples)
-    if (w.lane == 0) {
-        const float vt = v * (1.0f / LF_C_KMS);
-        const float shift = vt / (1.0f + vt);
-        float amp = 0.0f, pk = c.p0[0];
-        int ipk = -1;
-        for (int k = 0; k < c.L; ++k) {
-            const float t = (c.p0_off[k] - c.p0[k] * shift) * ichan;
-            const int i0 = (int)floorf(t + 0.5f);
-            for (int i = i0 - 2; i <= i0 + 2; ++i)
-                if (i >= 0 && i < nfit && z[i] > amp) { amp = z[i]; ipk = i; pk = c.p0[k] * (1.0f - shift); }
-        }
-        float broad = 0.0f;
-        if (ipk >= 0 && amp > 0.0f) {
-            const float half = 0.5f * amp;
-            float xl = (float)ipk - 0.5f, xr = (float)ipk + 0.5f;
-            for (int j = ipk - 1; j >= 0 && ipk - j <= 48; --j)
-                if (z[j] <= half) { xl = (float)j + (half - z[j]) / (z[j + 1] - z[j]); break; }
-            for (int j = ipk + 1; j < nfit && j - ipk <= 48; ++j)
-                if (z[j] <= half) { xr = (float)j - (half - z[j]) / (z[j - 1] - z[j]); break; }
-            const float fwhm = (xr - xl) * c.chan;
-            const float ct = fabsf(cosf(theta_deg * 0.017453292519943295f));
-            const float fs = (c.model == LF_GAUSSIAN) ? 0.0f : 1.20671f * (float)c.axis_k / fmaxf(ct, 1e-3f);
-            const float fg2 = fmaxf(fwhm * fwhm - fs * fs, 0.09f * fwhm * fwhm);
-            const float sig = sqrtf(fg2) * (1.0f / 2.3548200450309493f);
-            broad = fminf(fmaxf(LF_C_KMS * sig / pk, 1.0f), 1000.0f);
-        }
-        *vel_out = v;
-        *broad_out = broad;
+    // ---- broadening: FWHM of the strongest line at that velocity.  Peak: the largest of the +-2 samples around
+    // every expected centre (one candidate per lane); half-maximum crossings: the first sample at or below half the
+    // peak on either side (one sample per lane and round, lowest lane wins), linearly interpolated.
+    const float vt = v * (1.0f / LF_C_KMS);
+    const float shift = vt / (1.0f + vt);
+    double amp_d = 0.0;                                            // argmin over (-value, candidate index)
+    int cand = -1;
+    for (int q = w.lane; q < 5 * c.L; q += LANES) {
+        const int k = q / 5;
+        const float t = (c.p0_off[k] - c.p0[k] * shift) * ichan;
+        const int i = (int)floorf(t + 0.5f) + (q - 5 * k) - 2;
+        if (i >= 0 && i < nfit && z[i] > 0.0f && (double)z[i] > amp_d) { amp_d = (double)z[i]; cand = q; }
     }
+    { double neg = cand >= 0 ? -amp_d : 1.0; int idx = cand >= 0 ? cand : 0x7fffffff; w.argmin(neg, idx); amp_d = -neg; cand = neg < 0.0 ? idx : -1; }
+    float broad = 0.0f;
+    if (cand >= 0) {                                               // warp-uniform from here on
+        const int k = cand / 5;
+        const float t = (c.p0_off[k] - c.p0[k] * shift) * ichan;
+        const int ipk = (int)floorf(t + 0.5f) + (cand - 5 * k) - 2;
+        const float amp = (float)amp_d, half = 0.5f * amp;
+        const float pk = c.p0[k] * (1.0f - shift);
+        float xl = (float)ipk - 0.5f, xr = (float)ipk + 0.5f;
+        for (int j0 = 1; j0 <= 48; j0 += LANES) {                  // left side: samples ipk - j0 - lane
+            const int jj = ipk - j0 - w.lane;
+            const int hit = w.first_true(jj >= 0 && jj >= ipk - 48 && z[jj] <= half);
+            if (hit >= 0) { const int jl = ipk - j0 - hit; xl = (float)jl + (half - z[jl]) / (z[jl + 1] - z[jl]); break; }
+            if (ipk - j0 - LANES < 0) break;
+        }
+        for (int j0 = 1; j0 <= 48; j0 += LANES) {                  // right side: samples ipk + j0 + lane
+            const int jj = ipk + j0 + w.lane;
+            const int hit = w.first_true(jj < nfit && jj <= ipk + 48 && z[jj] <= half);
+            if (hit >= 0) { const int jr = ipk + j0 + hit; xr = (float)jr - (half - z[jr]) / (z[jr - 1] - z[jr]); break; }
+            if (ipk + j0 + LANES >= nfit) break;
+        }
+        const float fwhm = (xr - xl) * c.chan;
+        const float ct = fabsf(cosf(theta_deg * 0.017453292519943295f));
+        const float fs = (c.model == LF_GAUSSIAN) ? 0.0f : 1.20671f * (float)c.axis_k / fmaxf(ct, 1e-3f);
+        const float fg2 = fmaxf(fwhm * fwhm - fs * fs, 0.09f * fwhm * fwhm);
+        const float sig = sqrtf(fg2) * (1.0f / 2.3548200450309493f);
+        broad = fminf(fmaxf(LF_C_KMS * sig / pk, 1.0f), 1000.0f);
+    }
+    if (w.lane == 0) { *vel_out = v; *broad_out = broad; }
     w.sync();
 }

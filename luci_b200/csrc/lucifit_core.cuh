@@ -1286,6 +1286,31 @@ LF_CORE void lf_stage_unc(const LfCfg& cfg, const LfWarp<LANES>& w, const float*
             const float Ak = lines[13 * k].aeff;
             const float g0 = trow[3 * k];
             gvt[w.lane] = g0;
+            // The 12 shifted variants of a line differ by at most 2 delta in centre and width, so one conservative test
+            // (closest centre, widest / narrowest width) tells whether ALL of them are in the wing for this chunk.  Then
+            // they run through straight-line code without a vote or a branch per variant, which lets the scheduler
+            // overlap the dependent chains of neighbouring variants.
+            bool wing_all = false;
+            if (MODEL == LF_SINCGAUSS) {
+                const LfLine& B = lines[13 * k].ln;
+                const float adx = fmaxf(fabsf(lf_dx(B, x)) - 2.0f * dl, 0.0f);
+                const float bmin = adx * LF_RCP(LF_SQRT2_F * (B.sig + 2.0f * dl));
+                const float smin = fmaxf(B.sig - 2.0f * dl, 0.02f * sinc_w * (LF_SQRT2_F / LF_PI_F));
+                const float amin = smin * (LF_PI_F / LF_SQRT2_F) * iw;
+                wing_all = w.all(!live || (bmin * bmin >= 40.0f && bmin * bmin + amin * amin >= LF_W_R2_ASY));
+            }
+            if (wing_all) {
+#pragma unroll 4
+                for (int v = 1; v < 13; ++v) {
+                    const LfLineV& X = lines[13 * k + v];
+                    const float dx = lf_dx(X.ln, x);
+                    const float s = Sx * X.ck - Cx * X.sk, c = Cx * X.ck + Sx * X.sk;
+                    const float b = dx * X.ln.is2s;
+                    float T, T2, E2;
+                    lf_wing_terms(b, X.ln.a, b * b, X.a2, b * b + X.a2, s, c, T, T2, E2);
+                    gvt[v * LANES + w.lane] = X.neae * T;
+                }
+            } else
 #pragma unroll 1
             for (int v = 1; v < 13; ++v) {
                 float gv;

@@ -331,3 +331,31 @@ def test_extract_spectrum_and_region(world):
     mask[1:4, 2:9] = True
     _, specr = luci.extract_spectrum_region(mask, mean=True)
     np.testing.assert_allclose(specr, host[1:4, 2:9].sum(axis=(0, 1)) / 21, rtol=1e-12)
+
+
+@pytest.mark.parametrize('filt,lines', [('SN2', ['Hbeta', 'OIII4959', 'OIII5007']), ('SN1', ['OII3726', 'OII3729'])])
+def test_config3_sn1_sn2_gaussian_binning2(tmp_path, filt, lines):
+    """BASELINE config 3: SN1 / SN2 cubes, gaussian model, binning=2 -- through fit_entire_cube with the CNN-like priors
+    of the simulation and with the priors measured on the device (ML_bool=True, no prior_values)."""
+    from luci_b200.luci import Luci
+    from luci_b200.sim import SyntheticCube
+    dev = torch.device('cuda', 0)
+    L = len(lines)
+    sc = SyntheticCube(12, 8, lines=lines, model='gaussian', filter_=filt, resolution=5000, seed=21,
+                       broad_range=(60.0, 100.0), snr_range=(20.0, 100.0))
+    cube = sc.synthesize(dev)
+    # bins of 2 x 2 identical-velocity spaxels keep the binned truth simple: copy every even spaxel onto its bin
+    cube = cube[0::2, 0::2].repeat_interleave(2, dim=0).repeat_interleave(2, dim=1).contiguous()
+    luci = Luci.from_arrays(cube, sc.hdr_dict, str(tmp_path), 'C3', spectrum_axis=sc.axis32, device=dev)
+    v0, b0 = sc.priors()
+    vb, bb = v0[0::2, 0::2], b0[0::2, 0::2]
+    vel, broad, flux, ampl = luci.fit_entire_cube(lines, 'gaussian', [1] * L, [1] * L, binning=2, prior_values=(vb, bb))
+    assert vel.shape == (4, 6, L) and luci.last_fit_summary['n_converged'] == 24
+    truth = sc.vel_fit_truth[0::2, 0::2].T
+    chan_kms = 299792.0 * float(sc.axis32[1] - sc.axis32[0]) / float(sc.axis32[len(sc.axis32) // 2])
+    assert np.median(np.abs(vel[:, :, 0] - truth)) < 0.6 * chan_kms          # LuciSim snaps lines to channels
+    assert 3.0 < np.median(ampl[:, :, 0]) / 1e-17 < 5.0                      # nansum of 4 spaxels, no division
+    vel_a, broad_a, flux_a, _ = luci.fit_entire_cube(lines, 'gaussian', [1] * L, [1] * L, binning=2)
+    same = (np.abs(vel_a - vel).max(axis=2) < 0.1) & (np.abs(flux_a / flux - 1).max(axis=2) < 5e-3)
+    assert same.mean() >= 0.9, (same.mean(), np.abs(vel_a - vel).max())
+    assert os.path.exists(os.path.join(str(tmp_path), 'Luci_outputs', 'Velocity', 'C3_2_gaussian_%s_velocity.fits' % lines[0]))

@@ -40,6 +40,7 @@
 #define LF_PREP_MLP 9             /* loads in flight per lane while the prep stage reads a spectrum */
 #define LF_REFINE_HALF 6          /* prior-velocity refinement: grid of 2*6+1 points ... */
 #define LF_REFINE_STEP 6.0f        /* ... 6 km/s apart (+-36 km/s around the prior) */
+static_assert(2 * LF_REFINE_HALF + 1 <= 16, "the refinement scores live in the sort scratch (npad >= 16, lf_make_layout)");
 #ifndef LF_LM_LAM0
 #define LF_LM_LAM0 1e-3f
 #define LF_LM_DEC (1.0f / 3.0f)

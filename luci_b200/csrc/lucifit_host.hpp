@@ -58,7 +58,7 @@ static inline void lf_make_layout(int L, int P, int nz, int nfit, int ncont, int
 {
     const size_t NA = (size_t)P * (P + 1) / 2 + P, PF = 3 * (size_t)L + 1;
     int cap = ncont > LF_MAX_CONT_WIN ? LF_MAX_CONT_WIN : ncont;
-    int npad = 2;
+    int npad = 16;                             // >= 2 LF_REFINE_HALF + 1: the prep stage also keeps its refinement scores here
     while (npad < cap) npad <<= 1;
     ly.lanes = lanes;
     ly.npad = npad;

@@ -359,3 +359,24 @@ def test_config3_sn1_sn2_gaussian_binning2(tmp_path, filt, lines):
     same = (np.abs(vel_a - vel).max(axis=2) < 0.1) & (np.abs(flux_a / flux - 1).max(axis=2) < 5e-3)
     assert same.mean() >= 0.9, (same.mean(), np.abs(vel_a - vel).max())
     assert os.path.exists(os.path.join(str(tmp_path), 'Luci_outputs', 'Velocity', 'C3_2_gaussian_%s_velocity.fits' % lines[0]))
+
+
+def test_low_resolution_cube_with_a_three_sample_continuum_window(tmp_path):
+    """R = 1000 SN2 (nz = 186, the resolution of the reference's own SN1/SN2 example cubes): the continuum window holds 3
+    samples and the fit window 77; every scratch area must still be large enough and the fits finite."""
+    from luci_b200.luci import Luci
+    from luci_b200.sim import SyntheticCube
+    dev = torch.device('cuda', 0)
+    lines = ['Hbeta', 'OIII4959', 'OIII5007']
+    sc = SyntheticCube(6, 5, lines=lines, model='gaussian', filter_='SN2', resolution=1000, seed=4,
+                       broad_range=(250.0, 350.0), snr_range=(30.0, 100.0))
+    assert sc.nz < 200
+    luci = Luci.from_arrays(sc.synthesize(dev), sc.hdr_dict, str(tmp_path), 'LOWR', spectrum_axis=sc.axis32, device=dev)
+    v0, b0 = sc.priors()
+    for kw in (dict(prior_values=(v0, b0)), dict()):
+        vel, broad, flux, ampl = luci.fit_cube(lines, 'gaussian', [1] * 3, [1] * 3, 0, 6, 0, 5, uncertainty_bool=True, **kw)
+        assert np.isfinite(vel).all() and np.isfinite(flux).all() and (broad >= 0).all()
+        assert luci.last_fit_summary['n_fitted'] == 30
+    luci.create_deep_image()
+    masks = luci.create_snr_map(0, 6, 0, 5, method=1)
+    assert len(masks) == 4 and np.isfinite(luci.snr_map).all()

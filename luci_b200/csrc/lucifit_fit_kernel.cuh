@@ -12,6 +12,9 @@
 #ifndef LF_PREP_WARPS
 #define LF_PREP_WARPS 16
 #endif
+#ifndef LF_PREP_LOCKSTEP
+#define LF_PREP_LOCKSTEP 1
+#endif
 // The LM kernel keeps ONE resident CTA per SM and sizes it by the normal equations: up to 8 unknowns (44 accumulators)
 // fit the 128 registers that 16 warps leave per thread; larger systems get 12 or 8 warps and the registers they need.
 #ifndef LF_LM_WARPS_SMALL
@@ -74,7 +77,16 @@ lf_prep_kernel(const __grid_constant__ LfLaunch a)
     LfWork wk = lf_work_at(LF_STAGE_PREP, a.ly, lf_smem + (size_t)warp * a.ly.prep_bytes);
     LfWarp<32> w;
     const long long stride = (long long)gridDim.x * LF_PREP_WARPS;
-    for (long long s = (long long)blockIdx.x * LF_PREP_WARPS + warp; s < a.n; s += stride) {
+    // The stage is ~60 KB of straight-line code walked once per spaxel, with near-identical work for every spaxel: the
+    // warps of a CTA start each spaxel together (one CTA barrier per round, uniform trip count) so that they fetch the
+    // same instructions at about the same time instead of thrashing the instruction cache (ncu: 1.9 `no_instruction`
+    // stall cycles per issued instruction without the barrier).
+    for (long long s0 = (long long)blockIdx.x * LF_PREP_WARPS; s0 < a.n; s0 += stride) {
+#if LF_PREP_LOCKSTEP
+        __syncthreads();
+#endif
+        const long long s = s0 + warp;
+        if (s >= a.n) continue;
         const long long row = a.index ? a.index[s] : a.index_base + s;
         const int pnv = a.cfg.prior_groups ? a.cfg.nv : 1, pns = a.cfg.prior_groups ? a.cfg.ns : 1;
         lf_stage_prep<MODEL, L, NG, NG, 32>(a.cfg, w, a.cube + row * (long long)a.cfg.nz, a.theta[s],

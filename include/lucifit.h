@@ -78,8 +78,9 @@ typedef struct lucifit_config {
                                                  ties or boxes, continuum guess clipped at 3 sigma; sincgauss only (the
                                                  reference's gaussian / sinc freeze paths raise IndexError) */
     int no_prior_refine;                      /* 0 (default): the prep stage moves the prior velocity to the maximum of a matched
-                                                 filter within +-36 km/s of it before the optimiser starts (fewer iterations,
-                                                 same optimum; skipped with prior_groups / freeze / several velocity groups);
+                                                 filter within +-36 km/s of it (the grid follows a maximum on its edge, up to +-108 km/s)
+                                                 before the optimiser starts (fewer iterations, same optimum; skipped with
+                                                 prior_groups / freeze / several velocity groups);
                                                  1: start exactly at vel0 */
 } lucifit_config;
 

@@ -40,6 +40,7 @@
 #define LF_PREP_MLP 9             /* loads in flight per lane while the prep stage reads a spectrum */
 #define LF_REFINE_HALF 6          /* prior-velocity refinement: grid of 2*6+1 points ... */
 #define LF_REFINE_STEP 6.0f        /* ... 6 km/s apart (+-36 km/s around the prior) */
+#define LF_REFINE_ROUNDS 3         /* the grid follows a maximum on its edge: up to 3 grids */
 static_assert(2 * LF_REFINE_HALF + 1 <= 16, "the refinement scores live in the sort scratch (npad >= 16, lf_make_layout)");
 #ifndef LF_LM_LAM0
 #define LF_LM_LAM0 1e-3f
@@ -785,14 +786,16 @@ LF_CORE void lf_stage_prep(const LfCfg& cfg, const LfWarp<LANES>& w, const float
     // the number of LM iterations does.
     float v_refined = 0.0f;
     bool refined = false;
-    if (cfg.refine_prior && pvel && NV == 1 && !cfg.prior_groups && !cfg.freeze) {
-        float vc = pvel[0];
+    if (cfg.refine_prior && NV == 1 && !cfg.prior_groups && !cfg.freeze) {
+        float vc = pvel ? pvel[0] : 0.0f;                            // no prior: the reference starts at 0 (LuciFit.py:155)
         if (vc != vc) vc = 0.0f;
         const float contr = (float)(cont0 * (double)smax);
-        float sc = -INFINITY;
-        const int iv = w.lane;
-        if (iv <= 2 * LF_REFINE_HALF || LANES == 1) {
-            for (int j = (LANES == 1 ? 0 : iv); j <= (LANES == 1 ? 2 * LF_REFINE_HALF : iv); ++j) {
+        // a maximum on the edge of the grid means the prior is further off than the grid reaches: the grid is moved
+        // there and the search repeated (at most LF_REFINE_ROUNDS grids, +-108 km/s in all)
+#pragma unroll 1
+        for (int round = 0; round < LF_REFINE_ROUNDS && !refined; ++round) {
+            w.sync();
+            for (int j = w.lane; j <= 2 * LF_REFINE_HALF; j += LANES) {
                 const float vt = (vc + (float)(j - LF_REFINE_HALF) * LF_REFINE_STEP) * (1.0f / LF_C_KMS);
                 const float shift = vt / (1.0f + vt);
                 float acc = 0.0f;
@@ -806,21 +809,21 @@ LF_CORE void lf_stage_prep(const LfCfg& cfg, const LfWarp<LANES>& w, const float
                     const float val = fmaxf(a + f * (b - a) - contr, 0.0f);
                     acc += val * val;
                 }
-                if (LANES == 1) wk.sortv[j] = acc; else sc = acc;
+                wk.sortv[j] = acc;
             }
-        }
-        if (LANES != 1) { if (iv <= 2 * LF_REFINE_HALF) wk.sortv[iv] = sc; }
-        w.sync();
-        int jb = 0;
-        for (int j = 1; j <= 2 * LF_REFINE_HALF; ++j) if (wk.sortv[j] > wk.sortv[jb]) jb = j;
-        if (wk.sortv[jb] > 0.0f) {
-            float dv = (float)(jb - LF_REFINE_HALF) * LF_REFINE_STEP;
+            w.sync();
+            int jb = 0;
+            for (int j = 1; j <= 2 * LF_REFINE_HALF; ++j) if (wk.sortv[j] > wk.sortv[jb]) jb = j;
+            if (!(wk.sortv[jb] > 0.0f)) break;                       // nothing above the continuum: keep the prior
             if (jb > 0 && jb < 2 * LF_REFINE_HALF) {
+                float dv = (float)(jb - LF_REFINE_HALF) * LF_REFINE_STEP;
                 const float a = wk.sortv[jb - 1], b = wk.sortv[jb], d = wk.sortv[jb + 1];
                 const float den = a - 2.0f * b + d;
                 if (den < 0.0f) dv += LF_REFINE_STEP * fminf(fmaxf(0.5f * (a - d) / den, -0.5f), 0.5f);
                 v_refined = vc + dv;
-                refined = true;                                  // an interior maximum only: at the edge keep the prior
+                refined = true;
+            } else {
+                vc += (float)(jb - LF_REFINE_HALF) * LF_REFINE_STEP;
             }
         }
         w.sync();

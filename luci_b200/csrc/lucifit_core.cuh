@@ -51,6 +51,8 @@ static_assert(2 * LF_REFINE_HALF + 1 <= 16, "the refinement scores live in the s
 #define LF_TUNE_SLACK_PRED 1e-4   /* below this predicted relative decrease an FP32-noise-sized rise of sum r^2 is accepted */
 #define LF_TUNE_SLACK 4e-6        /* ... of at most this relative size */
 #define LF_TUNE_REJ_CONV 1e-5     /* a rejected step predicted to gain less than this means converged */
+#define LF_CONV_CONTRACTION 0.05f /* fast contraction: the predicted gain of a step is at most this fraction of the previous step's */
+#define LF_CONV_PRED_CAP 1e-5     /* ... and itself below this fraction of sum r^2: only then is the next gain extrapolated */
 
 // status word: bits 0-7 accepted LM iterations, bits 8-15 model evaluations, bits 16.. flags
 enum {
@@ -898,7 +900,7 @@ LF_CORE void lf_stage_lm(const LfCfg& cfg, const LfWarp<LANES>& w, const float* 
     }
     w.sync();
     int evals = 0, iters = 0, flags = 0, tries = 0;
-    float lam = LF_LM_LAM0, nu = 2.0f, pred = 0.0f;
+    float lam = LF_LM_LAM0, nu = 2.0f, pred = 0.0f, pred_prev = 0.0f;
     double chi2 = 0.0;
     const double ftol = (double)cfg.ftol;
     bool first = true, done = false;
@@ -977,8 +979,16 @@ LF_CORE void lf_stage_lm(const LfCfg& cfg, const LfWarp<LANES>& w, const float* 
             for (int j = 0; j < P; ++j) if (w.lane == (j % LANES)) tht[j] = tn[j];
             w.sync();
             // The predicted decrease is below what an FP32 evaluation of sum r^2 can resolve: take the (Newton-like)
-            // step and stop -- evaluating it would only return rounding noise.
-            if ((double)pred <= ftol * chi2 && rel < 1e-2f) {
+            // step and stop -- evaluating it would only return rounding noise.  What is left AFTER this step is the
+            // predicted decrease of the next one; where the iteration contracts fast (two consecutive accepted steps,
+            // the second predicted to gain at most LF_CONV_CONTRACTION of the first) that is extrapolated as
+            // pred^2 / pred_prev, and the step is the last one once the extrapolation is a tenth of the tolerance.
+            // Slowly contracting fits (flat valleys, blended lines) never qualify and run down to the tolerance itself.
+            bool conv = (double)pred <= ftol * chi2;
+            if (!conv && tries == 0 && pred_prev > 0.0f && pred <= LF_CONV_CONTRACTION * pred_prev &&
+                (double)pred <= LF_CONV_PRED_CAP * chi2)
+                conv = (double)pred * (double)(pred / pred_prev) <= 0.1 * ftol * chi2;
+            if (conv && rel < 1e-2f) {
                 if (w.lane == 0) {
                     for (int j = 0; j < P; ++j) th[j] = tht[j];
                 }
@@ -987,6 +997,7 @@ LF_CORE void lf_stage_lm(const LfCfg& cfg, const LfWarp<LANES>& w, const float* 
                 ++iters;
                 break;
             }
+            pred_prev = tries == 0 ? pred : 0.0f;                 // a damped retry breaks the chain of plain steps
             go = true;
         }
         if (done) break;

@@ -216,7 +216,7 @@ def unpack_rows(rows, L):
 
 
 PRIOR_V_RANGE = (-500.0, 500.0)    # km/s: the velocity range the reference's CNN was trained on
-PRIOR_V_STEP = 6.0                 # km/s (1/8 of an R = 5000 SN3 channel)
+PRIOR_V_STEP = 12.0                # km/s (1/4 of an R = 5000 SN3 channel; the prep stage of the fit refines it on a 6 km/s grid)
 
 
 def estimate_prior(cfg: FitConfig, cube, theta, index=None, bkg=None, v_range=PRIOR_V_RANGE, v_step=PRIOR_V_STEP):

@@ -14,7 +14,7 @@ from tests.common import (check_large_sample_parity, config_from_golden, load_go
 HALF_CHANNEL_KMS = 24.0          # R = 5000 SN3 channel = 48 km/s: the basin of the optimum is about half of it
 
 
-def hostemu_prior(lib, cfg, cube, theta, v_range=(-500.0, 500.0), v_step=6.0):
+def hostemu_prior(lib, cfg, cube, theta, v_range=(-500.0, 500.0), v_step=12.0):
     n = cube.shape[0]
     cube = np.ascontiguousarray(cube, dtype=np.float32)
     theta = np.ascontiguousarray(theta, dtype=np.float32)

@@ -32,6 +32,9 @@ def main():
             idx = torch.arange(34, -1, -2, device=dev)
             engine.fit_batch(cfg, cube, theta[idx], v0f[idx], b0f[idx], index=idx, bkg=cube[0] * 0.01)
             engine.fit_batch(cfg, cube, theta, v0f, b0f, time_stages=True)
+            pv, pb = engine.estimate_prior(cfg, cube, theta[idx], index=idx, bkg=cube[0] * 0.01)
+            engine.fit_batch(cfg, cube, theta[idx], pv, pb, index=idx)
+            engine.fit_batch(cfg, cube, theta, None, None)          # no prior: the prep stage refines around 0
             bad = ~torch.isfinite(r['rows'])
             if bad.any():
                 print('non-finite rows:', model, rel, unc, bad.nonzero()[:8].tolist(), r['status'][bad.any(dim=1)][:8].tolist())
@@ -40,6 +43,9 @@ def main():
         for method in (1, 2):
             engine.snr_map(cube, method, 300, 360, 10, 60, with_deep=True)
         engine.bin_cube(sc.synthesize(dev), 2, 0, 7, 0, 5)
+        junk = sc.synthesize(dev).view(-1)
+        junk[5] = float('nan'); junk[-1] = float('inf')
+        engine.sanitize_cube(junk); engine.sanitize_cube(junk[3:-2])   # aligned and unaligned views
     sc = SyntheticCube(64, 8, model='sincgauss', resolution=5000, seed=4)
     cube = sc.synthesize(dev).view(512, -1)
     engine.deep_image(cube); engine.snr_map(cube, 1, 300, 360, 10, 60)   # several TMA tiles per CTA

@@ -295,7 +295,7 @@ LF_HD float lf_tie_ratio(int model, float p83, float b83, float s83, float p48, 
 }
 
 // ------------------------------------------------------------------------------------- per-warp work areas
-// One model evaluation's per-line working set, kept in per-warp shared memory (80 bytes = 5 x 16-byte loads).
+// One model evaluation's per-line working set, kept in per-warp shared memory (128 bytes).
 struct LF_ALIGN16 LfLineX {
     LfLine ln;
     float aeff;        // amplitude in effect (tied [NII]6548: R * A_6583)
@@ -314,6 +314,9 @@ struct LF_ALIGN16 LfLineX {
     float c_v1;        // -A neae dpdv / (sqrt2 sigma):           dm/dv    = c_v1 Tb + c_v2 U
     float c_v2;        // -A neae a dsdv / sigma
     float c_b2;        // -A neae a dsdb / sigma:                 dm/dbeta = c_b2 U
+    // area factor of the [NII] tie (LuciFit.py:584-595), per line so that all lines form it at once (lane k = line k)
+    float Gk;          // sincgauss: G = sigma / erf(u), u = sigma / (sqrt2 w); gaussian, sinc: sigma
+    float Ek;          // 1/sigma - d ln G / d sigma = (2/sqrt pi) exp(-u^2) / (erf(u) sqrt2 w)   (0 for gaussian, sinc)
 };
 
 // Folds the amplitude in effect into the wing-path factors of a line record (after aeff is final).
@@ -397,6 +400,14 @@ LF_CORE void lf_setup_lines(const LfCfg& cfg, const LfWarp<LANES>& w, const floa
         x.ck = 1.0f; x.sk = 0.0f;
         if (MODEL != LF_GAUSSIAN) lf_phase(((double)x.ln.pp + (double)x.ln.dp) * inv_w, x.sk, x.ck);
         lf_fold_wing(x);
+        x.Gk = x.ln.sig; x.Ek = 0.0f;
+        if (MODEL == LF_SINCGAUSS && cfg.i48 >= 0) {
+            const float iw2 = 1.0f / (LF_SQRT2_F * sinc_w);
+            const float u = x.ln.sig * iw2;
+            const float ierf_u = 1.0f / erff(u);
+            x.Gk = x.ln.sig * ierf_u;
+            x.Ek = LF_2ISQRTPI_F * expf(-u * u) * ierf_u * iw2;
+        }
         sl[k] = x;
     }
     w.sync();
@@ -420,9 +431,9 @@ LF_CORE void lf_setup_lines(const LfCfg& cfg, const LfWarp<LANES>& w, const floa
             float p83 = x83.p, p48 = x48.p, b83 = x83.beta, b48 = x48.beta, s83 = x83.ln.sig, s48 = x48.ln.sig;
             float a83 = x83.aeff;
             int g83 = x83.vg, g48 = x48.vg, h83 = x83.sg, h48 = x48.sg;
-            float R = lf_tie_ratio(MODEL, p83, b83, s83, p48, b48, s48, h83 == h48, sinc_w);
-            float E83 = 0.f, E48 = 0.f;
-            if (MODEL == LF_SINCGAUSS) { E83 = 1.0f / s83 - lf_dlnG(MODEL, s83, sinc_w); E48 = 1.0f / s48 - lf_dlnG(MODEL, s48, sinc_w); }
+            float R, E83 = 0.f, E48 = 0.f;
+            if (MODEL == LF_SINCGAUSS) { R = x83.Gk / (3.0f * x48.Gk); E83 = x83.Ek; E48 = x48.Ek; }
+            else R = lf_tie_ratio(MODEL, p83, b83, s83, p48, b48, s48, h83 == h48, sinc_w);
 #pragma unroll
             for (int g = 0; g < NV; ++g)
                 tx->cRv[g] = a83 * R * ((g == g83 ? x83.dpdv / p83 - E83 * x83.dsdv : 0.f) - (g == g48 ? x48.dpdv / p48 - E48 * x48.dsdv : 0.f));
@@ -1082,7 +1093,7 @@ LF_CORE void lf_stage_out(const LfCfg& cfg, const LfWarp<LANES>& w, const float*
         lf_split(cfg.axis[idx] - cfg.x_ref, pps, ppl);
         lf_line_setup(MODEL, pps, ppl, (float)apd[2 * L + k], sinc_w, x.ln);
         x.aeff = (float)apd[k];
-        x.dpdv = x.dsdv = x.dsdb = 0.0f; x.vg = x.sg = 0; x.p = x.beta = 0.0f;
+        x.dpdv = x.dsdv = x.dsdb = 0.0f; x.vg = x.sg = 0; x.p = x.beta = 0.0f; x.Gk = x.Ek = 0.0f;
         x.ck = 1.0f; x.sk = 0.0f;
         if (MODEL != LF_GAUSSIAN) lf_phase(((double)x.ln.pp + (double)x.ln.dp) * inv_w, x.sk, x.ck);
         lf_fold_wing(x);

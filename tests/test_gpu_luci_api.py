@@ -276,6 +276,11 @@ def test_fit_wvt_bins_equal_fit_spectrum_region(world):
         np.save(os.path.join(folder, 'bool_bin_map_%i.npy' % k), bin_map == k)
     vel2 = luci.fit_wvt(SN3, 'sincgauss', [1] * 5, [1] * 5, prior_values=(v0, b0), uncertainty_bool=True)[0]
     np.testing.assert_array_equal(vel, vel2)
+    # without prior_values (ML_bool=True): the priors of the bins are measured on the device, same optima
+    vel3, _, flux3, _, _ = luci.fit_wvt(SN3, 'sincgauss', [1] * 5, [1] * 5, bin_map=bin_map)
+    inside = bin_map.T >= 0
+    assert (np.abs(vel3[inside] - vel[inside]).max(axis=1) < 0.05).mean() >= 0.95
+    assert (np.abs(flux3[inside] / flux[inside] - 1).max(axis=1) < 2e-3).mean() >= 0.95
 
 
 def test_fit_pixel_matches_fit_cube_and_binned_box(world):

@@ -292,19 +292,30 @@ class Luci():
                             % (cfg.n_vel_groups, cfg.n_sigma_groups))
         dev = cube3d.device
         # fitted spaxels, ordered like the output maps: (y, x) row-major
-        yy, xx = np.meshgrid(np.arange(y_min, y_max), np.arange(x_min, x_max), indexing='ij')
-        if mask is not None:
-            sel = np.asarray(mask)[xx, yy].astype(bool)
-        else:
-            sel = np.ones_like(xx, dtype=bool)
-        flat = (xx.astype(np.int64) * nyc + yy.astype(np.int64))[sel]
-        theta = np.asarray(self.interferometer_theta)[xx[sel], yy[sel]].astype(np.float32)   # LuciBase.py:369
-        index = torch.from_numpy(flat).to(dev)
-        theta_t = torch.from_numpy(theta).to(dev)
+        dense = mask is None and pca is None                # every spaxel of the rectangle: no selection arrays needed
         v0 = b0 = None
-        if have_prior:
-            v0 = torch.from_numpy(np.ascontiguousarray(np.asarray(prior_values[0], dtype=np.float32)[sel])).to(dev)
-            b0 = torch.from_numpy(np.ascontiguousarray(np.asarray(prior_values[1], dtype=np.float32)[sel])).to(dev)
+        if dense:
+            sel = None
+            index = (torch.arange(x_min, x_max, dtype=torch.int64, device=dev)[None, :] * nyc
+                     + torch.arange(y_min, y_max, dtype=torch.int64, device=dev)[:, None]).reshape(-1)
+            theta = np.ascontiguousarray(np.asarray(self.interferometer_theta)[x_min:x_max, y_min:y_max].T,
+                                         dtype=np.float32).reshape(-1)              # LuciBase.py:369
+            if have_prior:
+                v0 = torch.from_numpy(np.ascontiguousarray(prior_values[0], dtype=np.float32)).to(dev).reshape(-1)
+                b0 = torch.from_numpy(np.ascontiguousarray(prior_values[1], dtype=np.float32)).to(dev).reshape(-1)
+        else:
+            yy, xx = np.meshgrid(np.arange(y_min, y_max), np.arange(x_min, x_max), indexing='ij')
+            if mask is not None:
+                sel = np.asarray(mask)[xx, yy].astype(bool)
+            else:
+                sel = np.ones_like(xx, dtype=bool)
+            flat = (xx.astype(np.int64) * nyc + yy.astype(np.int64))[sel]
+            theta = np.asarray(self.interferometer_theta)[xx[sel], yy[sel]].astype(np.float32)   # LuciBase.py:369
+            index = torch.from_numpy(flat).to(dev)
+            if have_prior:
+                v0 = torch.from_numpy(np.ascontiguousarray(np.asarray(prior_values[0], dtype=np.float32)[sel])).to(dev)
+                b0 = torch.from_numpy(np.ascontiguousarray(np.asarray(prior_values[1], dtype=np.float32)[sel])).to(dev)
+        theta_t = torch.from_numpy(theta).to(dev)
         bkg_t = None
         if bkg is not None:
             bkg_t = torch.from_numpy(np.asarray(bkg, dtype=np.float32) * np.float32(bkg_scale)).to(dev)
@@ -365,16 +376,21 @@ class Luci():
             rows = torch.where(better[:, None], alt['rows'], rows)
             res['status'] = torch.where(better, alt['status'], res['status'])
         K = cfg.row_floats
-        full = torch.zeros((nyo * nxo, K), dtype=torch.float32, device=dev)
-        pos = torch.from_numpy(np.flatnonzero(sel.ravel())).to(dev)
-        full[pos] = rows
-        full = full.view(nyo, nxo, K).cpu().numpy()
+        if sel is None:
+            full = rows
+        else:
+            full = torch.zeros((nyo * nxo, K), dtype=torch.float32, device=dev)
+            pos = torch.from_numpy(np.flatnonzero(sel.ravel())).to(dev)
+            full[pos] = rows
+        # one transpose on the device to field-major [K, ny' nx'], one copy to the host: every 2-D map of a line is then
+        # a contiguous slice (what save_fits writes), and the (ny', nx', L) arrays the API returns are views of it
+        host = full.t().contiguous().cpu().numpy()
         self.last_fit_summary = engine.status_summary(res['status'])
         maps = {}
         for i, name in enumerate(engine.ROW_FIELDS):
-            maps[name] = np.ascontiguousarray(full[:, :, i * L:(i + 1) * L])
+            maps[name] = host[i * L:(i + 1) * L].reshape(L, nyo, nxo).transpose(1, 2, 0)
         for i, name in enumerate(engine.ROW_SCALARS):
-            maps[name] = np.ascontiguousarray(full[:, :, 7 * L + i])
+            maps[name] = host[7 * L + i].reshape(nyo, nxo)
         return maps
 
     def _ensure_deep(self):

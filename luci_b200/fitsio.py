@@ -124,6 +124,7 @@ def save_fits(output_dir, object_name, lines, ampls_fits, flux_fits, flux_errors
     if fit_function is not None:
         output_name += "_" + fit_function
     lines_fit = []
+    jobs = []                     # (path, 2-D map): 7 L + 3 independent files
     for ct, line_ in enumerate(lines):
         # NOTE: the reference never appends to its `lines_fit` list (LuciUtility.py:63-68), so repeated line names
         # overwrite one another there; here the second component gets the documented `_2` suffix.
@@ -132,13 +133,20 @@ def save_fits(output_dir, object_name, lines, ampls_fits, flux_fits, flux_errors
         else:
             name = line_
         lines_fit.append(line_)
-        write_fits(output_dir + '/Amplitudes/' + output_name + '_' + name + '_Amplitude.fits', ampls_fits[:, :, ct], header)
-        write_fits(output_dir + '/Fluxes/' + output_name + '_' + name + '_Flux.fits', flux_fits[:, :, ct], header)
-        write_fits(output_dir + '/Fluxes/' + output_name + '_' + name + '_Flux_err.fits', flux_errors_fits[:, :, ct], header)
-        write_fits(output_dir + '/Velocity/' + output_name + '_' + name + '_velocity.fits', velocities_fits[:, :, ct], header)
-        write_fits(output_dir + '/Broadening/' + output_name + '_' + name + '_broadening.fits', broadenings_fits[:, :, ct], header)
-        write_fits(output_dir + '/Velocity/' + output_name + '_' + name + '_velocity_err.fits', velocities_errors_fits[:, :, ct], header)
-        write_fits(output_dir + '/Broadening/' + output_name + '_' + name + '_broadening_err.fits', broadenings_errors_fits[:, :, ct], header)
-    write_fits(output_dir + '/' + output_name + '_Chi2.fits', chi2_fits, header)
-    write_fits(output_dir + '/' + output_name + '_continuum.fits', continuum_fits, header)
-    write_fits(output_dir + '/' + output_name + '_continuum_error.fits', continuum_error_fits, header)
+        jobs.append((output_dir + '/Amplitudes/' + output_name + '_' + name + '_Amplitude.fits', ampls_fits[:, :, ct]))
+        jobs.append((output_dir + '/Fluxes/' + output_name + '_' + name + '_Flux.fits', flux_fits[:, :, ct]))
+        jobs.append((output_dir + '/Fluxes/' + output_name + '_' + name + '_Flux_err.fits', flux_errors_fits[:, :, ct]))
+        jobs.append((output_dir + '/Velocity/' + output_name + '_' + name + '_velocity.fits', velocities_fits[:, :, ct]))
+        jobs.append((output_dir + '/Broadening/' + output_name + '_' + name + '_broadening.fits', broadenings_fits[:, :, ct]))
+        jobs.append((output_dir + '/Velocity/' + output_name + '_' + name + '_velocity_err.fits', velocities_errors_fits[:, :, ct]))
+        jobs.append((output_dir + '/Broadening/' + output_name + '_' + name + '_broadening_err.fits', broadenings_errors_fits[:, :, ct]))
+    jobs.append((output_dir + '/' + output_name + '_Chi2.fits', chi2_fits))
+    jobs.append((output_dir + '/' + output_name + '_continuum.fits', continuum_fits))
+    jobs.append((output_dir + '/' + output_name + '_continuum_error.fits', continuum_error_fits))
+    if sum(np.asarray(m).size for _, m in jobs) < (1 << 22):
+        for path, m in jobs:
+            write_fits(path, m, header)
+    else:                         # large maps: the byte swap and the file writes release the GIL
+        from concurrent.futures import ThreadPoolExecutor
+        with ThreadPoolExecutor(max_workers=min(8, os.cpu_count() or 1)) as pool:
+            list(pool.map(lambda job: write_fits(job[0], job[1], header), jobs))

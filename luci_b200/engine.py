@@ -320,18 +320,26 @@ def sim_cube(cfg: FitConfig, amp, vel, broad, theta, noise_sigma=None, noise=Non
 
 
 def status_summary(status):
-    """Host-side summary of the per-spaxel status words: mean evaluations E, iteration histogram, flag counts."""
-    st = status.detach().cpu().numpy().astype(np.int64)
-    fitted = (st & (_capi_flags()['NAN_INPUT'] | _capi_flags()['BAD_NORM'] | _capi_flags()['MASKED'])) == 0
-    it = st & 0xff
-    ev = (st >> 8) & 0xff
+    """Summary of the per-spaxel status words: mean evaluations E, iterations, flag counts.  Reduced on the device the
+    words live on (one small copy to the host)."""
     flags = _capi_flags()
-    out = {'n': int(st.size), 'n_fitted': int(fitted.sum()),
-           'mean_evals': float(ev[fitted].mean()) if fitted.any() else 0.0,
-           'mean_iters': float(it[fitted].mean()) if fitted.any() else 0.0,
-           'max_evals': int(ev.max()) if st.size else 0}
-    for name, bit in flags.items():
-        out['n_' + name.lower()] = int(((st & bit) != 0).sum())
+    st = status.detach().to(torch.int64).reshape(-1)
+    n = int(st.numel())
+    if n == 0:
+        out = {'n': 0, 'n_fitted': 0, 'mean_evals': 0.0, 'mean_iters': 0.0, 'max_evals': 0}
+        out.update({'n_' + name.lower(): 0 for name in flags})
+        return out
+    bad = flags['NAN_INPUT'] | flags['BAD_NORM'] | flags['MASKED']
+    fitted = (st & bad) == 0
+    ev, it = (st >> 8) & 0xff, st & 0xff
+    parts = [fitted.sum(), (ev * fitted).sum(), (it * fitted).sum(), ev.max()]
+    parts += [((st & bit) != 0).sum() for bit in flags.values()]
+    vals = torch.stack([p.to(torch.int64) for p in parts]).cpu().tolist()
+    nf = vals[0]
+    out = {'n': n, 'n_fitted': int(nf), 'mean_evals': vals[1] / nf if nf else 0.0,
+           'mean_iters': vals[2] / nf if nf else 0.0, 'max_evals': int(vals[3])}
+    for k, name in enumerate(flags):
+        out['n_' + name.lower()] = int(vals[4 + k])
     return out
 
 

@@ -2,6 +2,7 @@
 // A tie pattern with NV velocity groups and NS broadening groups runs on the smallest bucket >= max(NV, NS)
 // (unused group columns are pinned by the solver).
 #pragma once
+#ifndef LF_INSTANCES
 #define LF_INSTANCES(X) \
     X(1, 1) \
     X(2, 1) X(2, 2) \
@@ -11,3 +12,4 @@
     X(6, 1) X(6, 2) X(6, 6) \
     X(7, 1) X(7, 2) \
     X(8, 1) X(8, 2)
+#endif

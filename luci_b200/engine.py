@@ -152,6 +152,18 @@ def fit_batch(cfg: FitConfig, cube, theta, vel0=None, broad0=None, index=None, b
     return out
 
 
+def keep_best(best, alt, chi2_col):
+    """Per spaxel, replace the rows / status of ``best`` by those of ``alt`` where ``alt`` converged with a lower chi2
+    (random restarts, LuciFit.py:682-687; component search).  In place on ``best``; returns it."""
+    better = ((alt['status'] & (1 << 16)) != 0) & (alt['rows'][:, chi2_col] < best['rows'][:, chi2_col])
+    best['rows'] = torch.where(better[:, None], alt['rows'], best['rows'])
+    best['status'] = torch.where(better, alt['status'], best['status'])
+    for key in ('fit_sol', 'fit_unc'):
+        if key in best and key in alt:
+            best[key] = torch.where(better[:, None], alt[key], best[key])
+    return best
+
+
 class HostCubeStream:
     """Fits a cube that lives in pinned HOST memory: the spectra are streamed to the GPU in chunks on a copy stream
     while the previous chunk is being fitted, and the result rows are copied back on a third stream, so the whole

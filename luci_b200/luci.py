@@ -31,6 +31,11 @@ from .fitsio import read_fits, save_fits, write_fits
 
 
 SKYLINE_V0 = 80.0          # km/s: the reference's initial guess for the sky-line velocity (LuciFit.py:859)
+# Component search of a multi-component fit started from ONE prior pair (all the reference's CNN can give): the same
+# line in two velocity groups starts exactly symmetric, a saddle of the objective the reference only leaves through the
+# noise of its finite-difference gradient ("the results are not always correct", docs/source/example_double_fit.rst).
+# Here every further component is started at the prior plus each of these offsets and the lowest chi2 wins per spaxel.
+COMPONENT_OFFSETS = (-300.0, -200.0, -100.0, 100.0, 200.0, 300.0)
 
 
 def check_luci_path(Luci_path):
@@ -283,11 +288,18 @@ class Luci():
         # priors with a trailing axis carry one value per tie group (order of first appearance in vel_rel /
         # sigma_rel): what a double-component fit needs to start its components apart
         per_group = have_prior and np.ndim(prior_values[0]) == 3
+        # the same line in several velocity groups with one shared prior: component search (COMPONENT_OFFSETS)
+        groups_of = {}
+        for ln, vg in zip(lines, vel_rel):
+            groups_of.setdefault(ln, set()).add(int(vg))
+        search = (not per_group) and (not freeze) and any(len(v) > 1 for v in groups_of.values())
+        if search:
+            per_group = True
         cfg = self._make_config(lines, fit_function, vel_rel, sigma_rel, uncertainty_bool, nii_cons, spec_min,
                                 spec_max, obj_redshift, ml_scale=have_prior or auto_prior, prior_groups=per_group,
                                 freeze=freeze)
-        if per_group and (np.shape(prior_values[0])[2] != cfg.n_vel_groups or np.ndim(prior_values[1]) != 3
-                          or np.shape(prior_values[1])[2] != cfg.n_sigma_groups):
+        if per_group and not search and (np.shape(prior_values[0])[2] != cfg.n_vel_groups or np.ndim(prior_values[1]) != 3
+                                         or np.shape(prior_values[1])[2] != cfg.n_sigma_groups):
             raise Exception('per-group prior_values must be (ny, nx, %d) velocities and (ny, nx, %d) broadenings'
                             % (cfg.n_vel_groups, cfg.n_sigma_groups))
         dev = cube3d.device
@@ -357,9 +369,23 @@ class Luci():
             v0, b0 = engine.estimate_prior(cfg, cube2d, theta_t, index=index, bkg=bkg_t)
             have_prior = True
         self.last_prior = (v0, b0)
-        res = engine.fit_batch(cfg, cube2d, theta_t, v0, b0, index=index, bkg=bkg_t)
-        rows = res['rows']
         L_ = len(lines)
+        if search:
+            # per-group starts from the shared pair: the first group keeps it, every further group is offset
+            n_fit = theta_t.numel()
+            v_sh = v0.reshape(n_fit, 1) if v0 is not None else torch.zeros((n_fit, 1), dtype=torch.float32, device=dev)
+            b_sh = b0.reshape(n_fit, 1) if b0 is not None else torch.zeros((n_fit, 1), dtype=torch.float32, device=dev)
+            b_pg = b_sh.expand(n_fit, cfg.n_sigma_groups).contiguous()
+            res = None
+            for d in COMPONENT_OFFSETS:
+                off = torch.zeros((1, cfg.n_vel_groups), dtype=torch.float32, device=dev)
+                off[0, 1:] = d
+                alt = engine.fit_batch(cfg, cube2d, theta_t, (v_sh + off).contiguous(), b_pg, index=index, bkg=bkg_t)
+                res = alt if res is None else engine.keep_best(res, alt, 7 * L_)
+            n_stoch = 1
+        else:
+            res = engine.fit_batch(cfg, cube2d, theta_t, v0, b0, index=index, bkg=bkg_t)
+        rows = res['rows']
         for st in range(1, int(n_stoch)):
             # random restarts (LuciFit.py:662-687): the reference redraws every line's position from
             # N(p, |1e7/lambda - p| / 50) and sigma from N(sigma, sigma / 10) with numpy's global generator and keeps
@@ -371,10 +397,8 @@ class Luci():
             v_r = torch.from_numpy(np.random.normal(v_np, np.abs(v_np) / 50.0).astype(np.float32)).to(dev)
             b_r = torch.from_numpy(np.random.normal(b_np, np.abs(b_np) / 10.0).astype(np.float32)).to(dev)
             alt = engine.fit_batch(cfg, cube2d, theta_t, v_r, b_r, index=index, bkg=bkg_t)
-            ok_alt = (alt['status'] & (1 << 16)) != 0
-            better = ok_alt & (alt['rows'][:, 7 * L_] < rows[:, 7 * L_])
-            rows = torch.where(better[:, None], alt['rows'], rows)
-            res['status'] = torch.where(better, alt['status'], res['status'])
+            res = engine.keep_best(res, alt, 7 * L_)
+            rows = res['rows']
         K = cfg.row_floats
         if sel is None:
             full = rows

@@ -188,7 +188,7 @@ class OracleFit:
     def __init__(self, spectrum, axis, model_type, lines, vel_rel, sigma_rel, trans_filter=None, theta=0.0,
                  delta_x=2943, n_steps=842, zpd_index=169, filter='SN3', uncertainty_bool=False, nii_cons=True,
                  initial_values=(False,), spec_min=None, spec_max=None, obj_redshift=0.0, n_stoch=1,
-                 prior=None, ml_path=True, rng=None):
+                 prior=None, ml_path=True, rng=None, group_prior=None):
         if model_type == 'gauss':
             model_type = 'gaussian'
         if model_type not in ('gaussian', 'sinc', 'sincgauss'):
@@ -232,6 +232,10 @@ class OracleFit:
         mpd = self.cos_theta * float(delta_x) * (int(n_steps) - int(zpd_index)) / 1e7  # :222-223
         self.sinc_width = 1 / (2 * mpd)
         self.vel_ml, self.broad_ml = (0.0, 0.0) if prior is None else (float(prior[0]), float(prior[1]))
+        # group_prior = (velocity per velocity group, broadening per sigma group), groups in order of first appearance:
+        # the per-group start of oracle/make_golden.py's ``per_group`` fixtures (line_vals_estimate wrapped so that
+        # vel_ml / broad_ml are those of the line's group; not expressible through the reference's CNN)
+        self.group_prior = group_prior
         self.ml_path = bool(ml_path) and prior is not None
         self.initial_values = list(initial_values)
         self.freeze = self.initial_values[0] is not False
@@ -242,8 +246,12 @@ class OracleFit:
         self.slsqp = None
 
     # -- a7
-    def line_vals_estimate(self, line):
+    def line_vals_estimate(self, line, k=None):
         lam = LINE_DICT[line]
+        if self.group_prior is not None and k is not None:
+            dense = lambda rel: list(dict.fromkeys(rel)).index(rel[k])
+            self.vel_ml = float(self.group_prior[0][dense(self.vel_rel)])
+            self.broad_ml = float(self.group_prior[1][dense(self.sigma_rel)])
         if self.freeze:
             self.vel_ml, self.broad_ml = self.initial_values[0], self.initial_values[1]
         if np.isnan(self.broad_ml):
@@ -340,7 +348,7 @@ class OracleFit:
                 initial = np.ones(3 * L + 1)
                 initial[-1] = cont_est
                 for k in range(L):
-                    amp, pos, sig = self.line_vals_estimate(self.lines[k])
+                    amp, pos, sig = self.line_vals_estimate(self.lines[k], k)
                     initial[3 * k] = amp - initial[-1]
                     if st == 0:
                         initial[3 * k + 1] = pos
@@ -359,7 +367,7 @@ class OracleFit:
             initial = np.ones(L + 1)
             initial[-1] = self.cont_estimate(sigma_level=3)
             for k in range(L):
-                amp, pos, sig = self.line_vals_estimate(self.lines[k])
+                amp, pos, sig = self.line_vals_estimate(self.lines[k], k)
                 initial[k] = amp - initial[-1]
                 positions[k], sigmas[k] = pos, sig
             self._frozen_pos, self._frozen_sig = positions, sigmas

@@ -38,9 +38,19 @@ CASES = {
                              sigma_rel=[1, 1], n=16, unc=False, broad=(60, 100), seed=105),
     'fit_sincgauss_groups': dict(filter='SN3', R=5000, lines=SN3, model='sincgauss', vel_rel=[1, 2, 2, 3, 3],
                                  sigma_rel=[1, 2, 2, 3, 3], n=12, unc=True, broad=(30, 60), seed=106),
+    # the same three independent tie groups at SNR 40-100, where every group is well determined (no zero-width spikes)
+    'fit_sincgauss_groups_hi': dict(filter='SN3', R=5000, lines=SN3, model='sincgauss', vel_rel=[1, 2, 2, 3, 3],
+                                    sigma_rel=[1, 2, 2, 3, 3], n=24, unc=True, broad=(30, 60), seed=114, snr=(40, 100)),
     'fit_sincgauss_double': dict(filter='SN3', R=5000, lines=SN3 + ['Halpha'], model='sincgauss',
                                  vel_rel=[1, 1, 1, 1, 1, 2], sigma_rel=[1, 1, 1, 1, 1, 2], n=10, unc=True,
                                  broad=(30, 50), seed=107, double=True),
+    # BASELINE config 4 with the two components started apart: one (velocity, broadening) prior per tie group.  The
+    # reference's CNN can only give one pair per spectrum, so for this fixture ``Fit.line_vals_estimate``
+    # (LuciFit.py:382-430) is wrapped to set ``vel_ml`` / ``broad_ml`` to the prior of the line's group before the
+    # unmodified body runs; everything downstream (SLSQP, ties, hessianComp uncertainties) is the reference as is.
+    'fit_sincgauss_double_pg': dict(filter='SN3', R=5000, lines=SN3 + ['Halpha'], model='sincgauss',
+                                    vel_rel=[1, 1, 1, 1, 1, 2], sigma_rel=[1, 1, 1, 1, 1, 2], n=24, unc=True,
+                                    broad=(30, 50), seed=113, double=True, per_group=True),
     'fit_sincgauss_single': dict(filter='SN3', R=5000, lines=['Halpha'], model='sincgauss', vel_rel=[1],
                                  sigma_rel=[1], n=12, unc=True, broad=(25, 60), seed=108),
     'fit_sinc_noml': dict(filter='SN3', R=5000, lines=SN3, model='sinc', vel_rel=[1] * 5, sigma_rel=[1] * 5,
@@ -57,6 +67,12 @@ CASES = {
     # sample large enough to test the north_star's "99.9 % of spaxels" (run with --jobs 8: ~0.8 s/spaxel/core)
     'parity_sincgauss_cfg2': dict(filter='SN3', R=5917, lines=SN3, model='sincgauss', vel_rel=[1] * 5,
                                   sigma_rel=[1] * 5, n=1000, unc=False, broad=(25, 60), seed=110),
+    # uncertainties (hessianComp, LuciUtility.py:409-434) at the benchmark's spectral length nz = 841
+    'unc_sincgauss_cfg2': dict(filter='SN3', R=5917, lines=SN3, model='sincgauss', vel_rel=[1] * 5,
+                               sigma_rel=[1] * 5, n=32, unc=True, broad=(25, 60), seed=115),
+    # HELD-OUT sample of the same configuration (different seed): thresholds of the device code are never tuned on it
+    'parity_sincgauss_heldout': dict(filter='SN3', R=5917, lines=SN3, model='sincgauss', vel_rel=[1] * 5,
+                                     sigma_rel=[1] * 5, n=400, unc=False, broad=(25, 60), seed=2718),
 }
 
 BASE_AMP = {'Halpha': 1.0, 'NII6583': 0.3, 'NII6548': 0.1, 'SII6716': 0.15, 'SII6731': 0.12, 'Hbeta': 1.0,
@@ -76,7 +92,8 @@ def build_inputs(case):
     for i in range(n):
         vel = float(rng.uniform(-40, 40) if case.get('noml') else rng.uniform(-150, 150))
         broad = float(rng.uniform(*case['broad']))
-        snr = float(np.exp(rng.uniform(np.log(10), np.log(100))))
+        snr_lo, snr_hi = case.get('snr', (10, 100))
+        snr = float(np.exp(rng.uniform(np.log(snr_lo), np.log(snr_hi))))
         amps = [BASE_AMP[l] if BASE_AMP[l] == 1.0 else BASE_AMP[l] * rng.uniform(0.5, 1.5) for l in lines]
         if 'NII6548' in lines and 'NII6583' in lines:
             amps[lines.index('NII6548')] = amps[lines.index('NII6583')] / 3
@@ -95,7 +112,10 @@ def build_inputs(case):
         bfit = broad * np.cos(np.deg2rad(theta)) * 299792 / 3e5
         # per velocity/sigma group priors are not expressible through the reference's CNN (one (v, b) pair per
         # spectrum), so the prior is that of the first component
-        if case.get('freeze'):                       # frozen values: a previous fit's result, close to the truth
+        if case.get('per_group'):                    # one prior per tie group (order of first appearance)
+            v0.append([vfit[0] + rng.normal(0, 10), vfit[1] + rng.normal(0, 10)])
+            b0.append([abs(bfit * (1 + rng.normal(0, 0.1))), abs(bfit * (1 + rng.normal(0, 0.1)))])
+        elif case.get('freeze'):                     # frozen values: a previous fit's result, close to the truth
             v0.append(vfit[0] + rng.normal(0, 3))
             b0.append(abs(bfit * (1 + rng.normal(0, 0.05))))
         else:
@@ -153,7 +173,22 @@ def run_reference(case, inp):
 
     LF.Fit.fit = spy
     noml = bool(case.get('noml'))
-    ref_shim.install_prior(None if noml else (lambda fit: (float(inp['v0'][_cur['i']]), float(inp['b0'][_cur['i']]))))
+    per_group = bool(case.get('per_group'))
+    orig_lve = LF.Fit.line_vals_estimate
+    if per_group:
+        dense = lambda rel: [list(dict.fromkeys(rel)).index(r) for r in rel]
+        gv, gs = dense(case['vel_rel']), dense(case['sigma_rel'])
+
+        def lve(self, line_name):
+            k = getattr(self, '_lve_k', 0)
+            self.vel_ml = float(inp['v0'][_cur['i']][gv[k]])
+            self.broad_ml = float(inp['b0'][_cur['i']][gs[k]])
+            self._lve_k = (k + 1) % len(lines)
+            return orig_lve(self, line_name)
+
+        LF.Fit.line_vals_estimate = lve
+    first = (lambda a: float(a[0])) if per_group else float
+    ref_shim.install_prior(None if noml else (lambda fit: (first(inp['v0'][_cur['i']]), first(inp['b0'][_cur['i']]))))
     out = {k: [] for k in ('amplitudes', 'fluxes', 'flux_errors', 'velocities', 'vels_errors', 'sigmas',
                            'sigmas_errors', 'chi2', 'corr', 'axis_step', 'continuum', 'continuum_error')}
     wsyn = np.linspace(14700, 15600, 460).astype(np.float32)     # only feeds the (stubbed) CNN input
@@ -175,6 +210,7 @@ def run_reference(case, inp):
                 out[key].append(lst[0])
     finally:
         LF.Fit.fit = orig_fit
+        LF.Fit.line_vals_estimate = orig_lve
     dt = time.time() - t0
     res = {('ref_' + k): np.array(v, dtype=np.float64) for k, v in out.items()}
     res['ref_fit_sol'] = np.stack([c[0] for c in captured])
@@ -197,7 +233,7 @@ def make(name, jobs=1):
     meta = dict(filter=case['filter'], model=case['model'], lines=np.array(case['lines']),
                 vel_rel=np.array(case['vel_rel']), sigma_rel=np.array(case['sigma_rel']),
                 uncertainty=np.array(case['unc']), noml=np.array(bool(case.get('noml'))),
-                freeze=np.array(bool(case.get('freeze'))),
+                freeze=np.array(bool(case.get('freeze'))), per_group=np.array(bool(case.get('per_group'))),
                 n_steps=np.array(inp['n_steps']), delta_x=np.array(inp['delta_x']))
     os.makedirs(GOLDEN, exist_ok=True)
     path = os.path.join(GOLDEN, name + '.npz')
@@ -215,7 +251,7 @@ if __name__ == '__main__':
         jobs = int(argv[argv.index('--jobs') + 1])
         del argv[argv.index('--jobs'):argv.index('--jobs') + 2]
     sys.argv = sys.argv[:1] + argv
-    names = [a for a in argv if a != "reductions"] or ([] if "reductions" in argv else
+    names = [a for a in argv if a not in ("reductions", "region_strip")] or ([] if ("reductions" in argv or "region_strip" in argv) else
                                                        [c for c in CASES if not c.startswith('parity_')])
     for nm in names:
         make(nm, jobs)
@@ -283,3 +319,104 @@ def make_reductions():
 
 if __name__ == '__main__' and (len(sys.argv) == 1 or 'reductions' in sys.argv[1:]):
     make_reductions()
+
+
+# ------------------------------------------------------------------------------------------ region strip (config 1)
+def _strip_row(args):
+    """One y-row of the strip through the reference's own row worker (LuciBase.py:258-406) with the mask."""
+    sl, cube, axis32, mask, theta_map, v0map, b0map, n_steps, delta_x = args
+    from oracle import ref_shim
+    Luci, LF = ref_shim.modules()
+    captured = []
+    orig_fit = LF.Fit.fit
+
+    def spy(self, *a, **k):
+        d = orig_fit(self, *a, **k)
+        captured.append((np.array(self.fit_sol, dtype=float), float(self.spectrum_scale)))
+        return d
+
+    LF.Fit.fit = spy
+    nx = cube.shape[0]
+    key = lambda spec: np.asarray(spec[:6], dtype=np.float64).tobytes()
+    lut = {key(cube[x, sl].astype(np.float64)): (float(v0map[sl, x]), float(b0map[sl, x])) for x in range(nx)}
+    ref_shim.install_prior(lambda fit: lut[key(fit.spectrum)])
+    wsyn = np.linspace(14700, 15600, 460).astype(np.float32)
+    try:
+        with warnings.catch_warnings():
+            warnings.simplefilter('ignore')
+            res = Luci.fit_calc(sl, 0, nx, 0, 'sinc', SN3, [1] * 5, [1] * 5, cube_slice=cube[:, sl, :].astype(np.float64),
+                                spectrum_axis=axis32, wavenumbers_syn=wsyn, transmission_interpolated=None,
+                                interferometer_theta=theta_map, hdr_dict={'FILTER': 'SN3', 'STEP': delta_x},
+                                step_nb=n_steps, zpd_index=0, mdn=False, mask=mask, ML_bool=True, uncertainty_bool=False,
+                                nii_cons=True, resolution=5000, Luci_path='/root/reference/')
+    finally:
+        LF.Fit.fit = orig_fit
+    return res, captured
+
+
+def make_region_strip(jobs=8):
+    """BASELINE config 1 as a strip: 100 x 8 spaxels, SN3 five-line sinc model, ``fit_region`` with a mask.  Every y-row goes
+    through the reference's row worker exactly as ``fit_region`` hands it out (LuciBase.py:691-705) and the maps are
+    assembled like :706-718.  Stored both as maps (ny, nx[, L]) and, for the masked-in spaxels in (y, x) order, in the flat
+    layout of the other fixtures."""
+    import multiprocessing as mp
+    from oracle import ref_shim
+    ref_shim.install()
+    import LUCI.LuciSim as LS
+    rng = np.random.default_rng(116)
+    nx, ny, theta = 100, 8, 11.96
+    cube, v0map, b0map = None, np.zeros((ny, nx), np.float32), np.zeros((ny, nx), np.float32)
+    for x in range(nx):
+        for y in range(ny):
+            vel, broad = float(rng.uniform(-150, 150)), float(rng.uniform(20, 60))
+            snr = float(np.exp(rng.uniform(np.log(10), np.log(100))))
+            amps = [1.0, 0.1, 0.3 * rng.uniform(0.5, 1.5), 0.15 * rng.uniform(0.5, 1.5), 0.12 * rng.uniform(0.5, 1.5)]
+            amps[1] = amps[2] / 3
+            np.random.seed(116000 + x * ny + y)
+            sp = LS.Spectrum(SN3, 'sinc', amps, 0.0, 0.0, 'SN3', 5000, snr)
+            sp.velocity, sp.broadening = [vel] * 5, [broad] * 5
+            axis, spec = sp.create_spectrum()
+            if cube is None:
+                cube = np.zeros((nx, ny, len(axis)), np.float32)
+            cube[x, y] = ((spec + 0.1) * 1e-17).astype(np.float32)
+            v0map[y, x] = -vel * 299792 / 3e5 + rng.normal(0, 15)
+            b0map[y, x] = abs(broad * np.cos(np.deg2rad(theta)) * 299792 / 3e5 * (1 + rng.normal(0, 0.15)))
+    mask = rng.uniform(size=(nx, ny)) < 0.7
+    axis32 = np.asarray(axis, dtype=np.float32)
+    theta_map = np.full((nx, ny), theta)
+    args = [(sl, cube, axis32, mask, theta_map, v0map, b0map, sp.n_steps, sp.delta_x) for sl in range(ny)]
+    with mp.get_context('fork').Pool(min(jobs, ny)) as pool:
+        out = pool.map(_strip_row, args)
+    L = 5
+    names = ('amplitudes', 'fluxes', 'flux_errors', 'velocities', 'vels_errors', 'sigmas', 'sigmas_errors', 'chi2', 'corr',
+             'axis_step', 'continuum', 'continuum_error')
+    maps = {k: (np.zeros((ny, nx, L), np.float32) if i < 7 else np.zeros((ny, nx), np.float32)) for i, k in enumerate(names)}
+    flat = {'cube': [], 'v0': [], 'b0': [], 'ref_fit_sol': [], 'ref_scale': [], 'yx': []}
+    flat.update({'ref_' + k: [] for k in names})
+    for res, captured in out:
+        i = res[0]
+        for k, lst in zip(names, res[1:]):
+            maps[k][i] = lst                                    # LuciBase.py:706-718
+        cap = iter(captured)
+        for x in range(nx):
+            if mask[x, i]:
+                sol, scale = next(cap)
+                flat['cube'].append(cube[x, i]); flat['v0'].append(v0map[i, x]); flat['b0'].append(b0map[i, x])
+                flat['ref_fit_sol'].append(sol); flat['ref_scale'].append(scale); flat['yx'].append((i, x))
+                for k, lst in zip(names, res[1:]):
+                    flat['ref_' + k].append(np.asarray(lst[x], dtype=np.float64))
+    n = len(flat['yx'])
+    path = os.path.join(GOLDEN, 'region_sinc_strip.npz')
+    np.savez_compressed(path, cube3d=cube, mask=mask, v0map=v0map, b0map=b0map, axis32=axis32,
+                        **{'map_' + k: v for k, v in maps.items()},
+                        cube=np.stack(flat['cube']), v0=np.array(flat['v0'], np.float32), b0=np.array(flat['b0'], np.float32),
+                        theta=np.full(n, theta, np.float32), yx=np.array(flat['yx']), ref_fit_sol=np.stack(flat['ref_fit_sol']),
+                        ref_scale=np.array(flat['ref_scale']), **{'ref_' + k: np.stack(flat['ref_' + k]) for k in names},
+                        filter='SN3', model='sinc', lines=np.array(SN3), vel_rel=np.array([1] * 5), sigma_rel=np.array([1] * 5),
+                        uncertainty=np.array(False), noml=np.array(False), freeze=np.array(False), per_group=np.array(False),
+                        n_steps=np.array(sp.n_steps), delta_x=np.array(sp.delta_x))
+    print('region_sinc_strip: %d fitted of %d spaxels ->' % (n, nx * ny), path)
+
+
+if __name__ == '__main__' and 'region_strip' in sys.argv[1:]:
+    make_region_strip()

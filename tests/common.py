@@ -16,8 +16,10 @@ TOL_REL = 1e-3
 TOL_CHI2 = 1e-4
 
 FIT_CASES = ['fit_sincgauss_sn3', 'fit_gaussian_sn3', 'fit_sinc_sn3', 'fit_gaussian_sn2', 'fit_gaussian_sn1',
-             'fit_sincgauss_groups', 'fit_sincgauss_double', 'fit_sincgauss_single', 'fit_sinc_noml',
-             'fit_sincgauss_trans']
+             'fit_sincgauss_groups', 'fit_sincgauss_groups_hi', 'fit_sincgauss_double', 'fit_sincgauss_double_pg',
+             'fit_sincgauss_single', 'fit_sinc_noml', 'fit_sincgauss_trans']
+UNC_CASES = ['fit_sincgauss_sn3', 'fit_gaussian_sn3', 'fit_sincgauss_single', 'fit_sincgauss_groups_hi',
+             'fit_sincgauss_double_pg', 'fit_sincgauss_trans', 'unc_sincgauss_cfg2']
 
 
 def load_golden(name):
@@ -38,6 +40,8 @@ def config_from_golden(g, uncertainty=None, **kw):
         kw.setdefault('freeze', True)
     if 'trans' in g:
         kw.setdefault('trans_filter', g['trans'])
+    if 'per_group' in g and bool(g['per_group']):
+        kw.setdefault('prior_groups', True)
     return FitConfig(g['model'], g['lines'], [int(v) for v in g['vel_rel']], [int(v) for v in g['sigma_rel']],
                      g['axis32'], filter=g['filter'], delta_x=float(g['delta_x']), n_steps=int(g['n_steps']),
                      zpd_index=0, uncertainty_bool=unc, nii_cons=True, ml_scale=not bool(g['noml']), **kw)
@@ -55,6 +59,8 @@ def run_hostemu(lib, cfg, cube, theta, v0, b0, want_unc=True):
     unc = np.zeros((n, PF), np.float32)
     st = np.zeros(n, np.int32)
     cube = np.ascontiguousarray(cube, dtype=np.float32)
+    v0 = None if v0 is None else np.ascontiguousarray(v0, dtype=np.float32)
+    b0 = None if b0 is None else np.ascontiguousarray(b0, dtype=np.float32)
     rc = lib.hostemu_fit_batch(cfg.byref(), n, ptr(cube), None, ptr(theta), ptr(v0), ptr(b0), None, ptr(rows),
                                ptr(sol), ptr(unc), ptr(st))
     assert rc == 0
@@ -88,26 +94,159 @@ def parity_report(rows, g, model, check_broadening=True):
     return dict(dv=dv, db=db, df=df, da=da, dchi=dchi, dcont=dcont, ok=ok, q=q, ref_spike=spike)
 
 
-def check_large_sample_parity(rows, status, g, float64_objective=None):
-    """north_star criterion on the 1000-spaxel sample of the benchmark configuration (parity_sincgauss_cfg2.npz):
-    velocity <= 0.5 km/s, broadening and fluxes <= 1e-3 relative, chi2 no worse than the reference by more than 1e-4
-    relative, for >= 99.9 % of spaxels.
+def rows_to_solution(q, g, i, scale):
+    """Our result row of spaxel ``i`` as the reference's normalised [A, p, sigma]*L + [c] vector."""
+    from oracle import luci_oracle as O
+    L = len(g['lines'])
+    full = np.zeros(3 * L + 1)
+    for k, line in enumerate(g['lines']):
+        p = 1e7 / (O.LINE_DICT[line] * (1 + q['velocities'][i][k] / 299792.0))
+        full[3 * k], full[3 * k + 1], full[3 * k + 2] = q['amplitudes'][i][k] / scale, p, p * q['sigmas'][i][k] / 299792.0
+    full[-1] = q['continuum'][i] / scale
+    return full
 
-    Velocity, broadening and chi2 meet it outright.  The flux of a weak line can sit in a flat direction of the
-    objective where the reference's SLSQP stops early: a few spaxels (3 of 1000 in the committed sample) differ by
-    1e-3..4e-3 in one [SII] flux.  For those the caller may pass ``float64_objective(i, rows)`` -> (ours, reference),
-    the float64 sum of squares at both solutions, and ours must not be the higher one."""
+
+def _within(d, t, model, check_broadening=True, amp_floor=0.0):
+    """north_star tolerances between two derived-quantity dicts; lines whose flux is below ``amp_floor`` times the
+    strongest line's (amplitudes pinned at the box edge, -1e-8) are compared absolutely against that floor."""
+    dv = np.abs(d['velocities'] - t['velocities']).max()
+    db = (np.abs(d['sigmas'] - t['sigmas']) / np.maximum(np.abs(t['sigmas']), 1e-12)).max()
+    den = np.maximum(np.abs(t['fluxes']), amp_floor * np.abs(t['fluxes']).max())
+    df = (np.abs(d['fluxes'] - t['fluxes']) / den).max()
+    ok = dv <= TOL_VEL_KMS and df <= TOL_REL and (db <= TOL_REL or not check_broadening)
+    return ok, dv, db, df
+
+
+def optimum_report(rows, g, tight=None, check_broadening=True):
+    """Objective-backed parity of every spaxel of a golden fixture.
+
+    The reference's problem is solved to machine precision from the reference's own answer (oracle/tight.py, or the
+    precomputed ``tight`` arrays of tools/parity_tight.py).  A spaxel passes when our solution is within the north_star
+    tolerances of that optimum (``same``), or when it sits in a different local minimum whose float64 objective is LOWER
+    than the reference's optimum and which is itself a converged optimum -- a tight solve started from OUR answer stays
+    within the tolerances of it (``lower``).  Also returned: where the reference's own SLSQP answer misses its optimum
+    (``ref_off``), the chi2 comparison against the reference and our objective excess over the optimum."""
+    from oracle import tight as T
+    L = len(g['lines'])
+    q = split_rows(rows, L)
+    n = rows.shape[0]
+    out = dict(same=np.zeros(n, bool), lower=np.zeros(n, bool), ref_off=np.zeros(n, bool), dv=np.zeros(n), db=np.zeros(n),
+               df=np.zeros(n), excess=np.zeros(n), q=q)
+    amp_floor = 1e-6          # a line fitted to (numerically) nothing: compare against 1e-6 of the strongest line
+    for i in range(n):
+        prob = T.problem_from_golden(g, i)
+        scale = float(g['ref_scale'][i])
+        ref = np.array(g['ref_fit_sol'][i], float).copy()
+        ref[0:-1:3] /= scale
+        ref[-1] /= scale
+        if tight is not None:
+            topt, tobj = tight['tight_sol'][i], float(tight['tight_obj'][i])
+        else:
+            topt, tobj, _ = prob.solve(ref)
+        dt = T.derived(prob, topt, scale)
+        ours = rows_to_solution(q, g, i, scale)
+        d_ours = {k: q[k][i] for k in ('velocities', 'sigmas', 'fluxes')}
+        ok, out['dv'][i], out['db'][i], out['df'][i] = _within(d_ours, dt, g['model'], check_broadening, amp_floor)
+        obj_ours = prob.objective_full(ours)
+        out['excess'][i] = obj_ours / tobj - 1.0
+        out['same'][i] = ok
+        if not ok and obj_ours < tobj * (1 - 1e-9):
+            mine, mobj, _ = prob.solve(ours)
+            ok2, _, _, _ = _within(d_ours, T.derived(prob, mine, scale), g['model'], check_broadening, amp_floor)
+            out['lower'][i] = ok2 and mobj <= tobj
+        d_ref = {'velocities': g['ref_velocities'][i], 'sigmas': g['ref_sigmas'][i], 'fluxes': g['ref_fluxes'][i]}
+        out['ref_off'][i] = not _within(d_ref, dt, g['model'], check_broadening, amp_floor)[0]
+    out['dchi'] = (q['chi2'] - g['ref_chi2']) / np.abs(g['ref_chi2'])
+    out['ok'] = out['same'] | out['lower']
+    return out
+
+
+def load_tight(name):
+    path = os.path.join(GOLDEN, name + '_tight.npz')
+    return dict(np.load(path)) if os.path.exists(path) else None
+
+
+def check_large_sample_parity(rows, status, g, tight):
+    """north_star criterion on a large sample of the benchmark configuration (parity_sincgauss_cfg2.npz: 1000 spaxels;
+    parity_sincgauss_heldout.npz: 400 spaxels of another seed, never used for tuning): velocity <= 0.5 km/s, broadening
+    and fluxes <= 1e-3 relative, chi2 no worse than the reference by more than 1e-4 relative, >= 99.9 % of spaxels.
+
+    Velocity, broadening and chi2 are compared with the reference directly.  A flux can only be compared with the
+    reference where the reference itself found its optimum: its SLSQP stops on the objective and leaves up to 1.6e-3
+    of a weak line's flux on the table (3 of the 1000 committed spaxels, tools/parity_tight.py).  So fluxes are held to
+    the tight optimum of the reference's objective (every spaxel), and to the reference wherever the reference is
+    within 5e-4 of that optimum."""
     rep = parity_report(rows, g, g['model'])
+    opt = optimum_report(rows, g, tight=tight)
     n = len(rep['dv'])
     assert ((status >> 16) & 1).all()
-    assert (rep['dv'] <= TOL_VEL_KMS).mean() >= 0.999, rep['dv'].max()
-    assert (rep['db'] <= TOL_REL).mean() >= 0.999, rep['db'].max()
-    assert (rep['dchi'] <= TOL_CHI2).mean() >= 0.999, rep['dchi'].max()
-    assert rep['dv'].max() < 0.05 and rep['db'].max() < 5e-4 and rep['dchi'].max() < 5e-5
-    flux_bad = np.flatnonzero(rep['df'] > TOL_REL)
-    assert len(flux_bad) <= 0.005 * n and rep['df'].max() < 1e-2, (flux_bad, rep['df'][flux_bad])
-    if float64_objective is not None:
-        for i in flux_bad:
-            ours, ref = float64_objective(int(i), rep)
-            assert ours <= ref * (1 + 1e-7), (i, ours, ref)
-    return rep
+    assert (rep['dv'] <= TOL_VEL_KMS).mean() >= 0.999 and rep['dv'].max() < 0.05, rep['dv'].max()
+    assert (rep['db'] <= TOL_REL).mean() >= 0.999 and rep['db'].max() < 5e-4, rep['db'].max()
+    assert (rep['dchi'] <= TOL_CHI2).mean() >= 0.999 and rep['dchi'].max() < 5e-5, rep['dchi'].max()
+    # against the optimum itself: every spaxel, all three quantities, and the objective reached
+    assert opt['same'].all(), np.flatnonzero(~opt['same'])
+    assert opt['df'].max() < TOL_REL and opt['dv'].max() < 0.05 and opt['db'].max() < 5e-4, (opt['df'].max(), opt['dv'].max())
+    # (our float32 rows satisfy the [NII] tie to 1e-7 only, which can lower the unconstrained objective by ~1e-8)
+    assert opt['excess'].max() < 1e-6 and opt['excess'].min() > -1e-7, (opt['excess'].min(), opt['excess'].max())
+    # against the reference: flux agrees wherever the reference is at its own optimum
+    tf = tight['tight_fluxes']
+    ref_close = (np.abs(g['ref_fluxes'] - tf) / np.abs(tf)).max(axis=1) <= 5e-4
+    assert ref_close.mean() >= 0.99
+    assert (rep['df'][ref_close] <= TOL_REL).all(), rep['df'][ref_close].max()
+    assert (rep['df'] <= TOL_REL).mean() >= 0.995
+    return rep, opt
+
+
+def golden_priors(g):
+    """(vel0, broad0) of a fixture as the C ABI wants them: None for the no-prior path, [n] or [n, groups] float32."""
+    if bool(g['noml']):
+        return None, None
+    return np.ascontiguousarray(g['v0'], dtype=np.float32), np.ascontiguousarray(g['b0'], dtype=np.float32)
+
+
+def assert_fixture_parity(name, rows, status, g):
+    """The parity statement of one small golden fixture, every spaxel accounted for:
+
+      * our solution is the optimum of the reference's objective reached from the reference's own answer (north_star
+        tolerances against a machine-precision solve), or a strictly lower converged minimum (``optimum_report``);
+      * wherever that optimum is shared AND the reference sits on it, the direct comparison with the reference's
+        numbers holds too (velocity, broadening, flux, chi2);
+      * the only exclusion: spaxels where the reference collapsed a line group to a zero-width spike (broadening
+        < 1e-3 km/s, a thousandth of a channel -- fit_sincgauss_groups at SNR ~10), which is not a point of the model.
+    """
+    model = g['model']
+    cb = model != 'sinc'          # sigma is not a parameter of the sinc profile: the reference's value is an SLSQP artefact
+    rep = parity_report(rows, g, model, check_broadening=cb)
+    opt = optimum_report(rows, g, check_broadening=cb)
+    keep = ~rep['ref_spike']
+    if name == 'fit_sincgauss_groups':
+        assert keep.sum() >= 0.75 * len(keep)
+    else:
+        assert keep.all()
+    assert opt['ok'][keep].all(), (name, np.flatnonzero(~opt['ok'] & keep), opt['dv'], opt['df'])
+    assert ((status[keep] >> 16) & 1).all()
+    direct = opt['same'] & ~opt['ref_off'] & keep
+    assert rep['ok'][direct].all(), (name, rep['dv'][direct], rep['db'][direct], rep['df'][direct], rep['dchi'][direct])
+    assert (opt['dchi'][opt['lower']] < 0).all()                 # a lower minimum shows in the reported chi2 as well
+    assert opt['excess'][opt['same']].max() < 1e-6
+    return rep, opt, direct
+
+
+def assert_uncertainty_parity(name, rows, unc, g, sel):
+    """1-sigma errors against the reference's (hessianComp, LuciUtility.py:409-434) on every spaxel of ``sel`` (where the
+    two fits share the optimum).  The reference's delta = 0.1 finite-difference Hessian is indefinite for some weak
+    lines (an eigenvalue of -0.2 next to 4e4 in unc_sincgauss_cfg2[11]); there its inverse amplifies the 1e-4
+    difference between two converged solutions to a few per cent -- in float64 just as on the device -- hence the
+    separate bounds on the bulk and on the worst entry."""
+    q = split_rows(rows, len(g['lines']))
+    rels = []
+    for key in ('vels_errors', 'sigmas_errors', 'flux_errors', 'continuum_error'):
+        ref, mine = g['ref_' + key][sel], q[key][sel]
+        rel = (np.abs(mine - ref) / np.abs(ref)).ravel()
+        rel = rel[np.isfinite(rel)]
+        assert np.median(rel) < 1e-4 and np.percentile(rel, 90) < 1.5e-3 and rel.max() < 0.1, (name, key, np.sort(rel)[-5:])
+        rels.append(rel)
+    u, ur = unc[sel], g['ref_fit_unc'][sel]
+    rel = np.abs(u - ur) / np.abs(ur)
+    assert np.median(rel) < 1e-4 and rel.max() < 0.1, (name, rel.max())
+    return np.concatenate(rels)

@@ -6,7 +6,8 @@ import numpy as np
 import pytest
 import torch
 
-from tests.common import (FIT_CASES, TOL_CHI2, TOL_REL, TOL_VEL_KMS, config_from_golden, load_golden,
+from tests.common import (FIT_CASES, TOL_CHI2, TOL_REL, TOL_VEL_KMS, UNC_CASES, assert_fixture_parity,
+                          assert_uncertainty_parity, config_from_golden, golden_priors, load_golden, optimum_report,
                           parity_report, split_rows)
 
 pytestmark = pytest.mark.gpu
@@ -34,47 +35,47 @@ def _gpu_fit_plain(cfg, cube, theta, v0, b0):
     return {k: v.cpu().numpy() for k, v in res.items()}
 
 
-@pytest.mark.parametrize('name', [c for c in FIT_CASES if c != 'fit_sincgauss_double'])
+@pytest.mark.parametrize('name', FIT_CASES)
 def test_cuda_matches_reference_golden(name):
+    """Every small fixture through the C ABI, every spaxel accounted for (tests.common.assert_fixture_parity): ours is
+    the machine-precision optimum of the reference's objective or a strictly lower converged minimum, and equals the
+    reference's numbers wherever the reference sits on that optimum."""
     g = load_golden(name)
-    cfg = config_from_golden(g)
-    noml = bool(g['noml'])
-    res = _gpu_fit(cfg, g['cube'], g['theta'], None if noml else g['v0'], None if noml else g['b0'])
-    rows, st = res['rows'], res['status']
-    rep = parity_report(rows, g, g['model'], check_broadening=(g['model'] != 'sinc'))
-    if name == 'fit_sinc_noml':
-        conv = rep['dv'] < TOL_VEL_KMS
-        assert conv.sum() >= 2 and (rep['df'][conv] < 5e-3).all() and (rep['dchi'] <= 1e-4 + 0.05 * conv).all()
+    if name == 'fit_sincgauss_double':
+        # BASELINE config 4 from ONE shared prior pair (all the reference's API can express): component search, see
+        # tests/test_hostemu_parity.py::test_hostemu_matches_reference
+        from tests.test_hostemu_parity import multistart_double
+        fit = lambda cfg, v, b: (lambda r: (r['rows'], r['status']))(_gpu_fit_plain(cfg, g['cube'], g['theta'], v, b))
+        rows, st = multistart_double(fit, g)
+        opt = optimum_report(rows, g)
+        assert opt['ok'].all() and opt['lower'].sum() >= 5, (opt['same'], opt['lower'])
+        assert (opt['dchi'] <= 1e-4).all()
         return
-    frac = rep['ok'].mean()
-    if name == 'fit_sincgauss_groups':
-        keep = ~rep['ref_spike']               # where the reference did not collapse a weak line to a zero-width spike
-        assert frac >= 0.75 and keep.sum() >= 0.75 * len(keep) and (rep['dchi'][keep] <= 1e-4).all(), (frac, rep['dchi'])
-    else:
-        assert frac >= 0.95, (name, frac, rep['dv'], rep['db'], rep['df'], rep['dchi'])
-    assert np.nanmedian(rep['dv']) < 0.02 and np.nanmedian(rep['df']) < 2e-4
-    assert ((st >> 16) & 1).all()
+    cfg = config_from_golden(g)
+    v0, b0 = golden_priors(g)
+    res = _gpu_fit(cfg, g['cube'], g['theta'], v0, b0)
+    rows, st = res['rows'], res['status']
+    rep, opt, direct = assert_fixture_parity(name, rows, st, g)
+    floor = {'fit_sinc_noml': 0.25, 'fit_sincgauss_groups': 0.75, 'fit_sincgauss_groups_hi': 0.85}.get(name, 1.0)
+    assert direct.mean() >= floor, (name, direct.mean())
     np.testing.assert_allclose(rep['q']['corr'], g['ref_corr'], rtol=1e-6)
     np.testing.assert_allclose(rep['q']['axis_step'], g['ref_axis_step'], rtol=1e-6)
     # fit_sol layout: amplitude, position, sigma per line + continuum
-    ok = rep['ok']
-    np.testing.assert_allclose(res['fit_sol'][ok][:, 1::3], g['ref_fit_sol'][ok][:, 1::3], rtol=2e-7, atol=3e-3)
+    np.testing.assert_allclose(res['fit_sol'][direct][:, 1::3], g['ref_fit_sol'][direct][:, 1::3], rtol=2e-7, atol=3e-3)
 
 
-@pytest.mark.parametrize('name', ['fit_sincgauss_sn3', 'fit_gaussian_sn3', 'fit_sincgauss_single'])
+@pytest.mark.parametrize('name', UNC_CASES)
 def test_cuda_uncertainties_match_reference(name):
+    """1-sigma errors (FD-stencil Hessian stage) against the reference on every spaxel where the fits agree, incl. the
+    double-component configuration (BASELINE config 4) and the benchmark's nz = 841."""
     g = load_golden(name)
     cfg = config_from_golden(g, uncertainty=True)
-    res = _gpu_fit(cfg, g['cube'], g['theta'], g['v0'], g['b0'])
+    v0, b0 = golden_priors(g)
+    res = _gpu_fit(cfg, g['cube'], g['theta'], v0, b0)
     rep = parity_report(res['rows'], g, g['model'])
-    good = rep['ok'] & (rep['df'] < 1e-4)
-    assert good.sum() >= 0.6 * len(good)
-    for key in ('vels_errors', 'sigmas_errors', 'flux_errors', 'continuum_error'):
-        rel = np.abs(rep['q'][key][good] - g['ref_' + key][good]) / np.abs(g['ref_' + key][good])
-        assert np.median(rel) < 2e-3 and rel.max() < 5e-2, (key, rel)
-    # fit_uncertainties vector itself
-    u, ur = res['fit_unc'][good], g['ref_fit_unc'][good]
-    assert np.median(np.abs(u - ur) / np.abs(ur)) < 2e-3
+    sel = rep['ok']
+    assert sel.mean() >= (0.85 if name == 'fit_sincgauss_groups_hi' else 1.0)
+    assert_uncertainty_parity(name, res['rows'], res['fit_unc'], g, sel)
 
 
 def test_cuda_matches_hostemu_build_of_the_same_source(hostemu):
@@ -217,15 +218,16 @@ def test_host_cube_stream_equals_resident_path():
         stream.run(cube, host_par, host_rows)                                  # device tensor: not a host cube
 
 
-def test_cuda_large_sample_parity_config2():
-    """1000 spaxels of the benchmark configuration against the unmodified reference (north_star: 99.9 % of spaxels
-    within 0.5 km/s, 1e-3 relative broadening / flux, chi2 not worse by more than 1e-4), through the C ABI."""
-    from tests.common import check_large_sample_parity
-    from tests.test_hostemu_parity import _float64_objective_factory
-    g = load_golden('parity_sincgauss_cfg2')
+@pytest.mark.parametrize('name', ['parity_sincgauss_cfg2', 'parity_sincgauss_heldout'])
+def test_cuda_large_sample_parity_config2(name):
+    """1000 spaxels of the benchmark configuration (and 400 held-out ones of another seed) against the unmodified
+    reference and the machine-precision optimum of its objective (north_star: 99.9 % of spaxels within 0.5 km/s, 1e-3
+    relative broadening / flux, chi2 not worse by more than 1e-4), through the C ABI."""
+    from tests.common import check_large_sample_parity, load_tight
+    g = load_golden(name)
     cfg = config_from_golden(g, uncertainty=False)
     res = _gpu_fit(cfg, g['cube'], g['theta'], g['v0'], g['b0'])
-    check_large_sample_parity(res['rows'], res['status'], g, _float64_objective_factory(g))
+    check_large_sample_parity(res['rows'], res['status'], g, load_tight(name))
 
 
 def test_cuda_freeze_mode_matches_reference():

@@ -4,65 +4,78 @@ the derived outputs without a GPU; the GPU tier repeats the same comparison thro
 import numpy as np
 import pytest
 
-from tests.common import FIT_CASES, TOL_VEL_KMS, config_from_golden, load_golden, parity_report, run_hostemu
+from tests.common import (FIT_CASES, TOL_VEL_KMS, UNC_CASES, assert_fixture_parity, assert_uncertainty_parity,
+                          config_from_golden, golden_priors, load_golden, optimum_report, parity_report, run_hostemu,
+                          split_rows)
+
+
+COMPONENT_OFFSETS = (-300.0, -200.0, -100.0, 100.0, 200.0, 300.0)   # luci_b200.luci.COMPONENT_OFFSETS
+
+
+def multistart_double(fit, g):
+    """The API's component search for a double-component fit given ONE shared prior (luci_b200/luci.py): the second
+    velocity group is started at the prior + each offset, the fit with the lowest chi2 wins per spaxel.
+    ``fit(cfg, v0 [n, 2], b0 [n, 2]) -> (rows, status)``."""
+    L = len(g['lines'])
+    cfg = config_from_golden(g, uncertainty=False, prior_groups=True)
+    best = best_st = None
+    for d in COMPONENT_OFFSETS:
+        v = np.stack([g['v0'], g['v0'] + d], axis=1).astype(np.float32)
+        b = np.stack([g['b0'], g['b0']], axis=1).astype(np.float32)
+        rows, st = fit(cfg, v, b)
+        if best is None:
+            best, best_st = rows.copy(), st.copy()
+        else:
+            m = (((st >> 16) & 1) == 1) & (rows[:, 7 * L] < best[:, 7 * L])
+            best[m], best_st[m] = rows[m], st[m]
+    return best, best_st
 
 
 @pytest.mark.parametrize('name', FIT_CASES)
 def test_hostemu_matches_reference(hostemu, name):
     g = load_golden(name)
-    cfg = config_from_golden(g)
-    noml = bool(g['noml'])
-    rows, sol, unc, st = run_hostemu(hostemu, cfg, g['cube'], g['theta'], None if noml else g['v0'],
-                                     None if noml else g['b0'])
-    model = g['model']
-    # sinc: the objective does not depend on sigma; the reference's broadening is an artefact of SLSQP's path
-    # (SURVEY.md A.10-14), so it is compared loosely and reported separately.
-    rep = parity_report(rows, g, model, check_broadening=(model != 'sinc'))
     if name == 'fit_sincgauss_double':
-        # identical priors for both components: a symmetric saddle in the reference (SURVEY.md hard part 7);
-        # the comparison is on the objective reached, see test below
-        pytest.skip('double component with one shared prior is path dependent in the reference')
-    frac = rep['ok'].mean()
-    if name == 'fit_sinc_noml':
-        # public ML_bool=False path: every fit starts at v = 0, where the reference's SLSQP often stalls on the
-        # multimodal sinc objective (2 of 4 here); where it did converge the results agree, elsewhere ours is lower
-        conv = rep['dv'] < TOL_VEL_KMS
-        assert conv.sum() >= 2 and (rep['df'][conv] < 5e-3).all() and (rep['dchi'] <= 1e-4 + 0.05 * conv).all()
+        # BASELINE config 4 started the only way the reference's API can (ONE prior pair for both components): an exactly
+        # symmetric start.  The reference leaves it through the noise of its finite-difference gradient and lands on the
+        # right answer in 2 of these 10 spectra ("the results are not always correct", docs/source/example_double_fit.rst);
+        # the API here searches the second component on a velocity grid.  Every spaxel must be the reference's optimum
+        # or a strictly lower converged minimum of the same objective.
+        fit = lambda cfg, v, b: (lambda r: (r[0], r[3]))(run_hostemu(hostemu, cfg, g['cube'], g['theta'], v, b, want_unc=False))
+        rows, st = multistart_double(fit, g)
+        opt = optimum_report(rows, g)
+        assert opt['ok'].all() and opt['lower'].sum() >= 5, (opt['same'], opt['lower'])
+        assert (opt['dchi'] <= 1e-4).all()
+        vel = split_rows(rows, 6)['velocities']
+        assert (np.abs(vel[:, 5] - vel[:, 0] - 200.0) < 50.0).all()   # the simulated second component at +200 km/s (each snapped to a channel)
         return
-    if name == 'fit_sincgauss_groups':
-        # three independent (velocity, broadening) groups: the weak-line groups are ill-posed at low SNR and
-        # the two optimisers may settle in different local minima; ours must then be the lower one
-        keep = ~rep['ref_spike']               # where the reference did not collapse a weak line to a zero-width spike
-        assert frac >= 0.75 and keep.sum() >= 0.75 * len(keep) and (rep['dchi'][keep] <= 1e-4).all(), (frac, rep['dchi'])
-    else:
-        assert frac >= 0.95, (name, frac, rep['dv'], rep['db'], rep['df'], rep['dchi'])
-    assert np.nanmedian(rep['dv']) < 0.02
-    assert np.nanmedian(rep['df']) < 2e-4
-    assert ((st >> 16) & 1).all()            # every spaxel converged
-    if model == 'sinc' and not noml:
+    cfg = config_from_golden(g)
+    v0, b0 = golden_priors(g)
+    rows, sol, unc, st = run_hostemu(hostemu, cfg, g['cube'], g['theta'], v0, b0)
+    rep, opt, direct = assert_fixture_parity(name, rows, st, g)
+    # how often the direct comparison with the reference is possible at all (it is at its own optimum): documented floor
+    floor = {'fit_sinc_noml': 0.25, 'fit_sincgauss_groups': 0.75, 'fit_sincgauss_groups_hi': 0.85}.get(name, 1.0)
+    assert direct.mean() >= floor, (name, direct.mean())
+    model = g['model']
+    if model == 'sinc' and not bool(g['noml']):
         # sigma is not a parameter of the sinc model: the broadening map returns the prior (the reference returns
         # the prior plus an SLSQP feasibility-restoration drift of 0.1-20 %, which is not a property of the data)
         np.testing.assert_allclose(rep['q']['sigmas'], np.repeat(np.abs(g['b0'])[:, None], 5, axis=1), rtol=1e-6)
     # geometry outputs are exact formulas
     np.testing.assert_allclose(rep['q']['corr'], g['ref_corr'], rtol=1e-6)
     np.testing.assert_allclose(rep['q']['axis_step'], g['ref_axis_step'], rtol=1e-6)
-    np.testing.assert_allclose(rep['q']['continuum'][rep['ok']], g['ref_continuum'][rep['ok']], rtol=2e-3)
+    np.testing.assert_allclose(rep['q']['continuum'][direct], g['ref_continuum'][direct], rtol=2e-3)
 
 
-@pytest.mark.parametrize('name', ['fit_sincgauss_sn3', 'fit_gaussian_sn3', 'fit_sincgauss_single'])
+@pytest.mark.parametrize('name', UNC_CASES)
 def test_hostemu_uncertainties(hostemu, name):
     g = load_golden(name)
     cfg = config_from_golden(g, uncertainty=True)
-    rows, sol, unc, st = run_hostemu(hostemu, cfg, g['cube'], g['theta'], g['v0'], g['b0'])
+    v0, b0 = golden_priors(g)
+    rows, sol, unc, st = run_hostemu(hostemu, cfg, g['cube'], g['theta'], v0, b0)
     rep = parity_report(rows, g, g['model'])
-    good = rep['ok'] & (rep['df'] < 1e-4)    # uncertainties are steep functions of the solution: compare where the
-    assert good.sum() >= 0.6 * len(good)     # two optimisers landed on the same point
-    for key in ('vels_errors', 'sigmas_errors', 'flux_errors', 'continuum_error'):
-        ref = g['ref_' + key][good]
-        mine = rep['q'][key][good]
-        rel = np.abs(mine - ref) / np.abs(ref)
-        assert np.median(rel) < 2e-3, (key, rel)
-        assert rel.max() < 5e-2, (key, rel)
+    sel = rep['ok']                       # every spaxel where the two fits agree (all of them but the reference's run-aways)
+    assert sel.mean() >= (0.85 if name == 'fit_sincgauss_groups_hi' else 1.0)
+    assert_uncertainty_parity(name, rows, unc, g, sel)
 
 
 def test_hostemu_eval_count_is_small(hostemu):
@@ -176,44 +189,16 @@ def test_hostemu_double_component_with_per_group_priors(hostemu):
     assert (ratio < 1 + 1e-4).all() and ratio.min() < 0.7                       # the shared prior stays on the saddle
 
 
-def _float64_objective_factory(g):
-    """Float64 sum of squared residuals of the normalised fit window (the quantity both optimisers minimise, up to
-    the constant noise factor) at our solution and at the reference's."""
-    import warnings
-    from oracle import luci_oracle as O
-
-    def objective(i, theta_full, scale):
-        with warnings.catch_warnings():
-            warnings.simplefilter('ignore')
-            f = O.OracleFit(g['cube'][i].astype(np.float64), g['axis32'], g['model'], g['lines'], [1] * 5, [1] * 5,
-                            theta=float(g['theta'][i]), delta_x=float(g['delta_x']), n_steps=int(g['n_steps']),
-                            zpd_index=0, filter='SN3', nii_cons=True, prior=(float(g['v0'][i]), float(g['b0'][i])))
-        th = np.array(theta_full, dtype=float).copy()
-        th[0:15:3] /= scale
-        th[-1] /= scale
-        m = O.model_sum(g['model'], f.axis_restricted, th, 5, f.sinc_width) + th[-1]
-        return float(np.sum((f.spectrum_restricted_norm - m) ** 2))
-
-    def both(i, rep):
-        from oracle import luci_oracle as O2
-        q, ours = rep['q'], np.zeros(16)
-        for k, line in enumerate(g['lines']):
-            p = 1e7 / (O2.LINE_DICT[line] * (1 + q['velocities'][i][k] / 299792.0))
-            ours[3 * k], ours[3 * k + 1], ours[3 * k + 2] = q['amplitudes'][i][k], p, p * q['sigmas'][i][k] / 299792.0
-        ours[-1] = q['continuum'][i]
-        return objective(i, ours, g['ref_scale'][i]), objective(i, g['ref_fit_sol'][i], g['ref_scale'][i])
-
-    return both
-
-
-def test_hostemu_large_sample_parity_config2(hostemu):
+@pytest.mark.parametrize('name', ['parity_sincgauss_cfg2', 'parity_sincgauss_heldout'])
+def test_hostemu_large_sample_parity_config2(hostemu, name):
     """1000 spaxels of the benchmark configuration (nz = 841, 5-line sincgauss, ties + [NII] ratio) against the
-    unmodified reference: the north_star's 99.9 % criterion."""
-    from tests.common import check_large_sample_parity
-    g = load_golden('parity_sincgauss_cfg2')
+    unmodified reference and against the machine-precision optimum of its objective: the north_star's 99.9 % criterion.
+    The second fixture (400 spaxels, another seed) is held out: no constant of the device code was tuned on it."""
+    from tests.common import check_large_sample_parity, load_tight
+    g = load_golden(name)
     cfg = config_from_golden(g, uncertainty=False)
     rows, sol, unc, st = run_hostemu(hostemu, cfg, g['cube'], g['theta'], g['v0'], g['b0'], want_unc=False)
-    rep = check_large_sample_parity(rows, st, g, _float64_objective_factory(g))
+    check_large_sample_parity(rows, st, g, load_tight(name))
     assert (((st >> 8) & 0xff).mean()) < 7
 
 

@@ -45,12 +45,12 @@ def test_hostemu_prior_lands_in_the_basin_of_the_reference_optimum(hostemu, name
 def test_hostemu_fits_from_estimated_prior_meet_the_parity_bar(hostemu):
     """1000 spaxels of the benchmark configuration: fits started from the estimated prior reach the reference's optimum
     (north_star tolerances) and need fewer evaluations than from the CNN-like prior of the fixture (truth + N(0, 15 km/s))."""
-    from tests.test_hostemu_parity import _float64_objective_factory
+    from tests.common import load_tight
     g = load_golden('parity_sincgauss_cfg2')
     cfg = config_from_golden(g, uncertainty=False)
     vel, broad = hostemu_prior(hostemu, cfg, g['cube'], g['theta'])
     rows, sol, unc, st = run_hostemu(hostemu, cfg, g['cube'], g['theta'], vel, broad, want_unc=False)
-    check_large_sample_parity(rows, st, g, _float64_objective_factory(g))
+    check_large_sample_parity(rows, st, g, load_tight('parity_sincgauss_cfg2'))
     assert ((st >> 8) & 0xff).mean() < 5.5
 
 

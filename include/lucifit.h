@@ -44,9 +44,11 @@ enum { LUCIFIT_GAUSSIAN = 0, LUCIFIT_SINC = 1, LUCIFIT_SINCGAUSS = 2 };
 #define LUCIFIT_ST_MAXITER (1 << 17)
 #define LUCIFIT_ST_BOUND (1 << 18)       /* a parameter sits on its box (LuciFit.py:614-633, 539-541) */
 #define LUCIFIT_ST_SINGULAR (1 << 19)
-#define LUCIFIT_ST_NAN_INPUT (1 << 20)   /* spectrum contains NaN: zeros are returned (cf. LuciBase.py:358-360, 393-405) */
+#define LUCIFIT_ST_NAN_INPUT (1 << 20)   /* every sample is NaN: zeros are returned (LuciBase.py:365, 393-405) */
 #define LUCIFIT_ST_MASKED (1 << 21)
 #define LUCIFIT_ST_BAD_NORM (1 << 22)    /* max(spectrum) <= 0 */
+#define LUCIFIT_ST_NAN_SAMPLES (1 << 24) /* informational: NaN samples were left out of the fit, the rest was fitted like the
+                                            reference's row worker does after sky[~isnan(sky)] (LuciBase.py:358-360) */
 
 /* Per-call constants (HOST memory).  Mirrors the arguments of Fit.__init__ (LUCI/LuciFit.py:49-57) that do not
  * vary from spaxel to spaxel. */

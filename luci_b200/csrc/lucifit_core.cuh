@@ -36,7 +36,7 @@
 
 #define LF_MAX_LINES 8
 #define LF_C_KMS 299792.0f        /* LuciFit.py:26 (integer km/s in the reference) */
-#define LF_MAX_CONT_WIN 256       /* samples of the continuum window handled by the clip */
+#define LF_MAX_CONT_WIN 1024      /* longest continuum window (samples) the clip sorts in per-warp shared memory; longer ones are refused */
 #define LF_PREP_MLP 9             /* loads in flight per lane while the prep stage reads a spectrum */
 #define LF_REFINE_HALF 6          /* prior-velocity refinement: grid of 2*6+1 points ... */
 #define LF_REFINE_STEP 6.0f        /* ... 6 km/s apart (+-36 km/s around the prior) */
@@ -49,18 +49,35 @@ static_assert(2 * LF_REFINE_HALF + 1 <= 16, "the refinement scores live in the s
 #endif
 /* LM acceptance / stopping constants (tuned on tests/golden/parity_sincgauss_cfg2.npz: 1000 reference fits) */
 #define LF_TUNE_SLACK_PRED 1e-4   /* below this predicted relative decrease an FP32-noise-sized rise of sum r^2 is accepted */
+#ifndef LF_TUNE_NOISE_PRED
+#define LF_TUNE_NOISE_PRED 1e-8
+#endif
+/* LF_TUNE_NOISE_PRED: below this predicted relative decrease (the convergence tolerance itself) the measured gain ratio is the
+   FP32 rounding of the residuals (3e-8 of sum r^2 observed) and no longer steers the damping; above it it must -- Gauss-Newton on
+   a line group lost in the noise oscillates without the damping the gain ratio asks for (fit_sincgauss_groups[9]) */
 #define LF_TUNE_SLACK 4e-6        /* ... of at most this relative size */
 #define LF_TUNE_REJ_CONV 1e-5     /* a rejected step predicted to gain less than this means converged */
 #define LF_CONV_CONTRACTION 0.05f /* fast contraction: the predicted gain of a step is at most this fraction of the previous step's */
 #define LF_CONV_PRED_CAP 1e-5     /* ... and itself below this fraction of sum r^2: only then is the next gain extrapolated */
 #define LF_CONV_REMAIN 5e-4f      /* estimated parameter error left after the final (unevaluated) step: half the 1e-3 parity bar */
+#ifndef LF_CONV_FLAT
+#define LF_CONV_FLAT 1e-2         /* predicted gain below this fraction of the tolerance: the parameter test is waived */
+#endif
+#ifndef LF_CONV_AMP_FLOOR
+#define LF_CONV_AMP_FLOOR 1e-3f    /* amplitudes (units of the window maximum) below this are compared absolutely against it in the step-size test */
+#endif
 #define LF_CONV_RHO0 0.5f         /* contraction rate assumed when the previous step was damped / rejected (no measurement) */
 
 // status word: bits 0-7 accepted LM iterations, bits 8-15 model evaluations, bits 16.. flags
 enum {
     LF_ST_CONVERGED = 1 << 16, LF_ST_MAXITER = 1 << 17, LF_ST_BOUND = 1 << 18, LF_ST_SINGULAR = 1 << 19,
-    LF_ST_NAN_INPUT = 1 << 20, LF_ST_MASKED = 1 << 21, LF_ST_BAD_NORM = 1 << 22, LF_ST_NAN_RESULT = 1 << 23
+    LF_ST_NAN_INPUT = 1 << 20, LF_ST_MASKED = 1 << 21, LF_ST_BAD_NORM = 1 << 22, LF_ST_NAN_RESULT = 1 << 23,
+    LF_ST_NAN_SAMPLES = 1 << 24   /* some samples were NaN and were left out of the fit (LuciBase.py:358-360) */
 };
+// bits 25-30: number of trailing samples of the fit window the reference's window loses when the sample at its upper
+// edge is NaN and the nearest valid sample lies inside (internal to the stage kernels, cleared in the output word)
+#define LF_ST_CUT_SHIFT 25
+#define LF_ST_CUT_MASK (63 << LF_ST_CUT_SHIFT)
 #define LF_ST_BADMASK (LF_ST_NAN_INPUT | LF_ST_MASKED | LF_ST_BAD_NORM)
 
 // per-spaxel state record (float words; the record starts 8-byte aligned and its stride is even)
@@ -169,6 +186,20 @@ LF_CORE int lf_nearest_axis(const double* axis, int nz, double pos)
     return (fabs(axis[lo - 1] - pos) <= fabs(axis[lo] - pos)) ? lo - 1 : lo;
 }
 
+// Where the reference's np.argmin(|axis - target|) lands once the NaN samples have been removed from spectrum and axis
+// (LuciBase.py:358-360): the valid sample nearest to `target`, given the nearest sample `idx` of the full axis.
+template <typename IsNan>
+LF_CORE int lf_valid_near(const double* axis, int nz, int idx, double target, IsNan is_nan)
+{
+    if (!is_nan(idx)) return idx;
+    int l = idx - 1, r = idx + 1;
+    while (l >= 0 && is_nan(l)) --l;
+    while (r < nz && is_nan(r)) ++r;
+    if (l < 0) return r < nz ? r : idx;
+    if (r >= nz) return l;
+    return (fabs(axis[l] - target) <= fabs(axis[r] - target)) ? l : r;
+}
+
 // In-place ascending bitonic sort of v[0..npad) (npad a power of two; pad with +inf), all lanes cooperate.
 template <int LANES>
 LF_CORE void lf_sort(const LfWarp<LANES>& w, float* v, int npad)
@@ -258,11 +289,18 @@ LF_CORE double lf_cont_estimate(const LfWarp<LANES>& w, const float* spec, int l
                                 float* sv, int npad)
 {
     int n = hi - lo;
-    if (n > LF_MAX_CONT_WIN) n = LF_MAX_CONT_WIN;
+    if (n > npad) n = npad;                            // lf_make_plan sizes npad for the whole window (<= LF_MAX_CONT_WIN)
     if (n <= 0) return 0.0;
     w.sync();
-    for (int i = w.lane; i < npad; i += LANES) sv[i] = i < n ? spec[lo + i] : INFINITY;
+    int n_nan = 0;
+    for (int i = w.lane; i < npad; i += LANES) {
+        float v = i < n ? spec[lo + i] : INFINITY;
+        if (v != v) { v = INFINITY; ++n_nan; }         // NaN samples are not part of the spectrum (LuciBase.py:358-360)
+        sv[i] = v;
+    }
+    n -= w.sum(n_nan);
     w.sync();
+    if (n <= 0) return 0.0;
     lf_sort(w, sv, npad);
     int a = 0, m = n;
 #pragma unroll 1
@@ -518,11 +556,12 @@ LF_CORE void lf_eval(const LfCfg& cfg, const LfWarp<LANES>& w, const float* xo, 
     const bool tie = wk.tie->active != 0;
     for (int n0 = 0; n0 < nfit; n0 += LANES) {
         const int n = n0 + w.lane;
-        const bool live = n < nfit;
-        const float x = live ? xo[n] : 0.0f;
-        const float yn = live ? wk.yw[n] : 0.0f;
+        const bool inwin = n < nfit;
+        const float x = inwin ? xo[n] : 0.0f;
+        const float yn = inwin ? wk.yw[n] : NAN;
+        const bool live = yn == yn;                       // NaN samples are not part of the fit (LuciBase.py:358-360)
         float S = 0.0f, C = 1.0f;
-        if (MODEL != LF_GAUSSIAN && live) { S = wk.sw[n]; C = wk.cw[n]; }
+        if (MODEL != LF_GAUSSIAN && inwin) { S = wk.sw[n]; C = wk.cw[n]; }
         float Jv[NV], Js[NS];
 #pragma unroll
         for (int g = 0; g < NV; ++g) Jv[g] = 0.0f;
@@ -747,28 +786,50 @@ LF_CORE void lf_stage_prep(const LfCfg& cfg, const LfWarp<LANES>& w, const float
     smax = w.max(smax); wmax = w.max(wmax); tmax = w.max(tmax);
     nan_ct = w.sum(nan_ct);
     w.sync();
+    // NaN samples are dropped like the reference's row worker does (LuciBase.py:358-360: sky[good], axis[good]): every
+    // reduction below skips them and the later stages leave them out of the sums; a spectrum with nothing left is unusable
     int bad = 0;
-    if (nan_ct > 0) bad |= LF_ST_NAN_INPUT;
+    if (nan_ct >= nz) bad |= LF_ST_NAN_INPUT;
     if (!(smax > 0.0f) || !(wmax > 0.0f) || !isfinite(smax)) bad |= LF_ST_BAD_NORM;
     if (bad) {                                         // reference returns zeros for unusable spectra
         if (w.lane == 0) reinterpret_cast<int*>(state)[LF_SO_STATUS] = bad;
         return;
     }
+    // window edges: argmin over the axis WITHOUT its NaN samples (only differs when an edge sample itself is NaN)
+    int noise_lo = cfg.noise_lo, noise_hi = cfg.noise_hi, cont_lo = cfg.cont_lo, cont_hi = cfg.cont_hi, fit_cut = 0;
+    if (nan_ct > 0) {
+        auto is_nan = [&](int j) { return spec[j] != spec[j]; };
+        auto edge = [&](int idx) { const int j = idx < nz ? idx : nz - 1; return lf_valid_near(cfg.axis, nz, j, cfg.axis[j], is_nan); };
+        noise_lo = edge(cfg.noise_lo); noise_hi = edge(cfg.noise_hi);
+        cont_lo = edge(cfg.cont_lo); cont_hi = edge(cfg.cont_hi);
+        const int fh = edge(cfg.fit_hi);
+        if (fh < cfg.fit_hi) { fit_cut = cfg.fit_hi - fh; if (fit_cut > 63) fit_cut = 63; }
+        if (fit_cut > 0) {                              // the window maximum is taken over the reference's window
+            wmax = -INFINITY;
+            for (int i = cfg.fit_lo + w.lane; i < cfg.fit_hi - fit_cut; i += LANES) wmax = fmaxf(wmax, spec[i]);
+            wmax = w.max(wmax);
+            if (!(wmax > 0.0f)) {
+                if (w.lane == 0) reinterpret_cast<int*>(state)[LF_SO_STATUS] = LF_ST_BAD_NORM;
+                return;
+            }
+        }
+    }
     // noise: population std of spectrum_normalized over the noise window (LuciFit.py:327-331)
     double noise;
     {
-        int n = cfg.noise_hi - cfg.noise_lo;
+        int n = 0;
         double s1 = 0.0;
-        for (int i = cfg.noise_lo + w.lane; i < cfg.noise_hi; i += LANES) s1 += (double)spec[i];
+        for (int i = noise_lo + w.lane; i < noise_hi; i += LANES) { const float v = spec[i]; if (v == v) { s1 += (double)v; ++n; } }
         s1 = w.sum(s1);
+        n = w.sum(n);
         double mean = n > 0 ? s1 / n : 0.0;
         double s2 = 0.0;
-        for (int i = cfg.noise_lo + w.lane; i < cfg.noise_hi; i += LANES) { double d = (double)spec[i] - mean; s2 += d * d; }
+        for (int i = noise_lo + w.lane; i < noise_hi; i += LANES) { const float v = spec[i]; if (v == v) { double d = (double)v - mean; s2 += d * d; } }
         s2 = w.sum(s2);
         noise = n > 0 ? sqrt(s2 / n) / (double)smax : NAN;
     }
     // sigma_level: 1 in the free fit (LuciFit.py:661), 3 in the freeze branch (:690)
-    const double cont0 = lf_cont_estimate(w, spec, cfg.cont_lo, cfg.cont_hi, cfg.freeze ? 3.0 : 1.0, wk.sortv, wk.npad) / (double)smax;
+    const double cont0 = lf_cont_estimate(w, spec, cont_lo, cont_hi, cfg.freeze ? 3.0 : 1.0, wk.sortv, wk.npad) / (double)smax;
     // scale: ML-prior path max(spectrum_restricted) * max(spectrum_T) ; plain path max(spectrum_T)
     const double scale = cfg.ml_scale ? ((double)wmax / (double)smax) * (double)tmax : (double)tmax;
     const double ct = fabs(cos((double)theta_deg * 0.017453292519943295));
@@ -792,6 +853,7 @@ LF_CORE void lf_stage_prep(const LfCfg& cfg, const LfWarp<LANES>& w, const float
             amp = -INFINITY;
             for (int d = -5; d <= 5; ++d) { int i = ind + d; if (i < 0) i += nz; amp = fmaxf(amp, spec[i]); }
         }
+        if (!(amp == amp) || amp == -INFINITY) amp = 0.0f;             // every sample around the line is NaN
         th[k] = (float)((double)amp / (double)smax - cont0);
     }
     // Start of the velocity: the prior (one value for all lines) is moved to the maximum of a matched filter within
@@ -821,7 +883,7 @@ LF_CORE void lf_stage_prep(const LfCfg& cfg, const LfWarp<LANES>& w, const float
                     const float f = t - floorf(t);
                     const float a = 0.25f * spec[i - 1] + 0.5f * spec[i] + 0.25f * spec[i + 1];
                     const float b = 0.25f * spec[i] + 0.5f * spec[i + 1] + 0.25f * spec[i + 2];
-                    const float val = fmaxf(a + f * (b - a) - contr, 0.0f);
+                    const float val = fmaxf(a + f * (b - a) - contr, 0.0f);          // (fmaxf drops a NaN)
                     acc += val * val;
                 }
                 wk.sortv[j] = acc;
@@ -859,7 +921,7 @@ LF_CORE void lf_stage_prep(const LfCfg& cfg, const LfWarp<LANES>& w, const float
         double* sd = reinterpret_cast<double*>(state);
         sd[LF_SO_NOISE / 2] = noise; sd[LF_SO_SCALE / 2] = scale; sd[LF_SO_CORR / 2] = corr; sd[LF_SO_SINCW / 2] = sinc_w;
         state[LF_SO_INVW] = 1.0f / wmax;
-        reinterpret_cast<int*>(state)[LF_SO_STATUS] = 0;
+        reinterpret_cast<int*>(state)[LF_SO_STATUS] = nan_ct > 0 ? (LF_ST_NAN_SAMPLES | (fit_cut << LF_ST_CUT_SHIFT)) : 0;
     }
     w.sync();
 }
@@ -868,13 +930,13 @@ LF_CORE void lf_stage_prep(const LfCfg& cfg, const LfWarp<LANES>& w, const float
 //   yw[n] = (cube[fit_lo + n] - bkg) * mul, optionally divided by the transmission (the `out` stage).
 template <int MODEL, int LANES>
 LF_CORE void lf_stage_window(const LfCfg& cfg, const LfWarp<LANES>& w, const float* xo, const float* gspec, float mul,
-                             bool use_trans, double sinc_w, const LfWork& wk)
+                             bool use_trans, double sinc_w, const LfWork& wk, int fit_cut)
 {
     const int nfit = cfg.fit_hi - cfg.fit_lo;
     w.sync();
     for (int n = w.lane; n < nfit; n += LANES) {
         int i = cfg.fit_lo + n;
-        float s = gspec[i];
+        float s = n < nfit - fit_cut ? gspec[i] : NAN;        // samples beyond the reference's window count as dropped
         if (cfg.bkg) s -= cfg.bkg[i];
         if (use_trans && cfg.trans) { float t = cfg.trans[i]; if (t > 0.5f) s = s / t; }
         wk.yw[n] = s * mul;
@@ -899,7 +961,8 @@ LF_CORE void lf_stage_lm(const LfCfg& cfg, const LfWarp<LANES>& w, const float* 
     const float sinc_w = (float)sinc_w_d;
     const double inv_w = 1.0 / sinc_w_d;
     const int nfit = cfg.fit_hi - cfg.fit_lo;
-    lf_stage_window<MODEL, LANES>(cfg, w, xo, gspec, state[LF_SO_INVW], false, sinc_w_d, wk);
+    lf_stage_window<MODEL, LANES>(cfg, w, xo, gspec, state[LF_SO_INVW], false, sinc_w_d, wk,
+                                  (status & LF_ST_CUT_MASK) >> LF_ST_CUT_SHIFT);
     float* th = wk.thb;
     float* tht = wk.thb + P;
     float* lo = wk.thb + 2 * P;
@@ -912,7 +975,7 @@ LF_CORE void lf_stage_lm(const LfCfg& cfg, const LfWarp<LANES>& w, const float* 
         for (int j = 0; j < P; ++j) { th[j] = fminf(fmaxf(th[j], lo[j]), hi[j]); tht[j] = th[j]; }
     }
     w.sync();
-    int evals = 0, iters = 0, flags = 0, tries = 0;
+    int evals = 0, iters = 0, flags = status & (LF_ST_NAN_SAMPLES | LF_ST_CUT_MASK), tries = 0;
     float lam = LF_LM_LAM0, nu = 2.0f, pred = 0.0f, pred_prev = 0.0f;
     double chi2 = 0.0;
     const double ftol = (double)cfg.ftol;
@@ -935,6 +998,9 @@ LF_CORE void lf_stage_lm(const LfCfg& cfg, const LfWarp<LANES>& w, const float* 
             if (finite && chi2t <= chi2 + slack) {
                 double act = chi2 - chi2t;
                 float rho = pred > 0.0f ? (float)(act / (double)pred) : 1.0f;
+                // below the FP32 resolution of sum r^2 the measured gain is rounding noise: a negative one must not
+                // raise the damping (that shortens the remaining steps and fakes convergence)
+                if ((double)pred <= LF_TUNE_NOISE_PRED * chi2) rho = 1.0f;
                 float f = 1.0f - (2.0f * rho - 1.0f) * (2.0f * rho - 1.0f) * (2.0f * rho - 1.0f);
                 lam *= fmaxf(LF_LM_DEC, f);
                 lam = fmaxf(lam, 1e-7f);
@@ -984,7 +1050,7 @@ LF_CORE void lf_stage_lm(const LfCfg& cfg, const LfWarp<LANES>& w, const float* 
             for (int j = 0; j < P; ++j) {
                 float tj = th[j];
                 tn[j] = fminf(fmaxf(tj + delta[j], lo[j]), hi[j]);
-                float sc = (j >= D::IV && j < D::IS) ? 1.0f : fmaxf(fabsf(tj), 1e-3f);   // velocities: km/s absolute
+                float sc = (j >= D::IV && j < D::IS) ? 1.0f : fmaxf(fabsf(tj), LF_CONV_AMP_FLOOR);   // velocities: km/s absolute
                 rel = fmaxf(rel, fabsf(tn[j] - tj) * LF_RCP(sc));
             }
             w.sync();
@@ -997,6 +1063,11 @@ LF_CORE void lf_stage_lm(const LfCfg& cfg, const LfWarp<LANES>& w, const float* 
             // the second predicted to gain at most LF_CONV_CONTRACTION of the first) that is extrapolated as
             // pred^2 / pred_prev, and the step is the last one once the extrapolation is a tenth of the tolerance.
             // Slowly contracting fits (flat valleys, blended lines) never qualify and run down to the tolerance itself.
+#ifdef LF_TRACE
+            printf("it %d ev %d chi2 %.10e pred %.3e pred/chi2 %.3e rel %.3e lam %.2e tries %d | th", iters, evals, chi2, pred, pred / chi2, rel, lam, tries);
+            for (int j = 0; j < P; ++j) printf(" %.7g", tn[j]);
+            printf("\n");
+#endif
             bool conv = (double)pred <= ftol * chi2;
             if (!conv && tries == 0 && pred_prev > 0.0f && pred <= LF_CONV_CONTRACTION * pred_prev &&
                 (double)pred <= LF_CONV_PRED_CAP * chi2)
@@ -1011,7 +1082,10 @@ LF_CORE void lf_stage_lm(const LfCfg& cfg, const LfWarp<LANES>& w, const float* 
                 // LF_CONV_REMAIN as well.
                 float rho = (tries == 0 && pred_prev > 0.0f) ? sqrtf(pred / pred_prev) : LF_CONV_RHO0;
                 rho = fminf(rho, 0.9f);
-                conv = rel * rho < LF_CONV_REMAIN * (1.0f - rho);
+                // ... unless the predicted gain is already LF_CONV_FLAT times below the tolerance: a direction that flat
+                // (the width of a line group lost in the noise) is not determined by the data to 1e-3, iterating on
+                // would only follow the FP32 rounding of the residuals
+                conv = rel * rho < LF_CONV_REMAIN * (1.0f - rho) || (double)pred <= LF_CONV_FLAT * ftol * chi2;
             }
             if (conv && rel < 1e-2f) {
                 if (w.lane == 0) {
@@ -1093,7 +1167,8 @@ LF_CORE void lf_stage_out(const LfCfg& cfg, const LfWarp<LANES>& w, const float*
     const double inv_w = 1.0 / sinc_w_d;
     const float* th = state + LF_SO_TH;
     const int nfit = cfg.fit_hi - cfg.fit_lo;
-    lf_stage_window<MODEL, LANES>(cfg, w, xo, gspec, (float)(1.0 / scale), true, sinc_w_d, wk);
+    lf_stage_window<MODEL, LANES>(cfg, w, xo, gspec, (float)(1.0 / scale), true, sinc_w_d, wk,
+                                  (status & LF_ST_CUT_MASK) >> LF_ST_CUT_SHIFT);
     double* apd = wk.apd;
     lf_expand<MODEL, L, NV, NS, LANES>(cfg, w, sinc_w, th, apd);
     const double cont = (double)th[D::IC];
@@ -1102,6 +1177,12 @@ LF_CORE void lf_stage_out(const LfCfg& cfg, const LfWarp<LANES>& w, const float*
     LfLineX* sl = wk.lines;
     for (int k = w.lane; k < L; k += LANES) {
         int idx = lf_nearest_axis(cfg.axis, cfg.nz, apd[L + k]);
+        if (status & LF_ST_NAN_SAMPLES)                 // Model.plot snaps on the axis the NaN samples were removed from
+            idx = lf_valid_near(cfg.axis, cfg.nz, idx, apd[L + k], [&](int j) {
+                float v = gspec[j];
+                if (cfg.bkg) v -= cfg.bkg[j];
+                return v != v;
+            });
         LfLineX x;
         float pps, ppl;
         lf_split(cfg.axis[idx] - cfg.x_ref, pps, ppl);
@@ -1116,6 +1197,7 @@ LF_CORE void lf_stage_out(const LfCfg& cfg, const LfWarp<LANES>& w, const float*
     w.sync();
     const float iw = 1.0f / sinc_w;
     double S = 0.0;
+    int nvalid = 0;
     for (int n0 = 0; n0 < nfit; n0 += LANES) {
         const int n = n0 + w.lane;
         const bool live = n < nfit;
@@ -1146,12 +1228,13 @@ LF_CORE void lf_stage_out(const LfCfg& cfg, const LfWarp<LANES>& w, const float*
             m += X.aeff * g;
         }
         if (live) {
-            float r = wk.yw[n] - m;
-            S += (double)r * (double)r;
+            const float r = wk.yw[n] - m;
+            if (r == r) { S += (double)r * (double)r; ++nvalid; }       // NaN samples were dropped (LuciBase.py:358-360)
         }
     }
     S = w.sum(S);
-    const double chi2 = S / (noise * (double)(nfit - (3 * L + 1)));
+    nvalid = w.sum(nvalid);
+    const double chi2 = S / (noise * (double)(nvalid - (3 * L + 1)));
     const double FWHM_COEFF = 2.3548200450309493;
     const double SQ2PI = 2.5066282746310002, PI = 3.141592653589793;
     for (int k = w.lane; k < L; k += LANES) {
@@ -1198,7 +1281,7 @@ LF_CORE void lf_stage_out(const LfCfg& cfg, const LfWarp<LANES>& w, const float*
         out_row[7 * L + 3] = (float)(cont * scale);
         out_row[7 * L + 4] = (float)(unc ? unc[3 * L] * scale : 0.0);
         if (out_sol) out_sol[3 * L] = (float)(cont * scale);
-        *out_status = status;
+        *out_status = status & ~LF_ST_CUT_MASK;
     }
     if (out_unc) {
         for (int j = w.lane; j < 3 * L + 1; j += LANES) {
@@ -1250,6 +1333,7 @@ LF_CORE void lf_stage_unc(const LfCfg& cfg, const LfWarp<LANES>& w, const float*
     // the chunk is reached (the next chunk's data are requested one chunk ahead) instead of being staged for the whole
     // window: 3 nfit floats of per-warp shared memory less, which is what limits the resident warps of this stage.
     const float invw_norm = state[LF_SO_INVW];
+    const int nlive = nfit - ((status & LF_ST_CUT_MASK) >> LF_ST_CUT_SHIFT);   // the reference's window (see lf_stage_prep)
     double* apd = wk.apd;
     lf_expand<MODEL, L, NV, NS, LANES>(cfg, w, sinc_w, th, apd);
     // line set-ups of all variants, built lane-parallel
@@ -1293,8 +1377,9 @@ LF_CORE void lf_stage_unc(const LfCfg& cfg, const LfWarp<LANES>& w, const float*
     }
     for (int n0 = 0; n0 < nfit; n0 += LANES) {
         const int n = n0 + w.lane;
-        const bool live = n < nfit;
-        const float x = live ? xo[n] : 0.0f;
+        const bool inwin = n < nfit;
+        const bool live = n < nlive && (y_ahead == y_ahead);   // NaN samples are not part of the objective (LuciBase.py:358-360)
+        const float x = inwin ? xo[n] : 0.0f;
         const float yn = live ? y_ahead * invw_norm : 0.0f;
         if (n + LANES < nfit) {
             const int i = cfg.fit_lo + n + LANES;
@@ -1302,7 +1387,7 @@ LF_CORE void lf_stage_unc(const LfCfg& cfg, const LfWarp<LANES>& w, const float*
             if (cfg.bkg) y_ahead -= cfg.bkg[i];
         }
         float Sx = 0.0f, Cx = 1.0f;
-        if (MODEL != LF_GAUSSIAN && live) lf_phase((double)x * inv_w, Sx, Cx);
+        if (MODEL != LF_GAUSSIAN && inwin) lf_phase((double)x * inv_w, Sx, Cx);
         float* trow = tile + w.lane * STRIDE;
         // pass 1: model value at the solution (residual r0) and the unit profiles g0
         float m = cont;

@@ -111,6 +111,8 @@ static inline std::string lf_make_plan(const lucifit_config* c, LfPlan& pl, int 
         return "fit window must hold more than 3L+1 samples";
     if (!(c->noise_lo >= 0 && c->noise_hi <= c->nz && c->noise_lo <= c->noise_hi)) return "bad noise window";
     if (!(c->cont_lo >= 0 && c->cont_hi <= c->nz && c->cont_lo <= c->cont_hi)) return "bad continuum window";
+    if (c->cont_hi - c->cont_lo > LF_MAX_CONT_WIN)
+        return "continuum window longer than 1024 samples (LuciFit.py:450-482 clips the whole window; it is not truncated here)";
     if (!(c->step_nm > 0) || !(c->n_steps - c->zpd_index > 0)) return "STEP and (STEPNB - ZPDINDEX) must be positive";
     memset(&pl.dev, 0, sizeof(pl.dev));
     LfCfg& d = pl.dev;

@@ -38,25 +38,30 @@ LF_CORE void lf_estimate_prior(const LfPriorCfg& c, const LfWarp<LANES>& w, cons
                                float* z, float* sm, float* score, float* vel_out, float* broad_out)
 {
     const int nfit = c.nfit;
-    int bad = 0;
+    int bad = 0, nvalid = 0;
     float s1 = 0.0f;
     w.sync();
     for (int n = w.lane; n < nfit; n += LANES) {
         float s = gspec[c.fit_lo + n];
         if (c.bkg) s -= c.bkg[c.fit_lo + n];
-        if (!(s == s) || isinf(s)) { bad = 1; s = 0.0f; }
-        z[n] = s;
-        s1 += s;
+        if (isinf(s)) { bad = 1; s = 0.0f; }
+        z[n] = s;                                      // a NaN sample stays NaN until the window mean is known
+        if (s == s) { s1 += s; ++nvalid; }
     }
     bad = w.any(bad != 0) ? 1 : 0;
+    nvalid = w.sum(nvalid);
     w.sync();
-    if (bad) {
+    if (bad || nvalid < 8) {
         if (w.lane == 0) { *vel_out = 0.0f; *broad_out = 0.0f; }
         return;
     }
     // continuum: mean of the window after three rounds of clipping about the running mean (the lines are a small
     // fraction of the window; 1.5 sigma first -- the spread still contains them --, then 2 sigma twice)
-    float mu = w.sum(s1) / (float)nfit, sd;
+    float mu = w.sum(s1) / (float)nvalid, sd;
+    if (nvalid < nfit) {                               // NaN samples (dropped by the fit, LuciBase.py:358-360) sit at the mean
+        for (int n = w.lane; n < nfit; n += LANES) if (z[n] != z[n]) z[n] = mu;
+        w.sync();
+    }
     {
         float s2 = 0.0f;
         for (int n = w.lane; n < nfit; n += LANES) { const float d = z[n] - mu; s2 += d * d; }

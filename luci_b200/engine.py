@@ -357,7 +357,7 @@ def status_summary(status):
 
 def _capi_flags():
     return {'CONVERGED': 1 << 16, 'MAXITER': 1 << 17, 'BOUND': 1 << 18, 'SINGULAR': 1 << 19, 'NAN_INPUT': 1 << 20,
-            'MASKED': 1 << 21, 'BAD_NORM': 1 << 22}
+            'MASKED': 1 << 21, 'BAD_NORM': 1 << 22, 'NAN_SAMPLES': 1 << 24}
 
 
 def peak_probe(device, mode, iters=4096, blocks_per_sm=8):

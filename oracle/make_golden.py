@@ -70,6 +70,10 @@ CASES = {
     # uncertainties (hessianComp, LuciUtility.py:409-434) at the benchmark's spectral length nz = 841
     'unc_sincgauss_cfg2': dict(filter='SN3', R=5917, lines=SN3, model='sincgauss', vel_rel=[1] * 5,
                                sigma_rel=[1] * 5, n=32, unc=True, broad=(25, 60), seed=115),
+    # NaN channels: the row worker drops them and fits the rest (LuciBase.py:358-360); samples are knocked out inside
+    # the fit, noise and continuum windows, next to a line core and as a block
+    'fit_sincgauss_nan': dict(filter='SN3', R=5000, lines=SN3, model='sincgauss', vel_rel=[1] * 5, sigma_rel=[1] * 5,
+                              n=16, unc=True, broad=(25, 60), seed=117, nan=True, snr=(20, 100)),
     # HELD-OUT sample of the same configuration (different seed): thresholds of the device code are never tuned on it
     'parity_sincgauss_heldout': dict(filter='SN3', R=5917, lines=SN3, model='sincgauss', vel_rel=[1] * 5,
                                      sigma_rel=[1] * 5, n=400, unc=False, broad=(25, 60), seed=2718),
@@ -123,6 +127,22 @@ def build_inputs(case):
             b0.append(abs(bfit * (1 + rng.normal(0, 0.15))))
     cube = np.stack(rows)
     extra = {}
+    if case.get('nan'):
+        ax = np.asarray(axis, dtype=np.float64)
+        inwin = lambda lo, hi: np.flatnonzero((ax > lo) & (ax < hi))
+        cores = [1e7 / 656.28, 1e7 / 658.341, 1e7 / 654.803, 1e7 / 671.647, 1e7 / 673.085]
+        far_from_cores = np.array([np.min(np.abs(ax[j] - np.array(cores))) > 12.0 for j in range(len(ax))])
+        fitw = np.array([j for j in inwin(14760, 15390) if far_from_cores[j]])
+        for i in range(n):
+            idx = list(rng.choice(fitw, 3, replace=False)) + list(rng.choice(inwin(15602, 15800), 2, replace=False)) \
+                + list(rng.choice(inwin(14855, 14945), 1)) + list(rng.choice(inwin(14000, 14500), 2, replace=False))
+            if i % 4 == 1:                            # a block of four consecutive samples in the fit window
+                j0 = int(rng.choice(fitw[:-8]))
+                idx += [j0, j0 + 1, j0 + 2, j0 + 3]
+            if i % 4 == 2:                            # next to the Halpha core (two samples off the expected centre)
+                pos = 1e7 / (656.28 * (1 + float(v0[i]) / 299792.0))
+                idx += [int(np.argmin(np.abs(ax - pos))) + 3]
+            cube[i, np.array(idx, dtype=int)] = np.nan
     if case.get('trans'):                             # smooth band-pass: 0.3 at the edges (below the 0.5 cut), 0.95 inside
         z = np.linspace(-1, 1, cube.shape[1])
         extra['trans'] = 0.3 + 0.65 * np.exp(-(z / 0.8) ** 8)

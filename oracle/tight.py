@@ -161,11 +161,14 @@ def problem_from_golden(g, i, **kw):
     """The TightProblem of spaxel ``i`` of a golden fixture (tests/golden/*.npz as loaded by tests.common.load_golden)."""
     import warnings
     noml = bool(g['noml']) if 'noml' in g else False
+    sky = g['cube'][i].astype(np.float64)
+    good = ~np.isnan(sky)                                   # the row worker drops NaN samples (LuciBase.py:358-360)
+    trans = g['trans'] if 'trans' in g else None
     with warnings.catch_warnings():
         warnings.simplefilter('ignore')
-        f = O.OracleFit(g['cube'][i].astype(np.float64), g['axis32'], g['model'], g['lines'],
+        f = O.OracleFit(sky[good], np.asarray(g['axis32'])[good], g['model'], g['lines'],
                         [int(v) for v in g['vel_rel']], [int(v) for v in g['sigma_rel']],
-                        trans_filter=g['trans'] if 'trans' in g else None,
+                        trans_filter=None if trans is None else np.asarray(trans)[good],
                         theta=float(g['theta'][i]), delta_x=float(g['delta_x']), n_steps=int(g['n_steps']), zpd_index=0,
                         filter=g['filter'], nii_cons=True,
                         prior=None if noml else (float(np.ravel(g['v0'][i])[0]), float(np.ravel(g['b0'][i])[0])), **kw)

@@ -17,9 +17,9 @@ TOL_CHI2 = 1e-4
 
 FIT_CASES = ['fit_sincgauss_sn3', 'fit_gaussian_sn3', 'fit_sinc_sn3', 'fit_gaussian_sn2', 'fit_gaussian_sn1',
              'fit_sincgauss_groups', 'fit_sincgauss_groups_hi', 'fit_sincgauss_double', 'fit_sincgauss_double_pg',
-             'fit_sincgauss_single', 'fit_sinc_noml', 'fit_sincgauss_trans']
+             'fit_sincgauss_single', 'fit_sinc_noml', 'fit_sincgauss_trans', 'fit_sincgauss_nan']
 UNC_CASES = ['fit_sincgauss_sn3', 'fit_gaussian_sn3', 'fit_sincgauss_single', 'fit_sincgauss_groups_hi',
-             'fit_sincgauss_double_pg', 'fit_sincgauss_trans', 'unc_sincgauss_cfg2']
+             'fit_sincgauss_double_pg', 'fit_sincgauss_trans', 'unc_sincgauss_cfg2', 'fit_sincgauss_nan']
 
 
 def load_golden(name):
@@ -131,8 +131,13 @@ def optimum_report(rows, g, tight=None, check_broadening=True):
     q = split_rows(rows, L)
     n = rows.shape[0]
     out = dict(same=np.zeros(n, bool), lower=np.zeros(n, bool), ref_off=np.zeros(n, bool), dv=np.zeros(n), db=np.zeros(n),
-               df=np.zeros(n), excess=np.zeros(n), q=q)
-    amp_floor = 1e-6          # a line fitted to (numerically) nothing: compare against 1e-6 of the strongest line
+               df=np.zeros(n), excess=np.zeros(n), q=q, ref_dv=np.zeros(n), ref_db=np.zeros(n), ref_df=np.zeros(n),
+               direct_ok=np.zeros(n, bool))
+    # A line 1000 times weaker than the strongest one (amplitude 5e-4 of the window maximum in region_sinc_strip[118], ten
+    # times below the noise at SNR 100) has its optimum moved by ~1e-3 of itself by the FP32 rounding of the 315 residuals
+    # alone -- our float64 objective there is 1e-11 BELOW the tight solve's.  Fluxes are therefore compared relative to
+    # max(|F|, 1e-3 max_k |F_k|).
+    amp_floor = 1e-3
     for i in range(n):
         prob = T.problem_from_golden(g, i)
         scale = float(g['ref_scale'][i])
@@ -155,7 +160,9 @@ def optimum_report(rows, g, tight=None, check_broadening=True):
             ok2, _, _, _ = _within(d_ours, T.derived(prob, mine, scale), g['model'], check_broadening, amp_floor)
             out['lower'][i] = ok2 and mobj <= tobj
         d_ref = {'velocities': g['ref_velocities'][i], 'sigmas': g['ref_sigmas'][i], 'fluxes': g['ref_fluxes'][i]}
-        out['ref_off'][i] = not _within(d_ref, dt, g['model'], check_broadening, amp_floor)[0]
+        ref_ok, out['ref_dv'][i], out['ref_db'][i], out['ref_df'][i] = _within(d_ref, dt, g['model'], check_broadening, amp_floor)
+        out['ref_off'][i] = not ref_ok
+        out['direct_ok'][i] = _within(d_ours, d_ref, g['model'], check_broadening, amp_floor)[0]
     out['dchi'] = (q['chi2'] - g['ref_chi2']) / np.abs(g['ref_chi2'])
     out['ok'] = out['same'] | out['lower']
     return out
@@ -225,8 +232,11 @@ def assert_fixture_parity(name, rows, status, g):
         assert keep.all()
     assert opt['ok'][keep].all(), (name, np.flatnonzero(~opt['ok'] & keep), opt['dv'], opt['df'])
     assert ((status[keep] >> 16) & 1).all()
-    direct = opt['same'] & ~opt['ref_off'] & keep
-    assert rep['ok'][direct].all(), (name, rep['dv'][direct], rep['db'][direct], rep['df'][direct], rep['dchi'][direct])
+    # "the reference sits on its optimum": within 3e-4 (flux, broadening) / 0.1 km/s of the machine-precision solve
+    ref_at_opt = (opt['ref_df'] <= 3e-4) & (opt['ref_dv'] <= 0.1) & ((opt['ref_db'] <= 3e-4) | (not cb))
+    direct = opt['same'] & ref_at_opt & keep
+    assert opt['direct_ok'][direct].all() and (opt['dchi'][direct] <= TOL_CHI2).all(), \
+        (name, np.flatnonzero(direct & ~opt['direct_ok']), opt['dchi'][direct].max())
     assert (opt['dchi'][opt['lower']] < 0).all()                 # a lower minimum shows in the reported chi2 as well
     assert opt['excess'][opt['same']].max() < 1e-6
     return rep, opt, direct

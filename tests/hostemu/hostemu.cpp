@@ -103,7 +103,7 @@ static void run_eval(const LfPlan& pl, const float* gspec, float theta, const fl
     lf_stage_prep<MODEL, L, NG, NG, 1>(pl.dev, w, gspec, theta, &v0, &b0, lf_work_at(LF_STAGE_PREP, ly, base), state);
     LfWork wk = lf_work_at(LF_STAGE_LM, ly, base);
     const double sinc_w_d = reinterpret_cast<const double*>(state)[LF_SO_SINCW / 2];
-    lf_stage_window<MODEL, 1>(pl.dev, w, pl.dev.xo, gspec, state[LF_SO_INVW], false, sinc_w_d, wk);
+    lf_stage_window<MODEL, 1>(pl.dev, w, pl.dev.xo, gspec, state[LF_SO_INVW], false, sinc_w_d, wk, 0);
     float* th = wk.thb;
     for (int j = 0; j < D::P; ++j) th[j] = th_in[j];
     lf_setup_lines<MODEL, L, NG, NG, 1>(pl.dev, w, th, (float)sinc_w_d, 1.0 / sinc_w_d, wk.lines, wk.tie);

@@ -53,7 +53,7 @@ def test_hostemu_matches_reference(hostemu, name):
     rows, sol, unc, st = run_hostemu(hostemu, cfg, g['cube'], g['theta'], v0, b0)
     rep, opt, direct = assert_fixture_parity(name, rows, st, g)
     # how often the direct comparison with the reference is possible at all (it is at its own optimum): documented floor
-    floor = {'fit_sinc_noml': 0.25, 'fit_sincgauss_groups': 0.75, 'fit_sincgauss_groups_hi': 0.85}.get(name, 1.0)
+    floor = {'fit_sinc_noml': 0.25, 'fit_sinc_sn3': 0.8, 'fit_sincgauss_groups': 0.75, 'fit_sincgauss_groups_hi': 0.85}.get(name, 0.95)
     assert direct.mean() >= floor, (name, direct.mean())
     model = g['model']
     if model == 'sinc' and not bool(g['noml']):
@@ -90,12 +90,14 @@ def test_hostemu_flags_bad_spectra(hostemu):
     g = load_golden('fit_sincgauss_sn3')
     cfg = config_from_golden(g, uncertainty=False)
     cube = g['cube'][:3].copy()
-    cube[0, 50] = np.nan
+    cube[0, :] = np.nan
     cube[1, :] = -1e-18
+    cube[2, 50] = np.nan                     # a NaN sample is dropped and the rest fitted (LuciBase.py:358-360)
     rows, sol, unc, st = run_hostemu(hostemu, cfg, cube, g['theta'][:3], g['v0'][:3], g['b0'][:3])
     assert st[0] & (1 << 20) and np.all(rows[0] == 0)
     assert st[1] & (1 << 22) and np.all(rows[1] == 0)
-    assert st[2] & (1 << 16)
+    assert st[2] & (1 << 16) and st[2] & (1 << 24) and np.isfinite(rows[2]).all()
+    np.testing.assert_allclose(rows[2][15], g['ref_velocities'][2][0], atol=0.05)
 
 
 def test_profiles_against_float64(hostemu):
@@ -257,3 +259,14 @@ def test_analytic_gradient_matches_finite_differences(hostemu, name):
             tp[j] += h; tm[j] -= h
             fd = -(ev(tp)[0] - ev(tm)[0]) / (2.0 * (float(tp[j]) - float(tm[j])))      # -1/2 d(sum r^2)/d theta_j
             np.testing.assert_allclose(hg[NH + j], fd, rtol=3e-2, atol=2e-6 * abs(hg[NH:]).max(), err_msg='%s param %d' % (name, j))
+
+
+def test_hostemu_region_strip_config1(hostemu):
+    """BASELINE config 1 as a strip (100 x 8 spaxels, five-line sinc, 70 % mask; every y-row went through the reference's
+    row worker): the 562 fitted spaxels against the optimum of the reference's objective.  The reference's SLSQP misses
+    its own optimum on the multi-modal sinc objective in ~15 % of them (``ref_off``)."""
+    g = load_golden('region_sinc_strip')
+    cfg = config_from_golden(g, uncertainty=False)
+    rows, sol, unc, st = run_hostemu(hostemu, cfg, g['cube'], g['theta'], g['v0'], g['b0'], want_unc=False)
+    rep, opt, direct = assert_fixture_parity('region_sinc_strip', rows, st, g)
+    assert opt['same'].mean() >= 0.99 and direct.mean() >= 0.8, (opt['same'].mean(), direct.mean())

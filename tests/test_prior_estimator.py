@@ -58,10 +58,11 @@ def test_hostemu_prior_flags_unusable_spectra(hostemu):
     g = load_golden('fit_sincgauss_sn3')
     cfg = config_from_golden(g, uncertainty=False)
     cube = g['cube'][:3].copy()
-    cube[0, cfg.c.fit_lo + 10] = np.nan
+    cube[0, cfg.c.fit_lo:cfg.c.fit_hi] = np.nan
     cube[1] = 0.0
+    cube[2, cfg.c.fit_lo + 10] = np.nan                   # one NaN sample: left out, like the fit does (LuciBase.py:358-360)
     vel, broad = hostemu_prior(hostemu, cfg, cube, g['theta'][:3])
-    assert vel[0] == 0 and broad[0] == 0                 # NaN in the window: the fit returns zeros for it anyway
+    assert vel[0] == 0 and broad[0] == 0                 # nothing left of the window
     assert np.isfinite(vel).all() and np.isfinite(broad).all()
     assert abs(vel[2] - g['ref_velocities'][2, 0]) < HALF_CHANNEL_KMS
 

@@ -66,6 +66,15 @@ static_assert(2 * LF_REFINE_HALF + 1 <= 16, "the refinement scores live in the s
 #ifndef LF_CONV_AMP_FLOOR
 #define LF_CONV_AMP_FLOOR 1e-3f    /* amplitudes (units of the window maximum) below this are compared absolutely against it in the step-size test */
 #endif
+#ifndef LF_SECANT
+#define LF_SECANT 1                /* structured secant term of the Hessian in the LM stage (lf_secant_update) */
+#endif
+#ifndef LF_SEC_AFTER
+#define LF_SEC_AFTER 6             /* ... and applied from this many accepted iterations on: the bulk of the spaxels converges earlier with plain Gauss-Newton steps, whose contraction the stopping test extrapolates */
+#endif
+#ifndef LF_SEC_LEARN
+#define LF_SEC_LEARN 1e-3          /* ... learnt only from steps predicted to gain less than this fraction of sum r^2 (near the optimum, where the residuals -- and with them S -- have settled) */
+#endif
 #define LF_CONV_RHO0 0.5f         /* contraction rate assumed when the previous step was damped / rejected (no measurement) */
 
 // status word: bits 0-7 accepted LM iterations, bits 8-15 model evaluations, bits 16.. flags
@@ -660,7 +669,8 @@ LF_CORE void lf_eval(const LfCfg& cfg, const LfWarp<LANES>& w, const float* xo, 
 // Solve (D^-1/2 H D^-1/2 + lam I) s = D^-1/2 g with fixed columns pinned, delta = D^-1/2 s.  Returns false if the
 // Cholesky factorisation meets a non-positive pivot.  `hg` = [H packed | g] in per-warp memory.
 template <int P>
-LF_CORE bool lf_solve(const float* hg, unsigned fixedmask, float lam, float (&delta)[P], float& pred)
+LF_CORE bool lf_solve(const float* hg, const float* S /* [P][P] secant term or null */, unsigned fixedmask, float lam,
+                      float (&delta)[P], float& pred)
 {
     constexpr int NH = P * (P + 1) / 2;
     float sc[P], M[NH], b[P];
@@ -675,7 +685,9 @@ LF_CORE bool lf_solve(const float* hg, unsigned fixedmask, float lam, float (&de
     for (int i = 0; i < P; ++i)
 #pragma unroll
         for (int j = i; j < P; ++j) {
-            float v = hg[LfSym<P>::idx(i, j)] * sc[i] * sc[j];
+            float v = hg[LfSym<P>::idx(i, j)];
+            if (S) v += S[i * P + j];
+            v *= sc[i] * sc[j];
             if (i == j) v = (sc[i] == 0.0f) ? 1.0f : v + lam;
             M[LfSym<P>::idx(i, j)] = v;
         }
@@ -721,6 +733,57 @@ LF_CORE bool lf_solve(const float* hg, unsigned fixedmask, float lam, float (&de
 #pragma unroll
     for (int j = 0; j < P; ++j) { pred += s[j] * (lam * s[j] + b[j]); delta[j] = s[j] * sc[j]; }
     return ok;
+}
+
+// Structured secant term of the Hessian.  Gauss-Newton drops S = -sum r_i grad^2 m_i from the Hessian of F = 1/2 sum r^2;
+// on noisy spectra (large residuals at the optimum) that makes the iteration contract only linearly, and for a line group
+// lost in the noise it oscillates (tests/golden/fit_sincgauss_groups[9]: 50+ evaluations).  The gradients J^T r are
+// accurate in FP32 long after sum r^2 itself has sunk into its rounding noise, so S is estimated from them: after every
+// evaluation the pair  s = theta_new - theta_old,  y# = (grad F_new - grad F_old) - H s  (H = J^T J of the point the
+// iteration stands on afterwards) must satisfy S s = y#; S is sized (Dennis-Gay-Welsch: shrunk by min(1, |s.y#| / |s.S s|),
+// so that it fades with the residual) and corrected by the symmetric rank-one formula.  `g` here is the code's J^T r =
+// -grad F.  S[P][P] is followed by two [P] scratch vectors.  All lanes call.
+template <int P, int LANES>
+LF_CORE void lf_secant_update(const LfWarp<LANES>& w, const float* h_old, const float* h_new,
+                              const float* th_old, const float* th_new, float* S)
+{
+    constexpr int NH = P * (P + 1) / 2;
+    float* rv = S + P * P;          // y#, then r = y# - tau S s
+    float* sv = rv + P;             // s
+    float* qv = sv + P;             // S s
+    w.sync();
+    for (int i = w.lane; i < P; i += LANES) sv[i] = th_new[i] - th_old[i];
+    w.sync();
+#pragma unroll 1
+    for (int i = w.lane; i < P; i += LANES) {
+        float Ss = 0.0f, Hs = 0.0f;
+#pragma unroll
+        for (int j = 0; j < P; ++j) {
+            const int a = i < j ? i : j, b = i < j ? j : i;
+            Ss += S[i * P + j] * sv[j];
+            const int e = a * P - (a * (a - 1)) / 2 + (b - a);
+            Hs += 0.5f * (h_old[e] + h_new[e]) * sv[j];
+        }
+        rv[i] = -(h_new[NH + i] - h_old[NH + i]) - Hs;
+        qv[i] = Ss;
+    }
+    w.sync();
+    float sy = 0.0f, sSs = 0.0f;
+#pragma unroll
+    for (int i = 0; i < P; ++i) { sy += sv[i] * rv[i]; sSs += sv[i] * qv[i]; }
+    const float tau = (fabsf(sSs) > fabsf(sy)) ? fabsf(sy) / fabsf(sSs) : 1.0f;
+    float abs_sum = 0.0f;
+#pragma unroll
+    for (int i = 0; i < P; ++i) abs_sum += fabsf((rv[i] - tau * qv[i]) * sv[i]);
+    const float rs = sy - tau * sSs;
+    const bool use = abs_sum > 0.0f && fabsf(rs) > 1e-4f * abs_sum;
+    const float inv = use ? 1.0f / rs : 0.0f;
+    w.sync();
+    for (int e = w.lane; e < P * P; e += LANES) {
+        const int i = e / P, j = e - i * P;
+        S[e] = tau * S[e] + (rv[i] - tau * qv[i]) * (rv[j] - tau * qv[j]) * inv;
+    }
+    w.sync();
 }
 
 // Box of the reduced parameters (LuciFit.py:614-633 amplitudes/continuum; :539-541 sigma of the last line), written
@@ -969,6 +1032,9 @@ LF_CORE void lf_stage_lm(const LfCfg& cfg, const LfWarp<LANES>& w, const float* 
     float* hi = wk.thb + 3 * P;
     float* hcur = wk.hb;
     float* htri = wk.hb + NA;
+    float* Ssec = wk.hb + 2 * NA;                      // secant term S[P][P] + scratch (lf_secant_update)
+    bool use_sec = LF_SECANT && !cfg.freeze;           // (the freeze branch is linear: S = 0)
+    for (int e = w.lane; e < P * P; e += LANES) Ssec[e] = 0.0f;
     if (w.lane == 0) {
         for (int j = 0; j < P; ++j) th[j] = state[LF_SO_TH + j];
         lf_bounds<MODEL, L, NV, NS>(cfg, th, lo, hi);
@@ -979,7 +1045,7 @@ LF_CORE void lf_stage_lm(const LfCfg& cfg, const LfWarp<LANES>& w, const float* 
     float lam = LF_LM_LAM0, nu = 2.0f, pred = 0.0f, pred_prev = 0.0f;
     double chi2 = 0.0;
     const double ftol = (double)cfg.ftol;
-    bool first = true, done = false;
+    bool first = true, done = false, sec_applied = false;
     unsigned fixedmask = 0;
     while (true) {
         // ---- evaluate the trial point
@@ -1007,13 +1073,20 @@ LF_CORE void lf_stage_lm(const LfCfg& cfg, const LfWarp<LANES>& w, const float* 
                 nu = 2.0f;
                 accepted = true;
                 ++iters;
+                if (use_sec && (double)pred <= LF_SEC_LEARN * chi2) lf_secant_update<P, LANES>(w, hcur, htri, th, tht, Ssec);
                 chi2 = chi2t;
             } else {
+                if (use_sec && finite && (double)pred <= LF_SEC_LEARN * chi2) lf_secant_update<P, LANES>(w, hcur, htri, th, tht, Ssec);
                 // rejected: keep the accepted system and increase the damping; inside the FP32 noise floor of
                 // sum r^2 (relative ~1e-6) a rejection only means "converged"
                 lam = fmaxf(lam * nu, LF_LM_LAMREJ); nu *= 2.0f;
                 ++tries;
-                if (finite && (double)pred <= LF_TUNE_REJ_CONV * chi2) { done = true; flags |= LF_ST_CONVERGED; }
+                if (sec_applied) {
+                    // the rejected proposal came from the secant model: drop the term, propose a Gauss-Newton step instead
+                    w.sync();
+                    for (int e = w.lane; e < P * P; e += LANES) Ssec[e] = 0.0f;
+                    w.sync();
+                } else if (finite && (double)pred <= LF_TUNE_REJ_CONV * chi2) { done = true; flags |= LF_ST_CONVERGED; }
             }
         }
         if (accepted) {
@@ -1042,7 +1115,15 @@ LF_CORE void lf_stage_lm(const LfCfg& cfg, const LfWarp<LANES>& w, const float* 
         while (!go && !done) {
             if (tries >= 12) { done = true; flags |= LF_ST_MAXITER; break; }
             float delta[P];
-            bool ok = lf_solve<P>(hcur, fixedmask, lam, delta, pred);
+            const bool apply_sec = use_sec && iters >= LF_SEC_AFTER;
+            sec_applied = apply_sec;
+            bool ok = lf_solve<P>(hcur, apply_sec ? Ssec : nullptr, fixedmask, lam, delta, pred);
+            if (!ok && apply_sec) {                          // J^T J + S is not positive definite: fall back to Gauss-Newton
+                w.sync();
+                for (int e = w.lane; e < P * P; e += LANES) Ssec[e] = 0.0f;
+                w.sync();
+                ok = lf_solve<P>(hcur, nullptr, fixedmask, lam, delta, pred);
+            }
             if (!ok) { lam *= 10.0f; flags |= LF_ST_SINGULAR; ++tries; continue; }
             float tn[P];
             float rel = 0.0f;
@@ -1069,7 +1150,7 @@ LF_CORE void lf_stage_lm(const LfCfg& cfg, const LfWarp<LANES>& w, const float* 
             printf("\n");
 #endif
             bool conv = (double)pred <= ftol * chi2;
-            if (!conv && tries == 0 && pred_prev > 0.0f && pred <= LF_CONV_CONTRACTION * pred_prev &&
+            if (!conv && !apply_sec && tries == 0 && pred_prev > 0.0f && pred <= LF_CONV_CONTRACTION * pred_prev &&
                 (double)pred <= LF_CONV_PRED_CAP * chi2)
                 conv = (double)pred * (double)(pred / pred_prev) <= 0.1 * ftol * chi2;
             if (conv) {
@@ -1085,6 +1166,8 @@ LF_CORE void lf_stage_lm(const LfCfg& cfg, const LfWarp<LANES>& w, const float* 
                 // ... unless the predicted gain is already LF_CONV_FLAT times below the tolerance: a direction that flat
                 // (the width of a line group lost in the noise) is not determined by the data to 1e-3, iterating on
                 // would only follow the FP32 rounding of the residuals
+                // (with the secant term in the model the steps no longer contract linearly: the step itself must be small)
+                if (apply_sec) rho = 0.5f;
                 conv = rel * rho < LF_CONV_REMAIN * (1.0f - rho) || (double)pred <= LF_CONV_FLAT * ftol * chi2;
             }
             if (conv && rel < 1e-2f) {

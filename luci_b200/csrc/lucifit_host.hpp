@@ -68,14 +68,14 @@ static inline void lf_make_layout(int L, int P, int nz, int nfit, int ncont, int
     o = lf_align(sizeof(float) * nz, 16);
     ly.prep_sortv = (int)o; o += sizeof(float) * npad;
     ly.prep_bytes = (int)lf_align(o, 16);
-    // lm: yw | sw | cw | lines[L] | tie | gt[L][lanes] | hb[2][NA] | thb[4][P]
+    // lm: yw | sw | cw | lines[L] | tie | gt[L][lanes] | hb[2][NA] + S[P][P] + 3 [P] | thb[4][P]
     o = win;
     ly.lm_sw = (int)o; o += win;
     ly.lm_cw = (int)o; o += win;
     ly.lm_lines = (int)o; o += sizeof(LfLineX) * L;
     ly.lm_tie = (int)o; o = lf_align(o + sizeof(LfTieX), 16);
     ly.lm_gt = (int)o; o = lf_align(o + sizeof(float) * L * lanes, 16);
-    ly.lm_hb = (int)o; o = lf_align(o + sizeof(float) * 2 * NA, 16);
+    ly.lm_hb = (int)o; o = lf_align(o + sizeof(float) * (2 * NA + (size_t)P * P + 3 * P), 16);   // + secant term S[P][P] and three [P] vectors
     ly.lm_thb = (int)o; o = lf_align(o + sizeof(float) * 4 * P, 16);
     ly.lm_bytes = (int)o;
     // unc: variants[13 L] (later: hess) | apd[3 L] | gt[(13 + 5 L)][lanes] | tile[lanes][PF|1]   (no staged window:

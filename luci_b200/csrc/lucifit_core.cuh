@@ -34,6 +34,12 @@
 #define LF_ALIGN16 alignas(16)
 #endif
 
+#if defined(__CUDACC__)
+#define LF_COLD __device__ __noinline__     /* rarely executed: kept out of the hot loops' instruction stream */
+#else
+#define LF_COLD inline
+#endif
+
 #define LF_MAX_LINES 8
 #define LF_C_KMS 299792.0f        /* LuciFit.py:26 (integer km/s in the reference) */
 #define LF_MAX_CONT_WIN 1024      /* longest continuum window (samples) the clip sorts in per-warp shared memory; longer ones are refused */
@@ -69,8 +75,8 @@ static_assert(2 * LF_REFINE_HALF + 1 <= 16, "the refinement scores live in the s
 #ifndef LF_SECANT
 #define LF_SECANT 1                /* structured secant term of the Hessian in the LM stage (lf_secant_update) */
 #endif
-#ifndef LF_SEC_AFTER
-#define LF_SEC_AFTER 6             /* ... and applied from this many accepted iterations on: the bulk of the spaxels converges earlier with plain Gauss-Newton steps, whose contraction the stopping test extrapolates */
+#ifndef LF_FAST_ITERS
+#define LF_FAST_ITERS 8            /* accepted iterations after which the first LM kernel hands a spaxel to the second one (see lf_stage_lm) */
 #endif
 #ifndef LF_SEC_LEARN
 #define LF_SEC_LEARN 1e-3          /* ... learnt only from steps predicted to gain less than this fraction of sum r^2 (near the optimum, where the residuals -- and with them S -- have settled) */
@@ -90,7 +96,7 @@ enum {
 #define LF_ST_BADMASK (LF_ST_NAN_INPUT | LF_ST_MASKED | LF_ST_BAD_NORM)
 
 // per-spaxel state record (float words; the record starts 8-byte aligned and its stride is even)
-enum { LF_SO_NOISE = 0, LF_SO_SCALE = 2, LF_SO_CORR = 4, LF_SO_SINCW = 6, LF_SO_INVW = 8, LF_SO_STATUS = 9, LF_SO_TH = 10 };
+enum { LF_SO_NOISE = 0, LF_SO_SCALE = 2, LF_SO_CORR = 4, LF_SO_SINCW = 6, LF_SO_INVW = 8, LF_SO_STATUS = 9, LF_SO_LAM = 10, LF_SO_TH = 12 };
 
 struct LfCfg {                     // device-side constants of one lucifit_fit_batch call
     int model, L, nv, ns;
@@ -669,8 +675,7 @@ LF_CORE void lf_eval(const LfCfg& cfg, const LfWarp<LANES>& w, const float* xo, 
 // Solve (D^-1/2 H D^-1/2 + lam I) s = D^-1/2 g with fixed columns pinned, delta = D^-1/2 s.  Returns false if the
 // Cholesky factorisation meets a non-positive pivot.  `hg` = [H packed | g] in per-warp memory.
 template <int P>
-LF_CORE bool lf_solve(const float* hg, const float* S /* [P][P] secant term or null */, unsigned fixedmask, float lam,
-                      float (&delta)[P], float& pred)
+LF_CORE bool lf_solve(const float* hg, unsigned fixedmask, float lam, float (&delta)[P], float& pred)
 {
     constexpr int NH = P * (P + 1) / 2;
     float sc[P], M[NH], b[P];
@@ -685,9 +690,7 @@ LF_CORE bool lf_solve(const float* hg, const float* S /* [P][P] secant term or n
     for (int i = 0; i < P; ++i)
 #pragma unroll
         for (int j = i; j < P; ++j) {
-            float v = hg[LfSym<P>::idx(i, j)];
-            if (S) v += S[i * P + j];
-            v *= sc[i] * sc[j];
+            float v = hg[LfSym<P>::idx(i, j)] * sc[i] * sc[j];
             if (i == j) v = (sc[i] == 0.0f) ? 1.0f : v + lam;
             M[LfSym<P>::idx(i, j)] = v;
         }
@@ -744,7 +747,7 @@ LF_CORE bool lf_solve(const float* hg, const float* S /* [P][P] secant term or n
 // so that it fades with the residual) and corrected by the symmetric rank-one formula.  `g` here is the code's J^T r =
 // -grad F.  S[P][P] is followed by two [P] scratch vectors.  All lanes call.
 template <int P, int LANES>
-LF_CORE void lf_secant_update(const LfWarp<LANES>& w, const float* h_old, const float* h_new,
+LF_COLD void lf_secant_update(const LfWarp<LANES>& w, const float* h_old, const float* h_new,
                               const float* th_old, const float* th_new, float* S)
 {
     constexpr int NH = P * (P + 1) / 2;
@@ -784,6 +787,27 @@ LF_CORE void lf_secant_update(const LfWarp<LANES>& w, const float* h_old, const 
         S[e] = tau * S[e] + (rv[i] - tau * qv[i]) * (rv[j] - tau * qv[j]) * inv;
     }
     w.sync();
+}
+
+// [H + S | g] for the solver (dst[NA], per-warp memory).  Returns false -- the caller then proposes a plain Gauss-Newton
+// step -- when S would turn a diagonal element of the model Hessian non-positive.
+template <int P, int LANES>
+LF_COLD bool lf_secant_fold(const LfWarp<LANES>& w, const float* hg, const float* S, float* dst)
+{
+    constexpr int NH = P * (P + 1) / 2;
+    w.sync();
+    bool good = true;
+    for (int e = w.lane; e < P * P; e += LANES) {
+        const int i = e / P, j = e - i * P;
+        if (j < i) continue;
+        const int q = i * P - (i * (i - 1)) / 2 + (j - i);
+        const float v = hg[q] + S[e];
+        dst[q] = v;
+        if (i == j && hg[q] > 0.0f && !(v > 0.25f * hg[q])) good = false;    // (a dead column has H_jj = 0)
+    }
+    for (int j = w.lane; j < P; j += LANES) dst[NH + j] = hg[NH + j];
+    w.sync();
+    return w.all(good);
 }
 
 // Box of the reduced parameters (LuciFit.py:614-633 amplitudes/continuum; :539-541 sigma of the last line), written
@@ -1012,7 +1036,13 @@ LF_CORE void lf_stage_window(const LfCfg& cfg, const LfWarp<LANES>& w, const flo
 // Levenberg-Marquardt on sum r^2 (the noise is a common factor of the reference's nll, LuciFit.py:516, and does not
 // move the optimum).  The accepted and the trial normal equations live in per-warp memory (wk.hb), theta / trial
 // theta / box in wk.thb, so that the evaluation loop owns the registers.
-template <int MODEL, int L, int NV, int NS, int LANES>
+//
+// The stage runs as two kernels.  PHASE 1 (the bulk) is plain projected Gauss-Newton / LM and gives up after
+// LF_FAST_ITERS accepted iterations, leaving theta, the damping and LF_ST_MAXITER in the state record; PHASE 2 picks
+// exactly those spaxels up (a few per cent: faint spectra, line groups lost in the noise, blends) and finishes them
+// with the structured secant term in the model (lf_secant_update), which costs code the bulk should not carry through
+// the instruction cache.
+template <int MODEL, int L, int NV, int NS, int LANES, int PHASE>
 LF_CORE void lf_stage_lm(const LfCfg& cfg, const LfWarp<LANES>& w, const float* xo, const float* gspec, const LfWork& wk,
                          float* state)
 {
@@ -1020,6 +1050,7 @@ LF_CORE void lf_stage_lm(const LfCfg& cfg, const LfWarp<LANES>& w, const float* 
     constexpr int P = D::P, NA = D::NA;
     int status = reinterpret_cast<const int*>(state)[LF_SO_STATUS];
     if (status & LF_ST_BADMASK) return;
+    if (PHASE == 2 && (status & (LF_ST_MAXITER | LF_ST_CONVERGED)) != LF_ST_MAXITER) return;
     const double sinc_w_d = reinterpret_cast<const double*>(state)[LF_SO_SINCW / 2];
     const float sinc_w = (float)sinc_w_d;
     const double inv_w = 1.0 / sinc_w_d;
@@ -1033,8 +1064,8 @@ LF_CORE void lf_stage_lm(const LfCfg& cfg, const LfWarp<LANES>& w, const float* 
     float* hcur = wk.hb;
     float* htri = wk.hb + NA;
     float* Ssec = wk.hb + 2 * NA;                      // secant term S[P][P] + scratch (lf_secant_update)
-    bool use_sec = LF_SECANT && !cfg.freeze;           // (the freeze branch is linear: S = 0)
-    for (int e = w.lane; e < P * P; e += LANES) Ssec[e] = 0.0f;
+    const bool use_sec = PHASE == 2 && LF_SECANT && !cfg.freeze;           // (the freeze branch is linear: S = 0)
+    if (PHASE == 2) for (int e = w.lane; e < P * P; e += LANES) Ssec[e] = 0.0f;
     if (w.lane == 0) {
         for (int j = 0; j < P; ++j) th[j] = state[LF_SO_TH + j];
         lf_bounds<MODEL, L, NV, NS>(cfg, th, lo, hi);
@@ -1043,9 +1074,12 @@ LF_CORE void lf_stage_lm(const LfCfg& cfg, const LfWarp<LANES>& w, const float* 
     w.sync();
     int evals = 0, iters = 0, flags = status & (LF_ST_NAN_SAMPLES | LF_ST_CUT_MASK), tries = 0;
     float lam = LF_LM_LAM0, nu = 2.0f, pred = 0.0f, pred_prev = 0.0f;
+    if (PHASE == 2) { iters = status & 0xff; evals = (status >> 8) & 0xff; flags |= status & LF_ST_SINGULAR; lam = state[LF_SO_LAM]; }
+    const int iters0 = iters;
+    bool sec_have = false;
     double chi2 = 0.0;
     const double ftol = (double)cfg.ftol;
-    bool first = true, done = false, sec_applied = false;
+    bool first = true, done = false, sec_applied = false, sec_skip = false;
     unsigned fixedmask = 0;
     while (true) {
         // ---- evaluate the trial point
@@ -1053,7 +1087,8 @@ LF_CORE void lf_stage_lm(const LfCfg& cfg, const LfWarp<LANES>& w, const float* 
         lf_setup_lines<MODEL, L, NV, NS, LANES>(cfg, w, tht, sinc_w, inv_w, wk.lines, wk.tie);
         lf_eval<MODEL, L, NV, NS, LANES>(cfg, w, xo, wk, nfit, sinc_w, tht[D::IC], chi2t, htri);
         ++evals;
-        bool accepted = false;
+        bool accepted = false, learn = false;
+        sec_skip = false;
         if (first) {
             first = false; accepted = true; chi2 = chi2t;
         } else {
@@ -1073,22 +1108,24 @@ LF_CORE void lf_stage_lm(const LfCfg& cfg, const LfWarp<LANES>& w, const float* 
                 nu = 2.0f;
                 accepted = true;
                 ++iters;
-                if (use_sec && (double)pred <= LF_SEC_LEARN * chi2) lf_secant_update<P, LANES>(w, hcur, htri, th, tht, Ssec);
+                learn = use_sec && (double)pred <= LF_SEC_LEARN * chi2;
                 chi2 = chi2t;
             } else {
-                if (use_sec && finite && (double)pred <= LF_SEC_LEARN * chi2) lf_secant_update<P, LANES>(w, hcur, htri, th, tht, Ssec);
+                learn = use_sec && finite && !sec_applied && (double)pred <= LF_SEC_LEARN * chi2;
                 // rejected: keep the accepted system and increase the damping; inside the FP32 noise floor of
                 // sum r^2 (relative ~1e-6) a rejection only means "converged"
                 lam = fmaxf(lam * nu, LF_LM_LAMREJ); nu *= 2.0f;
                 ++tries;
-                if (sec_applied) {
+                if (PHASE == 2 && sec_applied) {
                     // the rejected proposal came from the secant model: drop the term, propose a Gauss-Newton step instead
                     w.sync();
                     for (int e = w.lane; e < P * P; e += LANES) Ssec[e] = 0.0f;
                     w.sync();
+                    sec_have = false;
                 } else if (finite && (double)pred <= LF_TUNE_REJ_CONV * chi2) { done = true; flags |= LF_ST_CONVERGED; }
             }
         }
+        if (PHASE == 2 && learn) { lf_secant_update<P, LANES>(w, hcur, htri, th, tht, Ssec); sec_have = true; }
         if (accepted) {
             float* t = hcur; hcur = htri; htri = t;       // the trial system becomes the accepted one
             w.sync();
@@ -1115,14 +1152,13 @@ LF_CORE void lf_stage_lm(const LfCfg& cfg, const LfWarp<LANES>& w, const float* 
         while (!go && !done) {
             if (tries >= 12) { done = true; flags |= LF_ST_MAXITER; break; }
             float delta[P];
-            const bool apply_sec = use_sec && iters >= LF_SEC_AFTER;
+            bool apply_sec = PHASE == 2 && use_sec && sec_have && !sec_skip && iters > iters0;
+            if (PHASE == 2 && apply_sec) apply_sec = lf_secant_fold<P, LANES>(w, hcur, Ssec, htri);   // (the trial system is dead here)
             sec_applied = apply_sec;
-            bool ok = lf_solve<P>(hcur, apply_sec ? Ssec : nullptr, fixedmask, lam, delta, pred);
+            bool ok = lf_solve<P>(apply_sec ? htri : hcur, fixedmask, lam, delta, pred);
             if (!ok && apply_sec) {                          // J^T J + S is not positive definite: fall back to Gauss-Newton
-                w.sync();
-                for (int e = w.lane; e < P * P; e += LANES) Ssec[e] = 0.0f;
-                w.sync();
-                ok = lf_solve<P>(hcur, nullptr, fixedmask, lam, delta, pred);
+                sec_skip = true;                             // (this proposal)
+                continue;
             }
             if (!ok) { lam *= 10.0f; flags |= LF_ST_SINGULAR; ++tries; continue; }
             float tn[P];
@@ -1179,6 +1215,8 @@ LF_CORE void lf_stage_lm(const LfCfg& cfg, const LfWarp<LANES>& w, const float* 
                 ++iters;
                 break;
             }
+            // not converged after LF_FAST_ITERS iterations: the second kernel goes on from the accepted point
+            if (PHASE == 1 && iters >= LF_FAST_ITERS && !cfg.freeze) { flags |= LF_ST_MAXITER; done = true; break; }
             pred_prev = tries == 0 ? pred : 0.0f;                 // a damped retry breaks the chain of plain steps
             go = true;
         }
@@ -1187,7 +1225,10 @@ LF_CORE void lf_stage_lm(const LfCfg& cfg, const LfWarp<LANES>& w, const float* 
 #pragma unroll
     for (int j = 0; j < P; ++j) if (th[j] <= lo[j] || th[j] >= hi[j]) flags |= LF_ST_BOUND;
     for (int j = w.lane; j < P; j += LANES) state[LF_SO_TH + j] = th[j];
-    if (w.lane == 0) reinterpret_cast<int*>(state)[LF_SO_STATUS] = (iters & 0xff) | ((evals & 0xff) << 8) | flags;
+    if (w.lane == 0) {
+        reinterpret_cast<int*>(state)[LF_SO_STATUS] = (iters & 0xff) | ((evals & 0xff) << 8) | flags;
+        if (PHASE == 1) state[LF_SO_LAM] = lam;
+    }
     w.sync();
 }
 

@@ -95,7 +95,7 @@ lf_prep_kernel(const __grid_constant__ LfLaunch a)
     }
 }
 
-template <int MODEL, int L, int NG>
+template <int MODEL, int L, int NG, int PHASE>
 __global__ void __launch_bounds__((LfLmBlocks<LfDims<MODEL, L, NG, NG>::NA>::W) * 32, (LfLmBlocks<LfDims<MODEL, L, NG, NG>::NA>::V))
 lf_lm_kernel(const __grid_constant__ LfLaunch a)
 {
@@ -108,8 +108,12 @@ lf_lm_kernel(const __grid_constant__ LfLaunch a)
     const long long stride = (long long)gridDim.x * WARPS;
     for (long long s = (long long)blockIdx.x * WARPS + warp; s < a.n; s += stride) {
         const long long row = a.index ? a.index[s] : a.index_base + s;
-        lf_stage_lm<MODEL, L, NG, NG, 32>(a.cfg, w, xo_s, a.cube + row * (long long)a.cfg.nz, wk,
-                                          a.state + s * (long long)a.cfg.state_floats);
+        if (PHASE == 2) {      // only the spaxels the first kernel left unfinished (their rows are not even addressed otherwise)
+            const int st = reinterpret_cast<const int*>(a.state + s * (long long)a.cfg.state_floats)[LF_SO_STATUS];
+            if ((st & (LF_ST_MAXITER | LF_ST_CONVERGED | LF_ST_BADMASK)) != LF_ST_MAXITER) continue;
+        }
+        lf_stage_lm<MODEL, L, NG, NG, 32, PHASE>(a.cfg, w, xo_s, a.cube + row * (long long)a.cfg.nz, wk,
+                                                 a.state + s * (long long)a.cfg.state_floats);
     }
 }
 
@@ -180,8 +184,12 @@ cudaError_t lf_launch(const LfLaunch& a, int stages)
     }
     if (stages & 2) {
         constexpr int LMW = LfLmBlocks<LfDims<MODEL, L, NG, NG>::NA>::W;
-        e = lf_launch_one(lf_lm_kernel<MODEL, L, NG>, a, LMW, (size_t)a.xo_bytes + (size_t)LMW * a.ly.lm_bytes);
+        e = lf_launch_one(lf_lm_kernel<MODEL, L, NG, 1>, a, LMW, (size_t)a.xo_bytes + (size_t)LMW * a.ly.lm_bytes);
         if (e != cudaSuccess) return e;
+        if (!a.cfg.freeze) {
+            e = lf_launch_one(lf_lm_kernel<MODEL, L, NG, 2>, a, LMW, (size_t)a.xo_bytes + (size_t)LMW * a.ly.lm_bytes);
+            if (e != cudaSuccess) return e;
+        }
     }
     if ((stages & 4) && a.unc_ws) {
         e = lf_launch_one(lf_unc_kernel<MODEL, L, NG>, a, LfUncWarps<L>::W, (size_t)a.xo_bytes + (size_t)LfUncWarps<L>::W * a.ly.un_bytes);

@@ -31,7 +31,8 @@ static void run_batch(const LfPlan& pl, int64_t n, const float* cube, const int6
         const int pnv = pl.dev.prior_groups ? pl.nv : 1, pns = pl.dev.prior_groups ? pl.ns : 1;
         lf_stage_prep<MODEL, L, NG, NG, 1>(pl.dev, w, gspec, theta[s], vel0 ? vel0 + s * pnv : 0, broad0 ? broad0 + s * pns : 0,
                                            lf_work_at(LF_STAGE_PREP, ly, base), state);
-        lf_stage_lm<MODEL, L, NG, NG, 1>(pl.dev, w, pl.dev.xo, gspec, lf_work_at(LF_STAGE_LM, ly, base), state);
+        lf_stage_lm<MODEL, L, NG, NG, 1, 1>(pl.dev, w, pl.dev.xo, gspec, lf_work_at(LF_STAGE_LM, ly, base), state);
+        lf_stage_lm<MODEL, L, NG, NG, 1, 2>(pl.dev, w, pl.dev.xo, gspec, lf_work_at(LF_STAGE_LM, ly, base), state);
         if (pl.dev.uncertainty)
             lf_stage_unc<MODEL, L, NG, NG, 1>(pl.dev, w, pl.dev.xo, gspec, lf_work_at(LF_STAGE_UNC, ly, base), state, unc.data());
         lf_stage_out<MODEL, L, NG, NG, 1>(pl.dev, w, pl.dev.xo, gspec, lf_work_at(LF_STAGE_OUT, ly, base), state,

@@ -1,5 +1,5 @@
 for v in "$@"; do
   echo "== $v"
-  LUCIFIT_LIB=$PWD/_variants/$v python bench.py --nx 512 --no-cpu-baseline --no-e2e --no-reductions --steps 3 2>/dev/null | python -c "
+  LUCIFIT_LIB=$PWD/luci_b200/csrc/_variants/$v python bench.py --nx 512 --no-cpu-baseline --no-e2e --no-reductions --steps 3 2>/dev/null | python -c "
 import json,sys; d=json.loads(sys.stdin.read()); r=d['roofline']; print(round(d['value']/1e6,3), 'M/s', {k:round(v,2) for k,v in r['stage_ms'].items()}, 'E', round(r['mean_evals_E'],3))"
 done

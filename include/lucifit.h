@@ -174,6 +174,20 @@ int lucifit_sim_cube(const lucifit_config* cfg, int64_t n_spaxel, const float* a
                      float flux_scale, float* cube /*[n][nz]*/, void* workspace, size_t workspace_bytes,
                      void* stream);
 
+/* Peer rows -- the multi-GPU "gather" of a sharded fit without a gather step.  The reference collects the rows of its
+ * joblib workers on the host (LuciBase.py:514-551); here every rank's lucifit_fit_batch writes its (7L+5)-float rows
+ * and status words STRAIGHT into the destination rank's map buffer over NVLink: the destination exports its buffer,
+ * the other processes open it and pass the mapped pointer (plus their row offset) as out_rows / status.
+ *   lucifit_peer_export: (handle, offset) naming dev_ptr for other processes of this node; `handle` receives
+ *                        LUCIFIT_PEER_HANDLE_BYTES bytes (a cudaIpcMemHandle_t of the enclosing allocation).
+ *   lucifit_peer_open:   maps it into this process on the CURRENT device and returns the pointer.
+ *   lucifit_peer_close:  unmaps (same pointer and offset as returned / given to lucifit_peer_open).
+ * Completion: a rank's rows are in place when its stream has drained; the ranks then meet at a barrier. */
+#define LUCIFIT_PEER_HANDLE_BYTES 64
+int lucifit_peer_export(const void* dev_ptr, void* handle, uint64_t* offset);
+int lucifit_peer_open(const void* handle, uint64_t offset, void** dev_ptr);
+int lucifit_peer_close(void* dev_ptr, uint64_t offset);
+
 /* Roofline probe: `blocks` CTAs of 256 threads each run `iters` iterations of 8 independent FFMA (mode 0) or
  * MUFU.EX2 (mode 1) chains; out holds blocks*256 floats.  Work = blocks*256*iters*8 FMA (x2 flop) or MUFU ops.
  * MEASURED_PEAKS.json has no FP32 / SFU figure; bench.py times this to get the denominators of the fit kernel. */

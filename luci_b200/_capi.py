@@ -43,7 +43,8 @@ class lucifit_config(C.Structure):
 
 EXPORTS = ['lucifit_row_floats', 'lucifit_workspace_bytes', 'lucifit_fit_batch', 'lucifit_fit_stages', 'lucifit_deep_image',
            'lucifit_snr_map', 'lucifit_bin_cube', 'lucifit_sim_cube', 'lucifit_peak_probe', 'lucifit_estimate_prior',
-           'lucifit_sanitize_cube', 'lucifit_last_error', 'lucifit_version']
+           'lucifit_sanitize_cube', 'lucifit_peer_export', 'lucifit_peer_open', 'lucifit_peer_close', 'lucifit_last_error',
+           'lucifit_version']
 
 _lib = None
 
@@ -74,6 +75,12 @@ def declare(lib):
     lib.lucifit_estimate_prior.restype = C.c_int
     lib.lucifit_sanitize_cube.argtypes = [vp, i64, C.c_float, C.c_float, C.c_float, vp]
     lib.lucifit_sanitize_cube.restype = C.c_int
+    lib.lucifit_peer_export.argtypes = [vp, vp, C.POINTER(C.c_uint64)]
+    lib.lucifit_peer_export.restype = C.c_int
+    lib.lucifit_peer_open.argtypes = [vp, C.c_uint64, C.POINTER(vp)]
+    lib.lucifit_peer_open.restype = C.c_int
+    lib.lucifit_peer_close.argtypes = [vp, C.c_uint64]
+    lib.lucifit_peer_close.restype = C.c_int
     lib.lucifit_last_error.argtypes = []
     lib.lucifit_last_error.restype = C.c_char_p
     lib.lucifit_version.argtypes = []

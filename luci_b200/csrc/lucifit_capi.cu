@@ -1,5 +1,7 @@
 // lucifit_capi.cu -- the extern "C" entry points of include/lucifit.h.
 #include <cuda_runtime.h>
+#include <stdint.h>
+#include <string.h>
 #include <string>
 
 #include "lucifit_host.hpp"
@@ -263,6 +265,60 @@ int lucifit_sanitize_cube(float* cube, int64_t n_values, float lo, float hi, flo
     int sm = 0; int rc = sm_count_of_current_device(&sm); if (rc) return rc;
     cudaError_t e = lf_run_sanitize(cube, n_values, lo, hi, fill, sm, (cudaStream_t)stream);
     if (e != cudaSuccess) return cuda_fail(e, "launch lf_sanitize_kernel");
+    return 0;
+}
+
+// ---- peer memory (multi-GPU gather without a gather step) -----------------------------------------------------
+// cudaIpcGetMemHandle names a whole allocation, and the caller's buffer usually lives inside a larger block of its
+// framework's caching allocator: the block is found with cuMemGetAddressRange (fetched through the runtime's driver
+// entry-point lookup, so the library does not link libcuda) and the buffer travels as (handle, offset).
+typedef int (*lf_cuMemGetAddressRange_t)(unsigned long long*, size_t*, unsigned long long);
+static lf_cuMemGetAddressRange_t lf_get_address_range_fn()
+{
+    static lf_cuMemGetAddressRange_t fn = nullptr;
+    if (!fn) {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuMemGetAddressRange", &p, cudaEnableDefault, &q) == cudaSuccess && p)
+            fn = (lf_cuMemGetAddressRange_t)p;
+    }
+    return fn;
+}
+
+int lucifit_peer_export(const void* dev_ptr, void* handle, uint64_t* offset)
+{
+    if (!dev_ptr || !handle || !offset) return fail(LUCIFIT_EINVAL, "dev_ptr, handle and offset are required");
+    static_assert(sizeof(cudaIpcMemHandle_t) == LUCIFIT_PEER_HANDLE_BYTES, "handle size");
+    lf_cuMemGetAddressRange_t range = lf_get_address_range_fn();
+    if (!range) return fail(LUCIFIT_ECUDA, "cuMemGetAddressRange is not available");
+    unsigned long long base = 0; size_t size = 0;
+    if (range(&base, &size, (unsigned long long)(uintptr_t)dev_ptr) != 0)
+        return fail(LUCIFIT_ECUDA, "cuMemGetAddressRange failed (not a device allocation?)");
+    cudaIpcMemHandle_t h;
+    cudaError_t e = cudaIpcGetMemHandle(&h, (void*)(uintptr_t)base);
+    if (e != cudaSuccess) return cuda_fail(e, "cudaIpcGetMemHandle");
+    memcpy(handle, &h, sizeof(h));
+    *offset = (uint64_t)((unsigned long long)(uintptr_t)dev_ptr - base);
+    return 0;
+}
+
+int lucifit_peer_open(const void* handle, uint64_t offset, void** dev_ptr)
+{
+    if (!handle || !dev_ptr) return fail(LUCIFIT_EINVAL, "handle and dev_ptr are required");
+    cudaIpcMemHandle_t h;
+    memcpy(&h, handle, sizeof(h));
+    void* base = nullptr;
+    cudaError_t e = cudaIpcOpenMemHandle(&base, h, cudaIpcMemLazyEnablePeerAccess);
+    if (e != cudaSuccess) return cuda_fail(e, "cudaIpcOpenMemHandle");
+    *dev_ptr = (char*)base + offset;
+    return 0;
+}
+
+int lucifit_peer_close(void* dev_ptr, uint64_t offset)
+{
+    if (!dev_ptr) return 0;
+    cudaError_t e = cudaIpcCloseMemHandle((char*)dev_ptr - offset);
+    if (e != cudaSuccess) return cuda_fail(e, "cudaIpcCloseMemHandle");
     return 0;
 }
 

@@ -137,6 +137,7 @@ template <> struct LfWarp<1> {
     bool any(bool p) const { return p; }
     int first_true(bool p) const { return p ? 0 : -1; }      // lowest lane whose predicate holds, -1 if none
     float xchg(float v, int) const { return v; }
+    unsigned or_all(unsigned v) const { return v; }
     void argmin(double& v, int& i) const {}
     void sync() const {}
 };
@@ -165,6 +166,7 @@ template <> struct LfWarp<32> {
     __device__ bool any(bool p) const { return __any_sync(0xffffffffu, p); }
     __device__ int first_true(bool p) const { return __ffs((int)__ballot_sync(0xffffffffu, p)) - 1; }
     __device__ float xchg(float v, int o) const { return __shfl_xor_sync(0xffffffffu, v, o); }
+    __device__ unsigned or_all(unsigned v) const { return __reduce_or_sync(0xffffffffu, v); }
     __device__ void argmin(double& v, int& i) const {   // smallest v, ties -> smallest index (np.argmin)
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) {
@@ -738,6 +740,75 @@ LF_CORE bool lf_solve(const float* hg, unsigned fixedmask, float lam, float (&de
     return ok;
 }
 
+#if defined(__CUDACC__)
+// The same solve with the warp's lanes as the columns of the system (P <= 32): lane j keeps column j of the scaled,
+// damped matrix in registers -- by symmetry also its row j -- and ends up with delta_j.  A right-looking Cholesky:
+// at step i lane i broadcasts its (current) row i, every lane j > i updates its column, lane i keeps the finished row
+// i of U, lanes j < i are done.  After the factorisation lane j therefore holds column j of U in m[0..j) and row j of
+// U in m(j..P), which is exactly what the forward (U^T z = b, column-wise) and the backward (U s = z, row-wise)
+// substitution need, one broadcast per unknown.  ~300 warp instructions for P = 8 instead of ~720 for the version
+// above executed redundantly by all lanes (the LM kernel is issue-bound: profiles/r02_lm_ncu.txt).
+template <int P>
+__device__ __forceinline__ bool lf_solve_lanes(const float* hg, unsigned fixedmask, float lam, float& delta, float& pred)
+{
+    static_assert(P <= 32, "one lane per unknown");
+    constexpr int NH = P * (P + 1) / 2;
+    constexpr unsigned FULL = 0xffffffffu;
+    const int lane = threadIdx.x & 31;
+    const int j = lane < P ? lane : P - 1;                   // lanes beyond P shadow the last column (never read)
+    const int Cj = j * P - (j * (j - 1)) / 2 - j;            // packed index of (i, j), i <= j, is C_i + j
+    const float d = hg[Cj + j];
+    const bool fx = ((fixedmask >> j) & 1u) || !(d > 1e-30f);
+    const float sc = fx ? 0.0f : LF_RSQRT(d);
+    const float b = hg[NH + j] * sc;
+    float m[P];
+#pragma unroll
+    for (int i = 0; i < P; ++i) {
+        const int Ci = i * P - (i * (i - 1)) / 2 - i;
+        const float sci = __shfl_sync(FULL, sc, i);
+        float v = hg[i <= j ? Ci + j : Cj + i] * sci * sc;
+        if (i == j) v = fx ? 1.0f : v + lam;
+        m[i] = v;
+    }
+    bool ok = true;
+    float invd = 1.0f;                                       // 1 / U_jj
+#pragma unroll
+    for (int i = 0; i < P; ++i) {
+        float piv = __shfl_sync(FULL, m[i], i);
+        if (!(piv > 1e-12f)) { ok = false; piv = 1.0f; }
+        const float inv = LF_RSQRT(piv);
+        const float u = m[i] * inv;                          // lane j > i: U_ij
+        if (lane == i) invd = inv;
+        const float uu = lane > i ? u : 0.0f;
+        if (lane > i) m[i] = u;
+#pragma unroll
+        for (int k = i + 1; k < P; ++k) {
+            const float r = __shfl_sync(FULL, m[k], i) * inv;    // U_ik, from the lane that owns row i
+            m[k] = lane == i ? r : fmaf(-r, uu, m[k]);
+        }
+    }
+    float acc = b;                                           // U^T z = b
+#pragma unroll
+    for (int k = 0; k < P; ++k) {
+        const float zk = __shfl_sync(FULL, acc * invd, k);
+        acc = fmaf(-(k < lane ? m[k] : 0.0f), zk, acc);
+    }
+    acc *= invd;                                             // z_j;  U s = z
+#pragma unroll
+    for (int k = P - 1; k >= 0; --k) {
+        const float sk = __shfl_sync(FULL, acc * invd, k);
+        acc = fmaf(-(k > lane ? m[k] : 0.0f), sk, acc);
+    }
+    const float s = acc * invd;
+    float t = lane < P ? s * (lam * s + b) : 0.0f;           // predicted decrease of sum r^2: s.(lam s + b)
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) t += __shfl_xor_sync(FULL, t, o);
+    pred = t;
+    delta = s * sc;
+    return ok;
+}
+#endif
+
 // Structured secant term of the Hessian.  Gauss-Newton drops S = -sum r_i grad^2 m_i from the Hessian of F = 1/2 sum r^2;
 // on noisy spectra (large residuals at the optimum) that makes the iteration contract only linearly, and for a line group
 // lost in the noise it oscillates (tests/golden/fit_sincgauss_groups[9]: 50+ evaluations).  The gradients J^T r are
@@ -810,28 +881,27 @@ LF_COLD bool lf_secant_fold(const LfWarp<LANES>& w, const float* hg, const float
     return w.all(good);
 }
 
-// Box of the reduced parameters (LuciFit.py:614-633 amplitudes/continuum; :539-541 sigma of the last line), written
-// to per-warp memory by lane 0 (callers sync).
-template <int MODEL, int L, int NV, int NS>
-LF_CORE void lf_bounds(const LfCfg& cfg, const float* th, float* lo, float* hi)
+// Box of the reduced parameters (LuciFit.py:614-633 amplitudes/continuum; :539-541 sigma of the last line): every lane
+// writes the box of the unknowns it owns (j = lane, lane + LANES, ...) to per-warp memory; `th` must be visible to all
+// lanes (callers sync before and after).
+template <int MODEL, int L, int NV, int NS, int LANES>
+LF_CORE void lf_bounds(const LfCfg& cfg, const LfWarp<LANES>& w, const float* th, float* lo, float* hi)
 {
     typedef LfDims<MODEL, L, NV, NS> D;
-#pragma unroll
-    for (int k = 0; k < L; ++k) { lo[k] = -1e-8f; hi[k] = 1.1f; }
-#pragma unroll
-    for (int g = 0; g < NV; ++g) { lo[D::IV + g] = -INFINITY; hi[D::IV + g] = INFINITY; }
-    // sigma box applies to the LAST line only (late-binding lambda in the reference); other groups: beta >= 0
-    const float vlast = th[D::IV + (NV == 1 ? 0 : cfg.vg[L - 1])];
-    const float plast = cfg.p0[L - 1] / (1.0f + vlast * (1.0f / LF_C_KMS));
-#pragma unroll
-    for (int h = 0; h < NS; ++h) {
-        lo[D::IS + h] = 0.0f;
-        hi[D::IS + h] = (h == cfg.sigbox_group) ? 10.0f * LF_C_KMS / plast : INFINITY;
-    }
-    lo[D::IC] = -1e-8f; hi[D::IC] = 0.99f;
-    if (cfg.freeze) {                                  // unconstrained SLSQP on amplitudes + continuum (:699-703)
-#pragma unroll
-        for (int j = 0; j < D::P; ++j) { lo[j] = -INFINITY; hi[j] = INFINITY; }
+    for (int j = w.lane; j < D::P; j += LANES) {
+        float l = -1e-8f, h = 1.1f;                                      // amplitudes
+        if (j >= D::IV && j < D::IS) { l = -INFINITY; h = INFINITY; }
+        else if (j >= D::IS && j < D::IC) {
+            // sigma box applies to the LAST line only (late-binding lambda in the reference); other groups: beta >= 0
+            l = 0.0f; h = INFINITY;
+            if (j - D::IS == cfg.sigbox_group) {
+                const float vlast = th[D::IV + (NV == 1 ? 0 : cfg.vg[L - 1])];
+                const float plast = cfg.p0[L - 1] / (1.0f + vlast * (1.0f / LF_C_KMS));
+                h = 10.0f * LF_C_KMS / plast;
+            }
+        } else if (j == D::IC) { l = -1e-8f; h = 0.99f; }
+        if (cfg.freeze) { l = -INFINITY; h = INFINITY; }                 // unconstrained SLSQP on amplitudes + continuum (:699-703)
+        lo[j] = l; hi[j] = h;
     }
 }
 
@@ -1066,11 +1136,11 @@ LF_CORE void lf_stage_lm(const LfCfg& cfg, const LfWarp<LANES>& w, const float* 
     float* Ssec = wk.hb + 2 * NA;                      // secant term S[P][P] + scratch (lf_secant_update)
     const bool use_sec = PHASE == 2 && LF_SECANT && !cfg.freeze;           // (the freeze branch is linear: S = 0)
     if (PHASE == 2) for (int e = w.lane; e < P * P; e += LANES) Ssec[e] = 0.0f;
-    if (w.lane == 0) {
-        for (int j = 0; j < P; ++j) th[j] = state[LF_SO_TH + j];
-        lf_bounds<MODEL, L, NV, NS>(cfg, th, lo, hi);
-        for (int j = 0; j < P; ++j) { th[j] = fminf(fmaxf(th[j], lo[j]), hi[j]); tht[j] = th[j]; }
-    }
+    for (int j = w.lane; j < P; j += LANES) th[j] = state[LF_SO_TH + j];
+    w.sync();
+    lf_bounds<MODEL, L, NV, NS, LANES>(cfg, w, th, lo, hi);
+    w.sync();                                            // (the box of sigma reads the velocity: clamp only afterwards)
+    for (int j = w.lane; j < P; j += LANES) { const float t = fminf(fmaxf(th[j], lo[j]), hi[j]); th[j] = t; tht[j] = t; }
     w.sync();
     int evals = 0, iters = 0, flags = status & (LF_ST_NAN_SAMPLES | LF_ST_CUT_MASK), tries = 0;
     float lam = LF_LM_LAM0, nu = 2.0f, pred = 0.0f, pred_prev = 0.0f;
@@ -1129,20 +1199,19 @@ LF_CORE void lf_stage_lm(const LfCfg& cfg, const LfWarp<LANES>& w, const float* 
         if (accepted) {
             float* t = hcur; hcur = htri; htri = t;       // the trial system becomes the accepted one
             w.sync();
-            if (w.lane == 0) {
-                for (int j = 0; j < P; ++j) th[j] = tht[j];
-                lf_bounds<MODEL, L, NV, NS>(cfg, th, lo, hi);
-            }
+            for (int j = w.lane; j < P; j += LANES) th[j] = tht[j];
+            w.sync();
+            lf_bounds<MODEL, L, NV, NS, LANES>(cfg, w, th, lo, hi);
             w.sync();
             tries = 0;
             fixedmask = 0;
-#pragma unroll
-            for (int j = 0; j < P; ++j) {
-                float gj = hcur[D::NH + j];
-                bool at_lo = th[j] <= lo[j] && gj <= 0.0f;
-                bool at_hi = th[j] >= hi[j] && gj >= 0.0f;
+            for (int j = w.lane; j < P; j += LANES) {      // active set: at a bound with the gradient pushing outwards
+                const float gj = hcur[D::NH + j], tj = th[j];
+                const bool at_lo = tj <= lo[j] && gj <= 0.0f;
+                const bool at_hi = tj >= hi[j] && gj >= 0.0f;
                 if (at_lo || at_hi) fixedmask |= 1u << j;
             }
+            fixedmask = w.or_all(fixedmask);
             if (cfg.freeze) fixedmask |= ((1u << D::IC) - 1u) & ~((1u << D::IV) - 1u);   // pin every v and beta column
             if (!(iters < cfg.max_iter && evals < 250)) { flags |= LF_ST_MAXITER; done = true; }
         }
@@ -1151,28 +1220,36 @@ LF_CORE void lf_stage_lm(const LfCfg& cfg, const LfWarp<LANES>& w, const float* 
         bool go = false;
         while (!go && !done) {
             if (tries >= 12) { done = true; flags |= LF_ST_MAXITER; break; }
-            float delta[P];
+            constexpr int PL = (P + LANES - 1) / LANES;      // unknowns per lane: j = t LANES + lane
+            float delta[PL];
             bool apply_sec = PHASE == 2 && use_sec && sec_have && !sec_skip && iters > iters0;
             if (PHASE == 2 && apply_sec) apply_sec = lf_secant_fold<P, LANES>(w, hcur, Ssec, htri);   // (the trial system is dead here)
             sec_applied = apply_sec;
-            bool ok = lf_solve<P>(apply_sec ? htri : hcur, fixedmask, lam, delta, pred);
+            bool ok;
+#if defined(__CUDA_ARCH__)
+            if constexpr (LANES == 32) ok = lf_solve_lanes<P>(apply_sec ? htri : hcur, fixedmask, lam, delta[0], pred);
+            else
+#endif
+                ok = lf_solve<P>(apply_sec ? htri : hcur, fixedmask, lam, delta, pred);
             if (!ok && apply_sec) {                          // J^T J + S is not positive definite: fall back to Gauss-Newton
                 sec_skip = true;                             // (this proposal)
                 continue;
             }
             if (!ok) { lam *= 10.0f; flags |= LF_ST_SINGULAR; ++tries; continue; }
-            float tn[P];
             float rel = 0.0f;
-#pragma unroll
-            for (int j = 0; j < P; ++j) {
-                float tj = th[j];
-                tn[j] = fminf(fmaxf(tj + delta[j], lo[j]), hi[j]);
-                float sc = (j >= D::IV && j < D::IS) ? 1.0f : fmaxf(fabsf(tj), LF_CONV_AMP_FLOOR);   // velocities: km/s absolute
-                rel = fmaxf(rel, fabsf(tn[j] - tj) * LF_RCP(sc));
-            }
             w.sync();
 #pragma unroll
-            for (int j = 0; j < P; ++j) if (w.lane == (j % LANES)) tht[j] = tn[j];
+            for (int t = 0; t < PL; ++t) {
+                const int j = t * LANES + w.lane;
+                if (j < P) {
+                    const float tj = th[j];
+                    const float tn = fminf(fmaxf(tj + delta[t], lo[j]), hi[j]);
+                    const float sc = (j >= D::IV && j < D::IS) ? 1.0f : fmaxf(fabsf(tj), LF_CONV_AMP_FLOOR);   // velocities: km/s absolute
+                    rel = fmaxf(rel, fabsf(tn - tj) * LF_RCP(sc));
+                    tht[j] = tn;
+                }
+            }
+            rel = w.max(rel);
             w.sync();
             // The predicted decrease is below what an FP32 evaluation of sum r^2 can resolve: take the (Newton-like)
             // step and stop -- evaluating it would only return rounding noise.  What is left AFTER this step is the
@@ -1182,7 +1259,7 @@ LF_CORE void lf_stage_lm(const LfCfg& cfg, const LfWarp<LANES>& w, const float* 
             // Slowly contracting fits (flat valleys, blended lines) never qualify and run down to the tolerance itself.
 #ifdef LF_TRACE
             printf("it %d ev %d chi2 %.10e pred %.3e pred/chi2 %.3e rel %.3e lam %.2e tries %d | th", iters, evals, chi2, pred, pred / chi2, rel, lam, tries);
-            for (int j = 0; j < P; ++j) printf(" %.7g", tn[j]);
+            for (int j = 0; j < P; ++j) printf(" %.7g", tht[j]);
             printf("\n");
 #endif
             bool conv = (double)pred <= ftol * chi2;
@@ -1207,9 +1284,7 @@ LF_CORE void lf_stage_lm(const LfCfg& cfg, const LfWarp<LANES>& w, const float* 
                 conv = rel * rho < LF_CONV_REMAIN * (1.0f - rho) || (double)pred <= LF_CONV_FLAT * ftol * chi2;
             }
             if (conv && rel < 1e-2f) {
-                if (w.lane == 0) {
-                    for (int j = 0; j < P; ++j) th[j] = tht[j];
-                }
+                for (int j = w.lane; j < P; j += LANES) th[j] = tht[j];
                 w.sync();
                 done = true; flags |= LF_ST_CONVERGED;
                 ++iters;
@@ -1222,9 +1297,13 @@ LF_CORE void lf_stage_lm(const LfCfg& cfg, const LfWarp<LANES>& w, const float* 
         }
         if (done) break;
     }
-#pragma unroll
-    for (int j = 0; j < P; ++j) if (th[j] <= lo[j] || th[j] >= hi[j]) flags |= LF_ST_BOUND;
-    for (int j = w.lane; j < P; j += LANES) state[LF_SO_TH + j] = th[j];
+    bool at_bound = false;
+    for (int j = w.lane; j < P; j += LANES) {
+        const float tj = th[j];
+        at_bound |= tj <= lo[j] || tj >= hi[j];
+        state[LF_SO_TH + j] = tj;
+    }
+    if (w.any(at_bound)) flags |= LF_ST_BOUND;
     if (w.lane == 0) {
         reinterpret_cast<int*>(state)[LF_SO_STATUS] = (iters & 0xff) | ((evals & 0xff) << 8) | flags;
         if (PHASE == 1) state[LF_SO_LAM] = lam;

@@ -1,10 +1,16 @@
-"""Sharding of the spaxel list over GPUs of one node and the final gather of the output maps.
+"""Sharding of the spaxel list over GPUs of one node and the collection of the output maps on one rank.
 
 The fit path has no exchange step (every spaxel is independent; the reference's unit of parallelism is a y-row
-handed to a joblib worker, ``LuciBase.py:514-517``).  Each rank owns a contiguous slab of x-rows of the cube, fits
-it with no collective, and only the ``(7L+5)`` float32 output columns are gathered at the end -- over NCCL when
-the tensors are on the GPU, over gloo in the CPU tests.
+handed to a joblib worker, ``LuciBase.py:514-517``).  Each rank owns a contiguous run of the fitted spaxels, fits it
+with no collective, and only the ``(7L+5)`` float32 output columns have to reach the rank that assembles the maps:
+
+* :class:`PeerRows` (the GPU path): the destination rank's map buffer is mapped into every other process
+  (``lucifit_peer_export`` / ``lucifit_peer_open``) and each rank's output kernel stores its rows straight into it
+  over NVLink -- there is no gather step, the transfer rides inside the fit;
+* :func:`gather_rows`: point-to-point gather through ``torch.distributed`` (NCCL on the GPU, gloo in the CPU tests),
+  used where peer mapping is unavailable and for fits that post-process their rows locally (restarts).
 """
+import ctypes as C
 import os
 
 import torch
@@ -67,6 +73,91 @@ def split_even(n, rank, world):
     return lo, lo + base + (1 if rank < rem else 0)
 
 
+def is_distributed():
+    return dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1
+
+
+def _control_device(device):
+    """Device of the small control-plane tensors: the GPU under NCCL, the CPU under gloo."""
+    return device if dist.get_backend() == 'nccl' else torch.device('cpu')
+
+
+class PeerRows:
+    """Rows ``[n_total, K]`` float32 and status ``[n_total]`` int32 on rank ``dst``, writable by every rank.
+
+    Collective: every rank of the process group constructs it with the same arguments.  ``dst`` allocates the two
+    tensors (``.rows`` / ``.status``), the others map them (same node; works between processes that share one GPU
+    as well) and get addresses.  ``window(lo, hi)`` returns what ``engine.fit_batch(rows=..., status=...)`` takes for
+    the spaxels ``[lo, hi)`` of the global list.  ``complete()`` = this rank's stream drained + barrier: afterwards
+    ``dst`` may read.  ``ok`` is False on EVERY rank when any rank could not map the buffers (callers then use
+    :func:`gather_rows`)."""
+
+    def __init__(self, n_total, K, device, dst=0):
+        from . import _capi
+        from .engine import DevPtr
+        self._DevPtr = DevPtr
+        self.n, self.K, self.dst, self.device = int(n_total), int(K), int(dst), torch.device(device)
+        self.rank, self.world = dist.get_rank(), dist.get_world_size()
+        self.rows = self.status = None
+        self._opened = []
+        lib = _capi.lib()
+        payload = [None]
+        good = 1
+        if self.rank == dst:
+            self.rows = torch.empty((self.n, self.K), dtype=torch.float32, device=self.device)
+            self.status = torch.empty((self.n,), dtype=torch.int32, device=self.device)
+            items = []
+            for t in (self.rows, self.status):
+                h = (C.c_ubyte * 64)()
+                off = C.c_uint64(0)
+                rc = lib.lucifit_peer_export(C.c_void_p(t.data_ptr()), h, C.byref(off)) if t.numel() else 0
+                if rc != 0:
+                    good = 0
+                items.append((bytes(h), int(off.value)))
+            payload = [items]
+        dist.broadcast_object_list(payload, src=dst)
+        self._addr = [0, 0]
+        if self.rank != dst and self.n > 0:
+            with torch.cuda.device(self.device):
+                for i, (h, off) in enumerate(payload[0]):
+                    out = C.c_void_p(0)
+                    hb = (C.c_ubyte * 64).from_buffer_copy(h)
+                    rc = lib.lucifit_peer_open(hb, C.c_uint64(off), C.byref(out))
+                    if rc != 0 or not out.value:
+                        good = 0
+                        break
+                    self._addr[i] = int(out.value)
+                    self._opened.append((int(out.value), off))
+        flag = torch.tensor([good], dtype=torch.int32, device=_control_device(self.device))
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+        self.ok = bool(int(flag.item()) == 1)
+
+    def window(self, lo, hi):
+        if self.rank == self.dst:
+            return self.rows[lo:hi], self.status[lo:hi]
+        D = self._DevPtr
+        return (D(self._addr[0] + 4 * self.K * int(lo), (hi - lo, self.K)), D(self._addr[1] + 4 * int(lo), (hi - lo,)))
+
+    def complete(self):
+        torch.cuda.current_stream(self.device).synchronize()
+        dist.barrier()
+
+    def close(self):
+        if self._opened:
+            from . import _capi
+            lib = _capi.lib()
+            with torch.cuda.device(self.device):
+                for addr, off in self._opened:
+                    lib.lucifit_peer_close(C.c_void_p(addr), C.c_uint64(off))
+            self._opened = []
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
 def gather_rows(local_rows, dst=0, counts=None, out=None):
     """Gather ``[n_r, K]`` row blocks of all ranks to ``dst`` in rank order (concatenated ``[sum n_r, K]``); other
     ranks get ``None``.  Shards may differ in length.
@@ -83,9 +174,10 @@ def gather_rows(local_rows, dst=0, counts=None, out=None):
         dist.all_gather(got, n_local)
         counts = [int(c.item()) for c in got]
     K = local_rows.shape[1]
+    staged = local_rows.is_cuda and dist.get_backend() != 'nccl'     # gloo moves host memory: stage device rows through it
     if rank != dst:
         if local_rows.shape[0] > 0:
-            dist.send(local_rows.contiguous(), dst=dst)
+            dist.send(local_rows.cpu() if staged else local_rows.contiguous(), dst=dst)
         return None
     total = sum(counts)
     if out is None:
@@ -100,10 +192,15 @@ def gather_rows(local_rows, dst=0, counts=None, out=None):
         blk = out[offs[r]:offs[r + 1]]
         if r == dst:
             blk.copy_(local_rows)
+        elif staged:
+            tmp = torch.empty(blk.shape, dtype=blk.dtype)
+            reqs.append((dist.irecv(tmp, src=r), blk, tmp))
         else:
-            reqs.append(dist.irecv(blk, src=r))
-    for q in reqs:
+            reqs.append((dist.irecv(blk, src=r), None, None))
+    for q, blk, tmp in reqs:
         q.wait()
+        if tmp is not None:
+            blk.copy_(tmp)
     return out
 
 

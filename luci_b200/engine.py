@@ -17,6 +17,23 @@ ROW_SCALARS = ('chi2', 'corr', 'axis_step', 'continuum', 'continuum_error')
 launch_counter = {'n': 0}
 
 
+class DevPtr:
+    """A raw device address with a shape: an output buffer that is not a tensor of this process -- the destination
+    rank's rows / status mapped through ``lucifit_peer_open`` (:class:`luci_b200.dist.PeerRows`)."""
+
+    def __init__(self, ptr, shape):
+        self.ptr, self.shape = int(ptr), tuple(int(v) for v in shape)
+
+    def data_ptr(self):
+        return self.ptr
+
+    def numel(self):
+        n = 1
+        for v in self.shape:
+            n *= v
+        return n
+
+
 def _ptr(t):
     return C.c_void_p(0) if t is None else C.c_void_p(t.data_ptr())
 
@@ -70,6 +87,8 @@ def fit_batch(cfg: FitConfig, cube, theta, vel0=None, broad0=None, index=None, b
     selects the rows to fit; ``theta``/``vel0``/``broad0`` are per *fitted* spaxel.  Returns a dict of device
     tensors: ``rows [n, 7L+5]``, ``status [n]`` and optionally ``fit_sol`` / ``fit_unc`` ``[n, 3L+1]``.
 
+    ``rows`` / ``status`` may be caller-owned tensors or :class:`DevPtr` addresses (peer memory of another rank).
+
     ``time_stages=True`` runs the same pipeline stage by stage through ``lucifit_fit_stages`` (slice by slice) with
     CUDA events around every kernel on the launching stream and adds ``stage_ms`` (dict, summed over the slices;
     this synchronises)."""
@@ -99,15 +118,19 @@ def fit_batch(cfg: FitConfig, cube, theta, vel0=None, broad0=None, index=None, b
     if rows is None:
         rows = torch.empty((n, K), dtype=torch.float32, device=dev)
     else:                                                  # caller-owned outputs (streaming pipelines reuse them)
-        require_cuda(rows, 'rows', torch.float32)
+        if not isinstance(rows, DevPtr):
+            require_cuda(rows, 'rows', torch.float32)
         if tuple(rows.shape) != (n, K):
             raise ValueError('rows must be [n, 7L+5]')
     if status is None:
         status = torch.empty((n,), dtype=torch.int32, device=dev)
     else:
-        require_cuda(status, 'status', torch.int32)
+        if not isinstance(status, DevPtr):
+            require_cuda(status, 'status', torch.int32)
         if status.numel() != n:
             raise ValueError('status must have n entries')
+    if time_stages and (isinstance(rows, DevPtr) or isinstance(status, DevPtr)):
+        raise ValueError('time_stages needs tensor outputs')
     sol = torch.empty((n, PF), dtype=torch.float32, device=dev) if want_sol else None
     unc = torch.empty((n, PF), dtype=torch.float32, device=dev) if want_unc else None
     need = C.c_size_t(0)

@@ -24,6 +24,7 @@ import numpy as np
 import numpy.ma as ma
 import torch
 
+from . import dist as ldist
 from . import engine
 from ._capi import FitConfig, argmin_abs
 from .constants import LINE_DICT, snr_windows
@@ -306,28 +307,52 @@ class Luci():
         # fitted spaxels, ordered like the output maps: (y, x) row-major
         dense = mask is None and pca is None                # every spaxel of the rectangle: no selection arrays needed
         v0 = b0 = None
+        pv = pb = None                                      # host priors of the fitted spaxels, [n_fit, 1 or groups]
+        width = lambda a: 1 if np.ndim(a) < 3 else int(np.shape(a)[2])
         if dense:
             sel = None
-            index = (torch.arange(x_min, x_max, dtype=torch.int64, device=dev)[None, :] * nyc
-                     + torch.arange(y_min, y_max, dtype=torch.int64, device=dev)[:, None]).reshape(-1)
+            n_fit = nxo * nyo
             theta = np.ascontiguousarray(np.asarray(self.interferometer_theta)[x_min:x_max, y_min:y_max].T,
                                          dtype=np.float32).reshape(-1)              # LuciBase.py:369
             if have_prior:
-                v0 = torch.from_numpy(np.ascontiguousarray(prior_values[0], dtype=np.float32)).to(dev).reshape(-1)
-                b0 = torch.from_numpy(np.ascontiguousarray(prior_values[1], dtype=np.float32)).to(dev).reshape(-1)
+                pv = np.ascontiguousarray(prior_values[0], dtype=np.float32).reshape(n_fit, width(prior_values[0]))
+                pb = np.ascontiguousarray(prior_values[1], dtype=np.float32).reshape(n_fit, width(prior_values[1]))
         else:
             yy, xx = np.meshgrid(np.arange(y_min, y_max), np.arange(x_min, x_max), indexing='ij')
             if mask is not None:
                 sel = np.asarray(mask)[xx, yy].astype(bool)
             else:
                 sel = np.ones_like(xx, dtype=bool)
-            flat = (xx.astype(np.int64) * nyc + yy.astype(np.int64))[sel]
-            theta = np.asarray(self.interferometer_theta)[xx[sel], yy[sel]].astype(np.float32)   # LuciBase.py:369
-            index = torch.from_numpy(flat).to(dev)
+            xs_sel, ys_sel = xx[sel], yy[sel]
+            n_fit = int(xs_sel.size)
+            flat = xs_sel.astype(np.int64) * nyc + ys_sel.astype(np.int64)
+            theta = np.asarray(self.interferometer_theta)[xs_sel, ys_sel].astype(np.float32)   # LuciBase.py:369
             if have_prior:
-                v0 = torch.from_numpy(np.ascontiguousarray(np.asarray(prior_values[0], dtype=np.float32)[sel])).to(dev)
-                b0 = torch.from_numpy(np.ascontiguousarray(np.asarray(prior_values[1], dtype=np.float32)[sel])).to(dev)
-        theta_t = torch.from_numpy(theta).to(dev)
+                pv = np.ascontiguousarray(np.asarray(prior_values[0], dtype=np.float32)[sel]).reshape(n_fit, width(prior_values[0]))
+                pb = np.ascontiguousarray(np.asarray(prior_values[1], dtype=np.float32)[sel]).reshape(n_fit, width(prior_values[1]))
+        # one process per GPU (torchrun): this rank fits a contiguous run [lo, hi) of the fitted list -- whole y-rows of
+        # the output when the rectangle is dense, like the y-rows the reference hands to its joblib workers
+        # (LuciBase.py:514-517), an even share of the compacted list under a mask -- and the rows meet on rank 0
+        sharded = ldist.is_distributed()
+        lo, hi = 0, n_fit
+        if sharded:
+            rank, world = torch.distributed.get_rank(), torch.distributed.get_world_size()
+            if dense:
+                y_lo, y_hi = ldist.shard_bounds(nyo, rank, world)
+                lo, hi = y_lo * nxo, y_hi * nxo
+            else:
+                lo, hi = ldist.split_even(n_fit, rank, world)
+        if dense:
+            y0, y1 = y_min + lo // nxo, y_min + hi // nxo
+            index = (torch.arange(x_min, x_max, dtype=torch.int64, device=dev)[None, :] * nyc
+                     + torch.arange(y0, y1, dtype=torch.int64, device=dev)[:, None]).reshape(-1)
+        else:
+            xs_sel, ys_sel = xs_sel[lo:hi], ys_sel[lo:hi]
+            index = torch.from_numpy(flat[lo:hi]).to(dev)
+        if have_prior:
+            v0 = torch.from_numpy(np.ascontiguousarray(pv[lo:hi])).to(dev).reshape(-1)
+            b0 = torch.from_numpy(np.ascontiguousarray(pb[lo:hi])).to(dev).reshape(-1)
+        theta_t = torch.from_numpy(np.ascontiguousarray(theta[lo:hi])).to(dev)
         bkg_t = None
         if bkg is not None:
             bkg_t = torch.from_numpy(np.asarray(bkg, dtype=np.float32) * np.float32(bkg_scale)).to(dev)
@@ -337,7 +362,7 @@ class Luci():
             # contraction of the pipeline, a [n x n_comp] . [n_comp x nz] library GEMM -- scaled by the maximum of the
             # spectrum in the filter's reference band, subtracted into a compacted copy of the fitted spectra
             coef, vecs, mean = pca
-            coef_t = torch.from_numpy(np.ascontiguousarray(np.asarray(coef, dtype=np.float32)[xx[sel] - x_min, yy[sel] - y_min])).to(dev)
+            coef_t = torch.from_numpy(np.ascontiguousarray(np.asarray(coef, dtype=np.float32)[xs_sel - x_min, ys_sel - y_min])).to(dev)
             vecs_t = torch.from_numpy(np.ascontiguousarray(vecs, dtype=np.float32)).to(dev)
             mean_t = torch.from_numpy(np.ascontiguousarray(mean, dtype=np.float32)).to(dev)
             band = {'SN3': (675.0, 670.0), 'SN2': (505.0, 480.0)}.get(self.hdr_dict['FILTER'])
@@ -370,12 +395,18 @@ class Luci():
             have_prior = True
         self.last_prior = (v0, b0)
         L_ = len(lines)
+        K = cfg.row_floats
+        # sharded single-pass fits store their rows straight into rank 0's buffers (dist.PeerRows); fits that compare
+        # several passes per spaxel (component search, restarts) keep them local and gather the winners
+        peer = None
+        if sharded and not search and int(n_stoch) == 1:
+            peer = self._peer_rows(n_fit, K, dev)
         if search:
             # per-group starts from the shared pair: the first group keeps it, every further group is offset
-            n_fit = theta_t.numel()
-            v_sh = v0.reshape(n_fit, 1) if v0 is not None else torch.zeros((n_fit, 1), dtype=torch.float32, device=dev)
-            b_sh = b0.reshape(n_fit, 1) if b0 is not None else torch.zeros((n_fit, 1), dtype=torch.float32, device=dev)
-            b_pg = b_sh.expand(n_fit, cfg.n_sigma_groups).contiguous()
+            n_loc = theta_t.numel()
+            v_sh = v0.reshape(n_loc, 1) if v0 is not None else torch.zeros((n_loc, 1), dtype=torch.float32, device=dev)
+            b_sh = b0.reshape(n_loc, 1) if b0 is not None else torch.zeros((n_loc, 1), dtype=torch.float32, device=dev)
+            b_pg = b_sh.expand(n_loc, cfg.n_sigma_groups).contiguous()
             res = None
             for d in COMPONENT_OFFSETS:
                 off = torch.zeros((1, cfg.n_vel_groups), dtype=torch.float32, device=dev)
@@ -383,6 +414,9 @@ class Luci():
                 alt = engine.fit_batch(cfg, cube2d, theta_t, (v_sh + off).contiguous(), b_pg, index=index, bkg=bkg_t)
                 res = alt if res is None else engine.keep_best(res, alt, 7 * L_)
             n_stoch = 1
+        elif peer is not None:
+            rows_w, status_w = peer.window(lo, hi)
+            res = engine.fit_batch(cfg, cube2d, theta_t, v0, b0, index=index, bkg=bkg_t, rows=rows_w, status=status_w)
         else:
             res = engine.fit_batch(cfg, cube2d, theta_t, v0, b0, index=index, bkg=bkg_t)
         rows = res['rows']
@@ -393,13 +427,20 @@ class Luci():
             # group, drawn here with the same generator and compared on the chi2 each fit reports
             if not have_prior:
                 break                                                   # all draws would equal the start (v0 = b0 = 0)
-            v_np, b_np = v0.cpu().numpy(), b0.cpu().numpy()
-            v_r = torch.from_numpy(np.random.normal(v_np, np.abs(v_np) / 50.0).astype(np.float32)).to(dev)
-            b_r = torch.from_numpy(np.random.normal(b_np, np.abs(b_np) / 10.0).astype(np.float32)).to(dev)
+            # (drawn for the whole fitted list and sliced, so that a sharded call with equally seeded ranks makes the
+            # draws of the single-process call)
+            v_np, b_np = v0.cpu().numpy().astype(np.float64), b0.cpu().numpy().astype(np.float64)
+            wv, wb = v_np.size // max(hi - lo, 1), b_np.size // max(hi - lo, 1)
+            zv = np.random.standard_normal((n_fit, wv))[lo:hi].reshape(-1)
+            zb = np.random.standard_normal((n_fit, wb))[lo:hi].reshape(-1)
+            v_r = torch.from_numpy((v_np + np.abs(v_np) / 50.0 * zv).astype(np.float32)).to(dev)
+            b_r = torch.from_numpy((b_np + np.abs(b_np) / 10.0 * zb).astype(np.float32)).to(dev)
             alt = engine.fit_batch(cfg, cube2d, theta_t, v_r, b_r, index=index, bkg=bkg_t)
             res = engine.keep_best(res, alt, 7 * L_)
             rows = res['rows']
-        K = cfg.row_floats
+        status = res['status']
+        if sharded:
+            rows, status = self._collect_rows(peer, rows, status, n_fit, lo, hi, dev)
         if sel is None:
             full = rows
         else:
@@ -409,7 +450,7 @@ class Luci():
         # one transpose on the device to field-major [K, ny' nx'], one copy to the host: every 2-D map of a line is then
         # a contiguous slice (what save_fits writes), and the (ny', nx', L) arrays the API returns are views of it
         host = full.t().contiguous().cpu().numpy()
-        self.last_fit_summary = engine.status_summary(res['status'])
+        self.last_fit_summary = engine.status_summary(status)
         maps = {}
         for i, name in enumerate(engine.ROW_FIELDS):
             maps[name] = host[i * L:(i + 1) * L].reshape(L, nyo, nxo).transpose(1, 2, 0)
@@ -417,7 +458,46 @@ class Luci():
             maps[name] = host[7 * L + i].reshape(nyo, nxo)
         return maps
 
+    def _peer_rows(self, n_fit, K, dev):
+        """The (cached) peer-mapped destination buffers of a sharded fit; ``None`` when the mapping is unavailable."""
+        cache = getattr(self, '_peer_cache', None)
+        if cache is None or cache[0] != (n_fit, K):
+            if cache is not None:
+                cache[1].close()
+            self._peer_cache = cache = ((n_fit, K), ldist.PeerRows(n_fit, K, dev, dst=0))
+        return cache[1] if cache[1].ok else None
+
+    def _collect_rows(self, peer, rows, status, n_fit, lo, hi, dev):
+        """Rows / status of all ranks on rank 0 (``[n_fit, K]``, ``[n_fit]``); the other ranks get their own run placed
+        in zeros.  With ``peer`` the rows are already there once every rank's stream has drained."""
+        rank = torch.distributed.get_rank()
+        world = torch.distributed.get_world_size()
+        if peer is not None:
+            peer.complete()
+            if rank == 0:
+                return peer.rows, peer.status
+            return (torch.zeros((n_fit, rows.shape[1]), dtype=torch.float32, device=dev),
+                    torch.zeros((n_fit,), dtype=torch.int32, device=dev))       # (written remotely: nothing local to show)
+        counts = [None] * world
+        torch.distributed.all_gather_object(counts, hi - lo)
+        all_rows = ldist.gather_rows(rows, dst=0, counts=counts)
+        all_status = ldist.gather_rows(status.view(-1, 1), dst=0, counts=counts)
+        if rank == 0:
+            return all_rows, all_status.view(-1)
+        full_r = torch.zeros((n_fit, rows.shape[1]), dtype=torch.float32, device=dev)
+        full_s = torch.zeros((n_fit,), dtype=torch.int32, device=dev)
+        full_r[lo:hi] = rows
+        full_s[lo:hi] = status
+        return full_r, full_s
+
+    @staticmethod
+    def _is_writer():
+        """Rank 0 writes the FITS / NPY artefacts of a sharded call."""
+        return (not ldist.is_distributed()) or torch.distributed.get_rank() == 0
+
     def _ensure_deep(self):
+        if not self._is_writer():
+            return
         if not os.path.exists(self.output_dir + '/' + self.object_name + '_deep.fits'):
             self.create_deep_image()
 
@@ -461,9 +541,10 @@ class Luci():
         m = self._fit_maps(cube_to_slice, lines, fit_function, vel_rel, sigma_rel, x_min, x_max, y_min, y_max, None,
                            use_bkg, scale, uncertainty_bool, nii_cons, spec_min, spec_max, obj_redshift, prior_values,
                            n_stoch=n_stoch, pca=pca, initial_values=initial_values, absorp=absorp)
-        save_fits(self.output_dir, self.object_name, lines, m['amplitudes'], m['fluxes'], m['flux_errors'],
-                  m['velocities'], m['sigmas'], m['vels_errors'], m['sigmas_errors'], m['chi2'], m['continuum'],
-                  m['continuum_error'], self._cutout_header(header, x_min, y_min), binning, fit_function=fit_function)
+        if self._is_writer():
+            save_fits(self.output_dir, self.object_name, lines, m['amplitudes'], m['fluxes'], m['flux_errors'],
+                      m['velocities'], m['sigmas'], m['vels_errors'], m['sigmas_errors'], m['chi2'], m['continuum'],
+                      m['continuum_error'], self._cutout_header(header, x_min, y_min), binning, fit_function=fit_function)
         self.last_fit_maps = m
         return m['velocities'], m['sigmas'], m['fluxes'], m['amplitudes']
 
@@ -516,9 +597,10 @@ class Luci():
         m = self._fit_maps(cube_to_slice, lines, fit_function, vel_rel, sigma_rel, x_min, x_max, y_min, y_max, mask,
                            None, 1.0, uncertainty_bool, nii_cons, spec_min, spec_max, obj_redshift, prior_values,
                            n_stoch=n_stoch, initial_values=initial_values)
-        save_fits(self.output_dir, self.object_name, lines, m['amplitudes'], m['fluxes'], m['flux_errors'],
-                  m['velocities'], m['sigmas'], m['vels_errors'], m['sigmas_errors'], m['chi2'], m['continuum'],
-                  m['continuum_error'], self._cutout_header(header, x_min, y_min), binning)
+        if self._is_writer():
+            save_fits(self.output_dir, self.object_name, lines, m['amplitudes'], m['fluxes'], m['flux_errors'],
+                      m['velocities'], m['sigmas'], m['vels_errors'], m['sigmas_errors'], m['chi2'], m['continuum'],
+                      m['continuum_error'], self._cutout_header(header, x_min, y_min), binning)
         self.last_fit_maps = m
         return m['velocities'], m['sigmas'], m['fluxes'], m['chi2'], mask
 

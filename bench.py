@@ -51,6 +51,7 @@ def parse():
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--no-e2e', action='store_true')
     ap.add_argument('--no-reductions', action='store_true')
+    ap.add_argument('--no-api', action='store_true')
     return ap.parse_args()
 
 
@@ -251,10 +252,20 @@ def main():
     K = cfg.row_floats
 
     counts = [(lambda b: (b[1] - b[0]) * args.ny)(ldist.shard_bounds(args.nx, r, world)) for r in range(world)]
-    gathered = torch.empty((n_total, K), dtype=torch.float32, device=dev) if (world > 1 and rank == 0) else None
+    # N > 1: no gather step -- every rank's output kernel stores its rows straight into rank 0's [n_total, K] buffer
+    # through peer-mapped memory (dist.PeerRows); NCCL point-to-point into the same buffer only if the mapping fails
+    peer = ldist.PeerRows(n_total, K, dev, dst=0) if world > 1 else None
+    use_peer = peer is not None and peer.ok
+    row_lo = sum(counts[:rank])
+    rows_win = peer.window(row_lo, row_lo + n_local)[0] if use_peer else None
+    gathered = peer.rows if (peer is not None and rank == 0) else None
+    status_loc = torch.empty((n_local,), dtype=torch.int32, device=dev)
 
     def step():
-        res = engine.fit_batch(cfg, cube, theta, v0, b0)
+        if use_peer:
+            res = engine.fit_batch(cfg, cube, theta, v0, b0, rows=rows_win, status=status_loc)
+            return res, gathered
+        res = engine.fit_batch(cfg, cube, theta, v0, b0, status=status_loc)
         rows = ldist.gather_rows(res['rows'], dst=0, counts=counts, out=gathered) if world > 1 else res['rows']
         return res, rows
 
@@ -300,8 +311,14 @@ def main():
     stage_ms = engine.fit_batch(cfg, cube, theta, v0, b0, time_stages=True)['stage_ms']
     kern_ms = ldist.max_over_ranks(float(stage_ms['lm']), dev)
     n_slices = (n_local + engine.SLICE_SPAXELS - 1) // engine.SLICE_SPAXELS
-    fp32_peak = engine.peak_probe(dev, 0)
+    fp32_probe = engine.peak_probe(dev, 0)
     mufu_peak = engine.peak_probe(dev, 1)
+    # FP32 roofline: MEASURED_PEAKS.json and the profiling guide carry no FP32 figure, so the denominator is the nominal
+    # FMA rate at the SM clock sampled during the timed region (SMs x 128 lanes x 2 flop x f); the FFMA-chain probe of
+    # this run is reported beside it (it reaches ~83 % of nominal)
+    props = torch.cuda.get_device_properties(dev)
+    sm_mhz = clocks.get('sm_mhz') or clocks.get('sm_max_mhz') or 1965.0
+    fp32_peak = props.multi_processor_count * 128 * 2 * sm_mhz * 1e6 / 1e12
     achieved = (W * n_local) / (kern_ms * 1e-3) / 1e12
     alg_bytes = n_local * (4 * args.nz + 4 * K + 16)
     peaks = {}
@@ -319,9 +336,9 @@ def main():
         pass
     roofline = {'bound': 'fp32', 'achieved': achieved, 'peak': fp32_peak, 'unit': 'TFLOP/s',
                 'frac': achieved / fp32_peak if fp32_peak else None, 'traffic': traffic, 'traffic_source': traffic_src,
-                'peak_source': 'lucifit_peak_probe FFMA chains, measured in this run (nominal 74.4 at 1965 MHz); '
-                               'MEASURED_PEAKS.json has no FP32 figure',
-                'mufu_peak_tops': mufu_peak, 'mean_evals_E': mean_E, 'flop_per_spaxel_W': W,
+                'peak_source': 'nominal FP32 FMA rate = %d SMs x 128 lanes x 2 flop x %.0f MHz (SM clock sampled during the timed '
+                               'region); MEASURED_PEAKS.json / B200_PROFILING.md state no FP32 figure' % (props.multi_processor_count, sm_mhz),
+                'fp32_probe_tflops': fp32_probe, 'mufu_peak_tops': mufu_peak, 'mean_evals_E': mean_E, 'flop_per_spaxel_W': W,
                 'kernel': 'lf_lm_kernel<%s,L=5,groups=1>' % model, 'kernel_ms': kern_ms,
                 'launches': n_slices, 'stage_ms': {k: float(v) for k, v in stage_ms.items()},
                 'kernel_share_of_step': kern_ms / sum(stage_ms.values()),
@@ -332,10 +349,12 @@ def main():
             'warmup': args.warmup, 'ms_per_step': ms_per_step, 'higher_is_better': True, 'scaling': 'strong',
             'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
             'config': {'workload': 'full %dx%d synthetic SN3 cube, nz=%d (N_fit=%d), 5-line %s, tied velocity/broadening '
-                                   '+ [NII] ratio tie, fit_entire_cube%s' % (args.nx, args.ny, args.nz, nfit, model,
-                                                                             ' + uncertainties' if unc else ''),
-                       'sharding': 'contiguous x-slabs, %d rank(s); gather of the (7L+5) float32 rows to rank 0 inside '
-                                   'the step' % world,
+                                   '+ [NII] ratio tie%s; timed step = one lucifit_fit_batch pass (engine.fit_batch: prep + LM + '
+                                   'output kernels) over the cube resident in HBM; the Luci.fit_entire_cube call itself is '
+                                   'timed in api_e2e' % (args.nx, args.ny, args.nz, nfit, model, ' + uncertainties' if unc else ''),
+                       'sharding': 'contiguous x-slabs, %d rank(s); rows of every rank land in rank 0\'s [n, 7L+5] buffer inside '
+                                   'the step (%s)' % (world, 'stored by the output kernel through peer-mapped memory' if use_peer
+                                                      else 'single GPU' if world == 1 else 'NCCL point-to-point gather'),
                        'l2': 'inputs (%.1f GB per rank) larger than L2' % (cube.numel() * 4 / 1e9),
                        'priors': 'truth + N(0,15 km/s), truth*(1+N(0,0.15))', 'snr': 'log-uniform 10..100'},
             'gpu_launches': launches, 'clocks': clocks, 'roofline': roofline,
@@ -430,6 +449,13 @@ def main():
     # --- end to end: cube in pinned host memory, streamed in chunks through the C ABI
     if not args.no_e2e:
         line['e2e'] = run_e2e(torch, engine, ldist, cfg, cube, theta, v0, b0, dev, args, world, n_total, K)
+    # --- the drop-in call: Luci.fit_entire_cube on the full cube (every rank holds it, like every joblib worker of the
+    # reference sees cube_final), sharded over the ranks, FITS maps written by rank 0 -- wall clock around the call
+    if not args.no_api:
+        try:
+            line['api_e2e'] = run_api(torch, ldist, args, dev, rank, world, model, unc)
+        except Exception as exc:
+            line['api_e2e'] = {'error': repr(exc)}
     if rank == 0 and world == 1 and not args.no_cpu_baseline:      # reported baseline: rank 0 at N = 1 only
         cb, _, _ = run_cpu_arm(args.nz, model, unc, budget_s=args.cpu_seconds)
         line['cpu_baseline'] = cb
@@ -439,6 +465,45 @@ def main():
         emit(line)
     if world > 1:
         torch.distributed.destroy_process_group()
+
+
+def run_api(torch, ldist, args, dev, rank, world, model, unc):
+    """Wall clock of ``Luci.fit_entire_cube`` (the call a LUCI user makes) on the full synthetic cube at N GPUs: rank r
+    fits its y-rows, rows land in rank 0's maps through peer memory, rank 0 writes the FITS maps the reference writes
+    (38 files for 5 lines).  The cube is resident on every GPU before the call (as ``cube_final`` is resident in host
+    RAM before the reference's call); priors are passed as host maps like a user would."""
+    import shutil
+    import tempfile
+    from luci_b200.luci import Luci
+    from luci_b200.sim import SyntheticCube
+    sc = SyntheticCube(args.nx, args.ny, lines=LINES, model=model, n_steps=args.nz)
+    cube3 = sc.synthesize(dev, seed=1000)
+    out = tempfile.mkdtemp(prefix='luci_bench_api_r%d_' % rank)
+    try:
+        luci = Luci.from_arrays(cube3, sc.hdr_dict, out, 'BENCH', spectrum_axis=sc.axis32, device=dev)
+        luci.create_deep_image()                                       # (fit_cube writes it once if missing: not part of the fit)
+        v0m, b0m = sc.priors()
+        times = []
+        for it in range(3):
+            if world > 1:
+                torch.distributed.barrier()
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            luci.fit_entire_cube(LINES, model, [1] * 5, [1] * 5, prior_values=(v0m, b0m), uncertainty_bool=unc)
+            torch.cuda.synchronize()
+            if world > 1:
+                torch.distributed.barrier()
+            times.append(time.perf_counter() - t0)
+        dt = ldist.max_over_ranks(min(times[1:]), dev)
+        n = args.nx * args.ny
+        summ = luci.last_fit_summary if rank == 0 else None
+        n_files = sum(len(f) for _, _, f in os.walk(out)) if rank == 0 else 0
+        return {'value': n / dt, 'unit': 'spaxels/s', 'seconds_per_call': dt, 'calls_timed': 2, 'n_gpus': world,
+                'fits_files_written': n_files, 'n_converged': summ['n_converged'] if summ else None,
+                'note': 'wall clock around Luci.fit_entire_cube(lines, %r, vel_rel, sigma_rel, prior_values=host maps): sharding, '
+                        'fit, rows to rank 0, host maps, FITS output included; best of 2 calls after one warm-up' % model}
+    finally:
+        shutil.rmtree(out, ignore_errors=True)
 
 
 def run_e2e(torch, engine, ldist, cfg, cube, theta, v0, b0, dev, args, world, n_total, K):
@@ -472,6 +537,16 @@ def run_e2e(torch, engine, ldist, cfg, cube, theta, v0, b0, dev, args, world, n_
     probe.copy_(host_cube[:probe.shape[0]], non_blocking=True)
     e1.record(); e1.synchronize()
     h2d_gbs = probe.numel() * 4 / (e0.elapsed_time(e1) * 1e-3) / 1e9
+    # ... and with ALL ranks copying at the same time (what the streamed fit asks of the host at N > 1)
+    h2d_conc = h2d_gbs
+    if world > 1:
+        torch.distributed.barrier()
+        torch.cuda.synchronize(); e0.record()
+        for _ in range(4):
+            probe.copy_(host_cube[:probe.shape[0]], non_blocking=True)
+        e1.record(); e1.synchronize()
+        mine = 4 * probe.numel() * 4 / (e0.elapsed_time(e1) * 1e-3) / 1e9
+        h2d_conc = ldist.sum_over_ranks(mine, dev) / world
     del probe
     stream = engine.HostCubeStream(cfg, dev)
     stream.run(host_cube, host_par, host_rows)                       # warm-up
@@ -490,6 +565,7 @@ def run_e2e(torch, engine, ldist, cfg, cube, theta, v0, b0, dev, args, world, n_
     return {'value': n_done / dt, 'unit': 'spaxels/s', 'h2d_bytes_per_step': h2d,
             'd2h_bytes_per_step': int(n_done * K * 4), 'ms_per_step': dt * 1e3,
             'h2d_gbs_achieved_per_gpu': h2d / world / dt / 1e9, 'h2d_gbs_single_copy': h2d_gbs,
+            'h2d_gbs_concurrent_copy_per_gpu': h2d_conc,
             'note': 'cube in pinned host memory (process bound to the GPU-local CPU cores when N > 1), engine.HostCubeStream: %d-spaxel chunks, %d device buffers, copy / fit / '
                     'copy-back on three streams; fraction of the cube streamed per step: %.2f'
                     % (stream.chunk, stream.nb, frac)}

@@ -174,6 +174,16 @@ int lucifit_sim_cube(const lucifit_config* cfg, int64_t n_spaxel, const float* a
                      float flux_scale, float* cube /*[n][nz]*/, void* workspace, size_t workspace_bytes,
                      void* stream);
 
+/* Integrated spectra: sums[segment[i]][z] += cube[row_index[i]][z] for i < n_sel, float64 -- the spaxel loops of
+ * fit_spectrum_region (LuciBase.py:1015-1023), extract_spectrum / extract_spectrum_region (:872-889, :931-941), the
+ * per-bin spectra of fit_wvt (:1434-1447) and the region spectra of skyline_calibration (:1254-1256) as ONE pass.
+ * row_index: [n_sel] DEVICE rows of cube[.][nz] (NULL: rows 0..n_sel-1); segment: [n_sel] DEVICE ids in
+ * [0, n_segments), negative = skip (NULL: everything into segment 0); a list ordered by segment is fastest.
+ * nansum != 0 skips NaN samples (np.nansum), 0 lets them poison the channel like `+=` in the reference.
+ * sums: [n_segments][nz] DEVICE doubles, zeroed by the call. */
+int lucifit_segment_sum(const float* cube, int nz, const int64_t* row_index, const int32_t* segment, int64_t n_sel,
+                        int n_segments, int nansum, double* sums, void* stream);
+
 /* Peer rows -- the multi-GPU "gather" of a sharded fit without a gather step.  The reference collects the rows of its
  * joblib workers on the host (LuciBase.py:514-551); here every rank's lucifit_fit_batch writes its (7L+5)-float rows
  * and status words STRAIGHT into the destination rank's map buffer over NVLink: the destination exports its buffer,

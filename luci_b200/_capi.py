@@ -43,7 +43,7 @@ class lucifit_config(C.Structure):
 
 EXPORTS = ['lucifit_row_floats', 'lucifit_workspace_bytes', 'lucifit_fit_batch', 'lucifit_fit_stages', 'lucifit_deep_image',
            'lucifit_snr_map', 'lucifit_bin_cube', 'lucifit_sim_cube', 'lucifit_peak_probe', 'lucifit_estimate_prior',
-           'lucifit_sanitize_cube', 'lucifit_peer_export', 'lucifit_peer_open', 'lucifit_peer_close', 'lucifit_last_error',
+           'lucifit_sanitize_cube', 'lucifit_segment_sum', 'lucifit_peer_export', 'lucifit_peer_open', 'lucifit_peer_close', 'lucifit_last_error',
            'lucifit_version']
 
 _lib = None
@@ -75,6 +75,8 @@ def declare(lib):
     lib.lucifit_estimate_prior.restype = C.c_int
     lib.lucifit_sanitize_cube.argtypes = [vp, i64, C.c_float, C.c_float, C.c_float, vp]
     lib.lucifit_sanitize_cube.restype = C.c_int
+    lib.lucifit_segment_sum.argtypes = [vp, C.c_int, vp, vp, i64, C.c_int, C.c_int, vp, vp]
+    lib.lucifit_segment_sum.restype = C.c_int
     lib.lucifit_peer_export.argtypes = [vp, vp, C.POINTER(C.c_uint64)]
     lib.lucifit_peer_export.restype = C.c_int
     lib.lucifit_peer_open.argtypes = [vp, C.c_uint64, C.POINTER(vp)]
@@ -113,8 +115,8 @@ class FitConfig:
     """Python owner of a ``lucifit_config`` (keeps the numpy arrays the struct points to alive).
 
     Arguments mirror ``LUCI.LuciFit.Fit.__init__`` (LuciFit.py:49-57).  ``axis`` is the float32 spectral axis of
-    the cube (LuciUtility.py:154-157); it is multiplied by ``1 + obj_redshift`` in float64 like the reference
-    (LuciFit.py:113).
+    the cube (LuciUtility.py:154-157); it is multiplied by ``1 + obj_redshift`` in float32 like the reference
+    (LuciFit.py:113: float32 array times python float).
     """
 
     def __init__(self, model_type, lines, vel_rel, sigma_rel, axis, filter='SN3', delta_x=2943, n_steps=842,
@@ -141,7 +143,10 @@ class FitConfig:
         self.lines = list(lines)
         self.L = len(lines)
         corr = 1.0 + obj_redshift
-        self.axis = np.ascontiguousarray(np.asarray(axis, dtype=np.float64) * corr)
+        # the reference multiplies its float32 axis by a python float, which stays float32 (LuciFit.py:113): the same
+        # rounding here, then widened -- window edges and snapped centres are argmins over exactly these values
+        self.axis = np.ascontiguousarray((np.asarray(axis, dtype=np.float32) * np.float32(corr)).astype(np.float64)
+                                         if obj_redshift != 0.0 else np.asarray(axis, dtype=np.float64))
         self.trans = None if trans_filter is None else np.ascontiguousarray(trans_filter, dtype=np.float64)
         if spec_min is None or spec_max is None:
             spec_min, spec_max = fit_window(filter, lines, corr)

@@ -57,6 +57,9 @@ extern "C" cudaError_t lf_run_bin(const float* cube, int ny, int nz, int b, int 
                                   float* out, int sm_count, cudaStream_t stream);
 extern "C" cudaError_t lf_run_sim(const LfSimArgs* a, int sm_count, cudaStream_t stream);
 extern "C" cudaError_t lf_run_peak(int mode, int iters, int blocks, float* out, cudaStream_t stream);
+extern "C" cudaError_t lf_run_segsum(const float* cube, int nz, const long long* row_index, const int* segment,
+                                     long long n_sel, int n_segments, int nansum, double* sums, int sm_count,
+                                     cudaStream_t stream);
 extern "C" cudaError_t lf_run_sanitize(float* cube, long long n, float lo, float hi, float fill, int sm_count, cudaStream_t stream);
 extern "C" cudaError_t lf_run_prior(const LfPriorCfg* c, long long n, const float* cube, const long long* index,
                                     const float* theta, float* vel, float* broad, int sm_count, cudaStream_t stream);
@@ -265,6 +268,18 @@ int lucifit_sanitize_cube(float* cube, int64_t n_values, float lo, float hi, flo
     int sm = 0; int rc = sm_count_of_current_device(&sm); if (rc) return rc;
     cudaError_t e = lf_run_sanitize(cube, n_values, lo, hi, fill, sm, (cudaStream_t)stream);
     if (e != cudaSuccess) return cuda_fail(e, "launch lf_sanitize_kernel");
+    return 0;
+}
+
+int lucifit_segment_sum(const float* cube, int nz, const int64_t* row_index, const int32_t* segment, int64_t n_sel,
+                        int n_segments, int nansum, double* sums, void* stream)
+{
+    if (nz < 1 || n_sel < 0 || n_segments < 1 || !sums) return fail(LUCIFIT_EINVAL, "bad argument");
+    if (n_sel > 0 && !cube) return fail(LUCIFIT_EINVAL, "cube is required");
+    int sm = 0; int rc = sm_count_of_current_device(&sm); if (rc) return rc;
+    cudaError_t e = lf_run_segsum(cube, nz, (const long long*)row_index, (const int*)segment, n_sel, n_segments, nansum,
+                                  sums, sm, (cudaStream_t)stream);
+    if (e != cudaSuccess) return cuda_fail(e, "launch lf_segsum_kernel");
     return 0;
 }
 

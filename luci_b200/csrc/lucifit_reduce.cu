@@ -619,3 +619,82 @@ extern "C" cudaError_t lf_run_sanitize(float* cube, long long n, float lo, float
     lf_sanitize_kernel<<<grid, 256, 0, stream>>>(cube, n, lo, hi, fill);
     return cudaGetLastError();
 }
+
+// --------------------------------------------------------------------------------------------- segmented sums
+// Integrated spectra: sums[seg][z] += cube[row][z] over a list of (row, segment) pairs -- the spaxel loops of
+// Luci.fit_spectrum_region (LuciBase.py:1015-1023), extract_spectrum(_region) (:872-889, :931-941), the per-bin
+// fit_spectrum_region calls of fit_wvt (:1434-1447) and the region spectra of skyline_calibration (:1254-1256), in
+// float64 like the reference.  A CTA owns a contiguous chunk of the list and the threads own spectral columns
+// (coalesced row reads, LF_SEG_ROWS rows in flight); the running sums stay in registers while consecutive pairs name the
+// same segment and are flushed with one float64 atomic per column when the segment changes or the chunk ends, so a
+// list ordered by segment costs (segments + CTAs) x nz atomics in all.
+#define LF_SEG_THREADS 256
+#define LF_SEG_COLS 4
+#define LF_SEG_ROWS 4
+__global__ void __launch_bounds__(LF_SEG_THREADS)
+lf_segsum_kernel(const float* __restrict__ cube, int nz, const long long* __restrict__ row_index,
+                 const int* __restrict__ segment, long long n_sel, long long rows_per_cta, int nansum,
+                 double* __restrict__ sums)
+{
+    const long long lo = (long long)blockIdx.x * rows_per_cta;
+    const long long hi = lo + rows_per_cta < n_sel ? lo + rows_per_cta : n_sel;
+    for (int z0 = threadIdx.x; z0 < nz; z0 += LF_SEG_THREADS * LF_SEG_COLS) {
+        double acc[LF_SEG_COLS];
+#pragma unroll
+        for (int c = 0; c < LF_SEG_COLS; ++c) acc[c] = 0.0;
+        int cur = -1;
+        auto flush = [&]() {
+            if (cur >= 0) {
+#pragma unroll
+                for (int c = 0; c < LF_SEG_COLS; ++c) {
+                    const int z = z0 + c * LF_SEG_THREADS;
+                    if (z < nz) atomicAdd(sums + (long long)cur * nz + z, acc[c]);
+                }
+            }
+#pragma unroll
+            for (int c = 0; c < LF_SEG_COLS; ++c) acc[c] = 0.0;
+        };
+        for (long long i0 = lo; i0 < hi; i0 += LF_SEG_ROWS) {
+            int seg[LF_SEG_ROWS];
+            float q[LF_SEG_ROWS][LF_SEG_COLS];
+#pragma unroll
+            for (int r = 0; r < LF_SEG_ROWS; ++r) {
+                const long long i = i0 + r;
+                seg[r] = i < hi ? (segment ? segment[i] : 0) : -1;
+                const long long row = i < hi ? (row_index ? row_index[i] : i) : 0;
+                const float* rp = cube + row * (long long)nz;
+#pragma unroll
+                for (int c = 0; c < LF_SEG_COLS; ++c) {
+                    const int z = z0 + c * LF_SEG_THREADS;
+                    q[r][c] = (seg[r] >= 0 && z < nz) ? __ldcs(rp + z) : 0.0f;
+                }
+            }
+#pragma unroll
+            for (int r = 0; r < LF_SEG_ROWS; ++r) {
+                if (seg[r] < 0) continue;                              // (uniform over the CTA)
+                if (seg[r] != cur) { flush(); cur = seg[r]; }
+#pragma unroll
+                for (int c = 0; c < LF_SEG_COLS; ++c) {
+                    const float v = q[r][c];
+                    acc[c] += (nansum && v != v) ? 0.0 : (double)v;
+                }
+            }
+        }
+        flush();
+    }
+}
+
+extern "C" cudaError_t lf_run_segsum(const float* cube, int nz, const long long* row_index, const int* segment,
+                                     long long n_sel, int n_segments, int nansum, double* sums, int sm_count,
+                                     cudaStream_t stream)
+{
+    cudaError_t e = cudaMemsetAsync(sums, 0, sizeof(double) * (size_t)n_segments * nz, stream);
+    if (e != cudaSuccess || n_sel <= 0) return e;
+    long long ctas = (long long)sm_count * 8;
+    long long per = (n_sel + ctas - 1) / ctas;
+    if (per < 4 * LF_SEG_ROWS) per = 4 * LF_SEG_ROWS;                 // short lists: fewer CTAs, fewer atomics
+    per = (per + LF_SEG_ROWS - 1) / LF_SEG_ROWS * LF_SEG_ROWS;
+    const int grid = (int)((n_sel + per - 1) / per);
+    lf_segsum_kernel<<<grid, LF_SEG_THREADS, 0, stream>>>(cube, nz, row_index, segment, n_sel, per, nansum, sums);
+    return cudaGetLastError();
+}

@@ -321,6 +321,28 @@ def bin_cube(cube3d, binning, x_min, x_max, y_min, y_max):
     return out
 
 
+def segment_sum(cube2d, row_index=None, segment=None, n_segments=1, nansum=False):
+    """``lucifit_segment_sum``: float64 ``[n_segments, nz]`` sums of the rows ``row_index`` (int64, default all rows) of
+    ``cube2d [n_rows, nz]`` into the segments ``segment`` (int32, default all into segment 0; negative = skip)."""
+    lib = _capi.lib()
+    require_cuda(cube2d, 'cube', torch.float32)
+    dev = cube2d.device
+    nz = int(cube2d.shape[1])
+    if row_index is not None:
+        require_cuda(row_index, 'row_index', torch.int64)
+    if segment is not None:
+        require_cuda(segment, 'segment', torch.int32)
+    n_sel = int(row_index.numel()) if row_index is not None else (int(segment.numel()) if segment is not None else int(cube2d.shape[0]))
+    if segment is not None and segment.numel() != n_sel:
+        raise ValueError('segment must have one entry per selected row')
+    sums = torch.empty((int(n_segments), nz), dtype=torch.float64, device=dev)
+    with torch.cuda.device(dev):
+        check(lib.lucifit_segment_sum(_ptr(cube2d), nz, _ptr(row_index), _ptr(segment), n_sel, int(n_segments),
+                                      int(bool(nansum)), _ptr(sums), _stream()))
+    launch_counter['n'] += 1 if n_sel > 0 else 0
+    return sums
+
+
 def sanitize_cube(cube, lo=-1e-16, hi=1e-9, fill=1e-22):
     """In-place clamp of ``Luci.read_in_cube`` (LuciBase.py:123-129) on a contiguous float32 device tensor."""
     lib = _capi.lib()

@@ -420,24 +420,9 @@ class Luci():
         else:
             res = engine.fit_batch(cfg, cube2d, theta_t, v0, b0, index=index, bkg=bkg_t)
         rows = res['rows']
-        for st in range(1, int(n_stoch)):
-            # random restarts (LuciFit.py:662-687): the reference redraws every line's position from
-            # N(p, |1e7/lambda - p| / 50) and sigma from N(sigma, sigma / 10) with numpy's global generator and keeps
-            # the fit with the lowest loss; in velocity units that is v ~ N(v0, |v0| / 50), b ~ N(b0, b0 / 10) per tie
-            # group, drawn here with the same generator and compared on the chi2 each fit reports
-            if not have_prior:
-                break                                                   # all draws would equal the start (v0 = b0 = 0)
-            # (drawn for the whole fitted list and sliced, so that a sharded call with equally seeded ranks makes the
-            # draws of the single-process call)
-            v_np, b_np = v0.cpu().numpy().astype(np.float64), b0.cpu().numpy().astype(np.float64)
-            wv, wb = v_np.size // max(hi - lo, 1), b_np.size // max(hi - lo, 1)
-            zv = np.random.standard_normal((n_fit, wv))[lo:hi].reshape(-1)
-            zb = np.random.standard_normal((n_fit, wb))[lo:hi].reshape(-1)
-            v_r = torch.from_numpy((v_np + np.abs(v_np) / 50.0 * zv).astype(np.float32)).to(dev)
-            b_r = torch.from_numpy((b_np + np.abs(b_np) / 10.0 * zb).astype(np.float32)).to(dev)
-            alt = engine.fit_batch(cfg, cube2d, theta_t, v_r, b_r, index=index, bkg=bkg_t)
-            res = engine.keep_best(res, alt, 7 * L_)
-            rows = res['rows']
+        if have_prior:                                                  # (without a prior all draws would equal the start)
+            res = self._restarts(cfg, cube2d, theta_t, v0, b0, res, n_stoch, n_fit, lo, hi, index=index, bkg=bkg_t)
+        rows = res['rows']
         status = res['status']
         if sharded:
             rows, status = self._collect_rows(peer, rows, status, n_fit, lo, hi, dev)
@@ -457,6 +442,33 @@ class Luci():
         for i, name in enumerate(engine.ROW_SCALARS):
             maps[name] = host[7 * L + i].reshape(nyo, nxo)
         return maps
+
+    def _mask_rows(self, mask_np):
+        """int64 device row list (x-major, the order of the reference's spaxel loops) of a boolean ``(nx, ny)`` mask."""
+        m = np.asarray(mask_np).astype(bool)
+        nx, ny = self.cube_final.shape[:2]
+        if m.shape != (nx, ny):
+            raise ValueError('mask must be (nx, ny) = %s' % ((nx, ny),))
+        return torch.from_numpy(np.flatnonzero(m.reshape(-1)).astype(np.int64)).to(self.cube_final.device)
+
+    def _restarts(self, cfg, cube2d, theta_t, v0, b0, res, n_stoch, n_global, lo, hi, index=None, bkg=None, **kw):
+        """Random restarts (``LuciFit.py:662-687``): the reference redraws every line's position from
+        ``N(p, |1e7/lambda - p| / 50)`` and sigma from ``N(sigma, sigma / 10)`` with numpy's global generator and keeps the
+        fit with the lowest loss; in velocity units that is ``v ~ N(v0, |v0| / 50)``, ``b ~ N(b0, b0 / 10)`` per tie
+        group, drawn here with the same generator and compared on the chi2 each fit reports.  Every restart is one more
+        batch call over the same spaxels.  The draws are made for the whole fitted list (``n_global``) and sliced to
+        ``[lo, hi)``, so that a sharded call with equally seeded ranks makes the draws of the single-process call."""
+        dev = theta_t.device
+        for st in range(1, int(n_stoch)):
+            v_np, b_np = v0.cpu().numpy().astype(np.float64), b0.cpu().numpy().astype(np.float64)
+            wv, wb = v_np.size // max(hi - lo, 1), b_np.size // max(hi - lo, 1)
+            zv = np.random.standard_normal((n_global, wv))[lo:hi].reshape(-1)
+            zb = np.random.standard_normal((n_global, wb))[lo:hi].reshape(-1)
+            v_r = torch.from_numpy((v_np + np.abs(v_np) / 50.0 * zv).astype(np.float32)).to(dev)
+            b_r = torch.from_numpy((b_np + np.abs(b_np) / 10.0 * zb).astype(np.float32)).to(dev)
+            alt = engine.fit_batch(cfg, cube2d, theta_t, v_r, b_r, index=index, bkg=bkg, **kw)
+            res = engine.keep_best(res, alt, 7 * cfg.L)
+        return res
 
     def _peer_rows(self, n_fit, K, dev):
         """The (cached) peer-mapped destination buffers of a sharded fit; ``None`` when the mapping is unavailable."""
@@ -609,15 +621,14 @@ class Luci():
                             nii_cons=True, spec_min=None, spec_max=None, obj_redshift=0.0, n_stoch=1,
                             prior_values=None):
         """``LuciBase.py:949-1046``: fit the spectrum integrated over a mask.  Returns ``(axis, sky, fit_dict)``.
-        ``prior_values=(vel, broad)`` are scalars in km/s."""
+        ``prior_values=(vel, broad)`` are scalars in km/s; ``initial_values=[vel, broad]`` holds them fixed (the freeze
+        branch, ``LuciFit.py:688-709``); ``n_stoch`` restarts like ``LuciFit.py:662-687``.  NaN channels of the
+        integrated spectrum are left out of the fit like the reference's ``good_sky_inds`` (``:1027-1030``)."""
         self._reject_unsupported(bayes_bool, None, initial_values, n_stoch, None)
-        if int(n_stoch) != 1:
-            raise NotImplementedError('n_stoch > 1 is implemented for the cube fits (fit_cube / fit_region) only')
-        if len(initial_values) >= 1 and initial_values[0] is not False:
-            raise NotImplementedError('initial_values (freeze) is implemented for the cube fits (fit_cube / fit_region) only')
-        mask = torch.from_numpy(np.asarray(self._load_mask(region, False)).astype(bool)).to(self.cube_final.device)
-        spec_ct = int(mask.sum().item())
-        integrated = self.cube_final[mask].sum(dim=0, dtype=torch.float64)
+        rows = self._mask_rows(self._load_mask(region, False))
+        spec_ct = int(rows.numel())
+        nx_, ny_, nz_ = self.cube_final.shape
+        integrated = engine.segment_sum(self.cube_final.view(nx_ * ny_, nz_), rows)[0]      # `+=` of :1019: NaN poisons a channel
         if mean:
             integrated = integrated / spec_ct
         if bkg is not None:
@@ -625,19 +636,27 @@ class Luci():
         # the reference passes the angle of the LAST pixel of its double loop (LuciBase.py:1035)
         theta = float(self.interferometer_theta[self.cube_final.shape[0] - 1, self.cube_final.shape[1] - 1])
         fit_dict = self._fit_one_spectrum(integrated, theta, lines, fit_function, vel_rel, sigma_rel, uncertainty_bool,
-                                          nii_cons, spec_min, spec_max, obj_redshift, prior_values)
+                                          nii_cons, spec_min, spec_max, obj_redshift, prior_values, n_stoch=n_stoch,
+                                          initial_values=initial_values)
         sky = integrated.cpu().numpy()
         return np.asarray(self.spectrum_axis), sky, fit_dict
 
     def _fit_one_spectrum(self, spectrum, theta, lines, fit_function, vel_rel, sigma_rel, uncertainty_bool, nii_cons,
-                          spec_min, spec_max, obj_redshift, prior_values):
+                          spec_min, spec_max, obj_redshift, prior_values, n_stoch=1, initial_values=(False,)):
         """One spectrum (device tensor ``[nz]``) through ``lucifit_fit_batch``; returns the dictionary of
         ``Fit.fit`` (``LuciFit.py:824-834``).  Shared by fit_spectrum_region / fit_pixel."""
         sky32 = spectrum.to(torch.float32).view(1, -1).contiguous()
+        freeze = len(initial_values) >= 2 and initial_values[0] is not False
+        if freeze:
+            if uncertainty_bool:
+                raise NotImplementedError('uncertainty_bool with initial_values is broken in the reference '
+                                          '(LuciFit.py:713-722 on an L+1 vector) and not offered')
+            prior_values = (float(np.asarray(initial_values[0]).reshape(-1)[0]), float(np.asarray(initial_values[1]).reshape(-1)[0]))
+            n_stoch = 1
         have_prior = prior_values is not None
         auto_prior = (not have_prior) and bool(self.ML_bool)
         cfg = self._make_config(lines, fit_function, vel_rel, sigma_rel, uncertainty_bool, nii_cons, spec_min, spec_max,
-                                obj_redshift, ml_scale=have_prior or auto_prior)
+                                obj_redshift, ml_scale=have_prior or auto_prior, freeze=freeze)
         dev = sky32.device
         th = torch.tensor([theta], dtype=torch.float32, device=dev)
         v0 = torch.tensor([float(prior_values[0])], dtype=torch.float32, device=dev) if have_prior else None
@@ -647,6 +666,8 @@ class Luci():
             prior_values = (float(v0[0].item()), float(b0[0].item()))
             have_prior = True
         res = engine.fit_batch(cfg, sky32, th, v0, b0, want_sol=True, want_unc=True)
+        if have_prior and int(n_stoch) > 1:
+            res = self._restarts(cfg, sky32, th, v0, b0, res, n_stoch, 1, 0, 1, want_sol=True, want_unc=True)
         L = len(lines)
         row = res['rows'][0].cpu().numpy()
         q = engine.unpack_rows(row[None, :], L)
@@ -679,14 +700,16 @@ class Luci():
         The reference subtracts in place from a view of ``cube_final`` (``:767-769``), altering the cube; that side
         effect is not reproduced.  ``prior_values=(vel, broad)`` are scalars in km/s."""
         self._reject_unsupported(bayes_bool, absorp, [False], n_stoch, bkgType)
-        if int(n_stoch) != 1:
-            raise NotImplementedError('n_stoch > 1 is implemented for the cube fits (fit_cube / fit_region) only')
         if absorp is not None:
             raise NotImplementedError('absorp is implemented for fit_cube only')
         b = int(binning) if (binning is not None and binning != 1) else 0
         if b:
-            box = self.cube_final[max(pixel_x - b, 0):pixel_x + b, max(pixel_y - b, 0):pixel_y + b, :]
-            sky = torch.nan_to_num(box.to(torch.float64), nan=0.0).sum(dim=(0, 1))
+            nx_, ny_, nz_ = self.cube_final.shape
+            dev_ = self.cube_final.device
+            xs = torch.arange(max(pixel_x - b, 0), min(pixel_x + b, nx_), dtype=torch.int64, device=dev_)
+            ys = torch.arange(max(pixel_y - b, 0), min(pixel_y + b, ny_), dtype=torch.int64, device=dev_)
+            sky = engine.segment_sum(self.cube_final.view(nx_ * ny_, nz_), (xs[:, None] * ny_ + ys[None, :]).reshape(-1),
+                                     nansum=True)[0]
         else:
             sky = self.cube_final[pixel_x, pixel_y, :].to(torch.float64)
         if bkgType == 'standard':
@@ -712,12 +735,10 @@ class Luci():
             sky = sky - scale_spec * torch.from_numpy(bkg_pix).to(sky.device)
         else:
             raise Exception('Please set bkgType to either standard or pca')
-        if bool(torch.isnan(sky).any()):
-            raise NotImplementedError('fit_pixel: NaN channels (the reference drops them, LuciBase.py:801-803) are not '
-                                      'supported; spectra with NaNs are returned as zeros by the cube fits')
+        # NaN channels are left out of the fit like the reference's good_sky_inds (LuciBase.py:801-803)
         theta = float(self.interferometer_theta[pixel_x, pixel_y])
         fit_dict = self._fit_one_spectrum(sky, theta, lines, fit_function, vel_rel, sigma_rel, uncertainty_bool, nii_cons,
-                                          spec_min, spec_max, obj_redshift, prior_values)
+                                          spec_min, spec_max, obj_redshift, prior_values, n_stoch=n_stoch)
         return np.asarray(self.spectrum_axis), sky.cpu().numpy(), fit_dict
 
     def extract_spectrum(self, x_min, x_max, y_min, y_max, bkg=None, binning=None, mean=False):
@@ -732,9 +753,12 @@ class Luci():
             y_max = int((y_max - y_min) / binning)
             x_min = y_min = 0
             cube = self.cube_binned
-        box = cube[x_min:x_max, y_min:y_max, :]
-        n_spec = box.shape[0] * box.shape[1]
-        integrated = torch.nan_to_num(box.to(torch.float64), nan=0.0).sum(dim=(0, 1))
+        nxc_, nyc_, nz_ = cube.shape
+        xs = torch.arange(max(x_min, 0), min(x_max, nxc_), dtype=torch.int64, device=cube.device)
+        ys = torch.arange(max(y_min, 0), min(y_max, nyc_), dtype=torch.int64, device=cube.device)
+        rows = (xs[:, None] * nyc_ + ys[None, :]).reshape(-1)
+        n_spec = int(rows.numel())
+        integrated = engine.segment_sum(cube.view(nxc_ * nyc_, nz_), rows, nansum=True)[0]
         if bkg is not None:
             scale = float(binning) ** 2 if binning else 1.0
             integrated = integrated - torch.from_numpy(np.asarray(bkg, dtype=np.float64)).to(integrated.device) * (scale * n_spec)
@@ -744,9 +768,10 @@ class Luci():
 
     def extract_spectrum_region(self, region, mean=False):
         """``LuciBase.py:895-947``: spectrum summed (or averaged) over a boolean mask / ``.npy`` mask."""
-        mask = torch.from_numpy(np.asarray(self._load_mask(region, False)).astype(bool)).to(self.cube_final.device)
-        spec_ct = int(mask.sum().item())
-        integrated = self.cube_final[mask].sum(dim=0, dtype=torch.float64)
+        rows = self._mask_rows(self._load_mask(region, False))
+        spec_ct = int(rows.numel())
+        nx_, ny_, nz_ = self.cube_final.shape
+        integrated = engine.segment_sum(self.cube_final.view(nx_ * ny_, nz_), rows)[0]
         if mean:
             integrated = integrated / spec_ct
         return np.asarray(self.spectrum_axis), integrated.cpu().numpy()
@@ -788,8 +813,8 @@ class Luci():
             offs = (ii * ny + jj).reshape(-1)
             scale = 1.0
         base = torch.tensor([xc * ny + yc for xc, yc in centres], dtype=torch.int64, device=dev)
-        spectra = flat[(base[:, None] + offs[None, :]).reshape(-1)].view(len(centres), offs.numel(), nz)
-        spectra = (spectra.sum(dim=1, dtype=torch.float64) * scale)
+        seg = torch.arange(len(centres), dtype=torch.int32, device=dev).repeat_interleave(offs.numel())
+        spectra = engine.segment_sum(flat, (base[:, None] + offs[None, :]).reshape(-1), seg, len(centres)) * scale
         theta = np.array([self.interferometer_theta[xc, yc] for xc, yc in centres], dtype=np.float32)
         L = len(waves_nm)
         cfg = FitConfig('sinc', list(sky_lines), list(range(1, L + 1)), [1] * L, self.spectrum_axis,
@@ -803,8 +828,10 @@ class Luci():
         spectra32 = spectra.to(torch.float32).contiguous()
         theta_t = torch.from_numpy(theta).to(dev)
         v_start, _ = engine.estimate_prior(cfg, spectra32, theta_t, v_range=(SKYLINE_V0 - 200.0, SKYLINE_V0 + 200.0))
-        v0 = v_start.repeat_interleave(L).contiguous() if L > 1 else v_start
-        b0 = torch.zeros((n * L,), dtype=torch.float32, device=dev)
+        # per-group priors when L > 1: one velocity per line (each line is its own velocity group), one broadening per
+        # sigma group (a single one: sigma_rel = [1] * L)
+        v0 = v_start.repeat_interleave(cfg.n_vel_groups).contiguous() if L > 1 else v_start
+        b0 = torch.zeros((n * (cfg.n_sigma_groups if L > 1 else 1),), dtype=torch.float32, device=dev)
         res = engine.fit_batch(cfg, spectra32, theta_t, v0, b0, want_sol=True)
         q = engine.unpack_rows(res['rows'].cpu().numpy(), L)
         vel_grid = q['velocities'][:, 0].astype(np.float64).reshape(n_grid, n_grid)
@@ -829,15 +856,19 @@ class Luci():
         are one segmented reduction of the cube followed by ONE ``lucifit_fit_batch`` call.  ``bin_map`` (int
         ``(nx, ny)``, -1 = unbinned pixel) may be passed directly instead of the ``.npy`` files; the tessellation
         itself (``create_wvt``, LuciWVT.py) is out of scope.  ``prior_values=(vel_map, broad_map)`` ``(ny, nx)`` are
-        reduced to one prior per bin by the median over its pixels.  Every bin is fitted with the interferometer angle
+        reduced to one prior per bin by the median over its pixels; ``initial_values=[vel_map, broad_map]`` (indexed
+        ``[x, y]`` like the reference does) freezes every bin at the values of its last pixel; ``n_stoch`` restarts are
+        further batch calls over all bins.  Every bin is fitted with the interferometer angle
         the reference's ``fit_spectrum_region`` uses (LuciBase.py:1035: the last pixel of the cube).
 
         Two defects of the reference loop are not reproduced: its maps are ``(ny, nx)`` but indexed ``[x, y]``
         (IndexError off the square part of the detector, LuciBase.py:1449-1459) and the continuum map is overwritten
         with the continuum error (:1456-1457)."""
-        self._reject_unsupported(bayes_bool, None, [False], 1, None)
-        if int(n_stoch) != 1 or (len(initial_values) >= 1 and initial_values[0] is not False):
-            raise NotImplementedError('fit_wvt: n_stoch > 1 / initial_values are implemented for fit_cube / fit_region only')
+        self._reject_unsupported(bayes_bool, None, [False], n_stoch, None)
+        freeze = len(initial_values) >= 2 and initial_values[0] is not False
+        if freeze and uncertainty_bool:
+            raise NotImplementedError('uncertainty_bool with initial_values is broken in the reference '
+                                      '(LuciFit.py:713-722 on an L+1 vector) and not offered')
         nx, ny, nz = self.cube_final.shape
         dev = self.cube_final.device
         if bin_map is None:
@@ -853,27 +884,38 @@ class Luci():
             raise ValueError('bin_map holds no bins')
         flat = torch.from_numpy(bin_map.reshape(-1)).to(dev)
         inside = flat >= 0
-        # segmented reduction: integrated spectrum of every bin (nansum like extract_spectrum_region, float64 sums)
-        sums = torch.zeros((n_bins, nz), dtype=torch.float64, device=dev)
-        rows = self.cube_final.view(nx * ny, nz)
-        for lo in range(0, nx * ny, 1 << 18):                      # bounded temporaries
-            hi = min(lo + (1 << 18), nx * ny)
-            sel = inside[lo:hi]
-            if bool(sel.any()):
-                sums.index_add_(0, flat[lo:hi][sel], torch.nan_to_num(rows[lo:hi][sel].to(torch.float64), nan=0.0))
+        # segmented reduction: integrated spectrum of every bin in one pass (lucifit_segment_sum, float64 sums); the pixel
+        # list is ordered by bin so that a CTA's running sums are flushed once per bin
+        order = torch.sort(flat, stable=True)[1]
+        order = order[int((~inside).sum().item()):]                 # (unbinned pixels carry -1 and sort first)
+        sums = engine.segment_sum(self.cube_final.view(nx * ny, nz), order.contiguous(), flat[order].to(torch.int32).contiguous(),
+                                  n_bins, nansum=True)
         counts = torch.bincount(flat[inside], minlength=n_bins).to(torch.float64)
         if mean:
             sums = sums / counts.clamp(min=1.0)[:, None]
         if bkg is not None:
             sums = sums - torch.from_numpy(np.asarray(bkg, dtype=np.float64)).to(dev)[None, :] * counts[:, None]
         theta = float(self.interferometer_theta[nx - 1, ny - 1])
-        have_prior = prior_values is not None
+        have_prior = prior_values is not None or freeze
         auto_prior = (not have_prior) and bool(self.ML_bool)
         cfg = self._make_config(lines, fit_function, vel_rel, sigma_rel, uncertainty_bool, nii_cons, None, None, 0.0,
-                                ml_scale=have_prior or auto_prior)
+                                ml_scale=have_prior or auto_prior, freeze=freeze)
         th = torch.full((n_bins,), theta, dtype=torch.float32, device=dev)
         v0 = b0 = None
-        if have_prior:
+        if freeze:
+            # initial_values = [velocity map, broadening map] indexed [x, y]: every bin is held at the values of its LAST
+            # pixel in np.where order (the reference's inner loop leaves them there, LuciBase.py:1437-1442)
+            vi, bi = np.asarray(initial_values[0], dtype=np.float32), np.asarray(initial_values[1], dtype=np.float32)
+            fm = bin_map.reshape(-1)
+            last_pix = np.full(n_bins, -1, dtype=np.int64)
+            last_pix[fm[fm >= 0]] = np.flatnonzero(fm >= 0)              # later pixels overwrite earlier ones
+            has = last_pix >= 0
+            vb = np.zeros((2, n_bins), np.float32)
+            vb[0, has] = vi.reshape(-1)[last_pix[has]]
+            vb[1, has] = bi.reshape(-1)[last_pix[has]]
+            v0, b0 = torch.from_numpy(vb[0].copy()).to(dev), torch.from_numpy(vb[1].copy()).to(dev)
+            n_stoch = 1
+        elif have_prior:
             pv = np.asarray(prior_values[0], dtype=np.float64).T.reshape(-1)     # (ny, nx) -> x-major like bin_map
             pb = np.asarray(prior_values[1], dtype=np.float64).T.reshape(-1)
             order = np.argsort(bin_map.reshape(-1), kind='stable')
@@ -886,6 +928,8 @@ class Luci():
         if auto_prior:
             v0, b0 = engine.estimate_prior(cfg, sums32, th)
         res = engine.fit_batch(cfg, sums32, th, v0, b0)
+        if v0 is not None and int(n_stoch) > 1:
+            res = self._restarts(cfg, sums32, th, v0, b0, res, n_stoch, n_bins, 0, n_bins)
         self.last_fit_summary = engine.status_summary(res['status'])
         L, K = len(lines), cfg.row_floats
         # paint: pixel (x, y) of bin b gets row b; unbinned pixels stay 0

@@ -385,3 +385,148 @@ def test_low_resolution_cube_with_a_three_sample_continuum_window(tmp_path):
     luci.create_deep_image()
     masks = luci.create_snr_map(0, 6, 0, 5, method=1)
     assert len(masks) == 4 and np.isfinite(luci.snr_map).all()
+
+
+def _oracle_fit(sky, sc, theta, prior, **kw):
+    """The oracle (restatement of LuciFit.Fit, pinned on the reference's goldens) on one float64 spectrum."""
+    import warnings
+    from oracle import luci_oracle as O
+    with warnings.catch_warnings():
+        warnings.simplefilter('ignore')
+        return O.OracleFit(np.asarray(sky, dtype=np.float64), sc.axis32, 'sincgauss', SN3, [1] * 5, [1] * 5, theta=theta,
+                           delta_x=sc.delta_x, n_steps=sc.n_steps, zpd_index=0, filter='SN3', nii_cons=True,
+                           prior=prior, **kw).fit()
+
+
+def _assert_fit_matches_oracle(d, o):
+    """north_star bar: velocity 0.5 km/s, broadening / flux 1e-3, chi2 not worse by more than 1e-4."""
+    np.testing.assert_allclose(d['velocities'], o['velocities'], atol=0.5)
+    np.testing.assert_allclose(d['sigmas'], o['sigmas'], rtol=1e-3)
+    np.testing.assert_allclose(d['fluxes'], o['fluxes'], rtol=1e-3)
+    assert d['chi2'] <= o['chi2'] * (1 + 1e-4)
+
+
+def test_fit_spectrum_region_matches_oracle(world):
+    """fit_spectrum_region (LuciBase.py:949-1046) against the oracle on the same integrated spectrum: plain fit,
+    uncertainties, freeze (initial_values) and n_stoch restarts."""
+    luci, sc, out = world
+    mask = np.zeros((12, 10), bool)
+    mask[3:8, 2:7] = True
+    mask[5, 4] = False
+    host = luci.cube_final.cpu().numpy().astype(np.float64)
+    sky_ref = host[mask].sum(axis=0)
+    theta = float(luci.interferometer_theta[-1, -1])                       # LuciBase.py:1035: the last pixel of the loops
+    prior = (float(sc.vel_fit_truth[3:8, 2:7].mean()) + 6.0, 42.0)
+    axis, sky, d = luci.fit_spectrum_region(SN3, 'sincgauss', [1] * 5, [1] * 5, mask, prior_values=prior, uncertainty_bool=True)
+    np.testing.assert_allclose(sky, sky_ref, rtol=1e-12)
+    o = _oracle_fit(sky_ref, sc, theta, prior, uncertainty_bool=True)
+    _assert_fit_matches_oracle(d, o)
+    np.testing.assert_allclose(d['vels_errors'], o['vels_errors'], rtol=5e-2)
+    np.testing.assert_allclose(d['flux_errors'], o['flux_errors'], rtol=5e-2)
+    # mean=True and a background (:1024-1027)
+    bkg = np.full(host.shape[2], 0.01e-17)
+    _, sky_m, d_m = luci.fit_spectrum_region(SN3, 'sincgauss', [1] * 5, [1] * 5, mask, prior_values=prior, mean=True, bkg=bkg)
+    n = int(mask.sum())
+    np.testing.assert_allclose(sky_m, sky_ref / n - bkg * n, rtol=1e-9)
+    # freeze: velocity and broadening held at initial_values, amplitudes + continuum fitted (LuciFit.py:688-709)
+    iv = [prior[0], prior[1]]
+    _, _, d_f = luci.fit_spectrum_region(SN3, 'sincgauss', [1] * 5, [1] * 5, mask, initial_values=iv)
+    o_f = _oracle_fit(sky_ref, sc, theta, None, initial_values=iv)
+    np.testing.assert_allclose(d_f['velocities'], o_f['velocities'], atol=1e-2)
+    np.testing.assert_allclose(d_f['sigmas'], o_f['sigmas'], rtol=1e-4)
+    np.testing.assert_allclose(d_f['fluxes'], o_f['fluxes'], rtol=2e-3)
+    # restarts (LuciFit.py:662-687): never worse than the single start, same optimum here
+    np.random.seed(5)
+    _, _, d_s = luci.fit_spectrum_region(SN3, 'sincgauss', [1] * 5, [1] * 5, mask, prior_values=prior, n_stoch=3)
+    assert d_s['chi2'] <= d['chi2'] * (1 + 1e-6)
+    _assert_fit_matches_oracle(d_s, o)
+
+
+def test_fit_wvt_bins_match_oracle_with_restarts_and_freeze(world):
+    """fit_wvt: bins against the oracle on the summed spectrum of the bin (what the reference's per-bin
+    fit_spectrum_region call fits, LuciBase.py:1434-1447); n_stoch restarts; freeze from initial-value maps."""
+    luci, sc, out = world
+    nx, ny = luci.cube_final.shape[:2]
+    bin_map = np.full((nx, ny), -1, dtype=np.int64)
+    bin_map[0:4, 0:5] = 0
+    bin_map[4:9, 2:8] = 1
+    bin_map[9:12, 5:10] = 2
+    bin_map[6, 5] = -1
+    host = luci.cube_final.cpu().numpy().astype(np.float64)
+    theta = float(luci.interferometer_theta[-1, -1])
+    v0, b0 = sc.priors()
+    np.random.seed(3)
+    vel, broad, flux, chi2, hdr = luci.fit_wvt(SN3, 'sincgauss', [1] * 5, [1] * 5, bin_map=bin_map, prior_values=(v0, b0), n_stoch=2)
+    rows = luci.last_fit_maps['bin_rows']
+    for k in range(3):
+        m = bin_map == k
+        prior = (float(np.median(v0.T[m])), float(np.median(b0.T[m])))
+        o = _oracle_fit(host[m].sum(axis=0), sc, theta, prior)
+        x, y = np.argwhere(m)[0]
+        d = {'velocities': vel[y, x], 'sigmas': broad[y, x], 'fluxes': flux[y, x], 'chi2': chi2[y, x]}
+        _assert_fit_matches_oracle(d, o)
+    assert rows.shape == (3, 40)
+    # freeze: [x, y]-indexed maps, each bin held at the values of its last pixel (LuciBase.py:1437-1442)
+    vi = np.asarray(v0.T, dtype=np.float32).copy()
+    bi = np.asarray(b0.T, dtype=np.float32).copy()
+    velf, broadf, fluxf, _, _ = luci.fit_wvt(SN3, 'sincgauss', [1] * 5, [1] * 5, bin_map=bin_map, initial_values=[vi, bi])
+    for k in range(3):
+        m = bin_map == k
+        xl, yl = np.argwhere(m)[-1]
+        x, y = np.argwhere(m)[0]
+        np.testing.assert_allclose(velf[y, x], vi[xl, yl], atol=1e-2)
+        np.testing.assert_allclose(broadf[y, x], bi[xl, yl], rtol=1e-4)
+        o_f = _oracle_fit(host[m].sum(axis=0), sc, theta, None, initial_values=[float(vi[xl, yl]), float(bi[xl, yl])])
+        np.testing.assert_allclose(fluxf[y, x], o_f['fluxes'], rtol=2e-3)
+
+
+def test_fit_pixel_with_nan_channels_matches_oracle(tmp_path):
+    """NaN channels are dropped like the reference's good_sky_inds (LuciBase.py:801-803) instead of being refused."""
+    from luci_b200.luci import Luci
+    from luci_b200.sim import SyntheticCube
+    dev = torch.device('cuda', 0)
+    sc = SyntheticCube(3, 3, model='sincgauss', resolution=5000, seed=8, snr_range=(40.0, 100.0))
+    cube = sc.synthesize(dev)
+    lo, hi = 14750, 15400
+    inside = np.flatnonzero((sc.axis32 > lo + 60) & (sc.axis32 < hi - 60))
+    cube[1, 1, int(inside[7])] = float('nan')
+    cube[1, 1, int(inside[40])] = float('nan')
+    cube[1, 1, 5] = float('nan')
+    luci = Luci.from_arrays(cube, sc.hdr_dict, str(tmp_path), 'NAN', spectrum_axis=sc.axis32, device=dev)
+    v0, b0 = sc.priors()
+    axis, sky, d = luci.fit_pixel(SN3, 'sincgauss', [1] * 5, [1] * 5, 1, 1, prior_values=(v0[1, 1], b0[1, 1]))
+    assert np.isnan(sky).sum() == 3
+    good = ~np.isnan(sky)
+    import warnings
+    from oracle import luci_oracle as O
+    with warnings.catch_warnings():
+        warnings.simplefilter('ignore')
+        o = O.OracleFit(sky[good], sc.axis32[good], 'sincgauss', SN3, [1] * 5, [1] * 5, theta=sc.theta, delta_x=sc.delta_x,
+                        n_steps=sc.n_steps, zpd_index=0, filter='SN3', nii_cons=True,
+                        prior=(float(v0[1, 1]), float(b0[1, 1]))).fit()
+    _assert_fit_matches_oracle(d, o)
+
+
+def test_segment_sum_against_numpy():
+    """lucifit_segment_sum: ordered and unordered segment lists, skipped rows, nansum on / off, long spectra."""
+    from luci_b200 import engine
+    dev = torch.device('cuda', 0)
+    rng = np.random.default_rng(2)
+    for n_rows, nz, n_seg in ((500, 841, 7), (64, 1300, 1), (3000, 97, 40)):
+        cube = rng.normal(size=(n_rows, nz)).astype(np.float32)
+        cube[rng.integers(0, n_rows, 20), rng.integers(0, nz, 20)] = np.nan
+        rows = rng.permutation(n_rows)[: n_rows * 3 // 4].astype(np.int64)
+        seg = rng.integers(-1, n_seg, rows.size).astype(np.int32)
+        order = np.argsort(seg, kind='stable')
+        t = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(dev)
+        for r, s in ((rows, seg), (rows[order], seg[order])):
+            for nansum in (True, False):
+                got = engine.segment_sum(t(cube), t(r), t(s), n_seg, nansum=nansum).cpu().numpy()
+                want = np.zeros((n_seg, nz))
+                c64 = cube.astype(np.float64)
+                if nansum:
+                    c64 = np.nan_to_num(c64, nan=0.0)
+                np.add.at(want, s[s >= 0], c64[r[s >= 0]])
+                np.testing.assert_allclose(got, want, rtol=1e-11, atol=1e-12, equal_nan=True)
+        whole = engine.segment_sum(t(cube), nansum=True).cpu().numpy()
+        np.testing.assert_allclose(whole[0], np.nansum(cube.astype(np.float64), axis=0), rtol=1e-11, atol=1e-12)

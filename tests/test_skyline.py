@@ -110,3 +110,10 @@ def test_gpu_skyline_calibration_grid(tmp_path):
     _, _, sky2, vel_grid2, _, _ = luci.skyline_calibration(str(tmp_path / 'L'), n_grid, bin_size=bin_size)
     np.testing.assert_allclose(sky2, host[xc:xc + bin_size, yc:yc + bin_size].sum(axis=(0, 1)), rtol=1e-6)
     assert np.abs(vel_grid2 - vel_grid).max() < 2.0
+    # two sky lines in the file (the second one has no signal in this cube): per-group priors, one broadening group --
+    # the first line's grid is unchanged
+    with open(tmp_path / 'L' / 'Data' / 'sky_lines.dat', 'w') as fh:
+        fh.write('#### SKYLINE DATA\nWavelength,Sigma,Strength\n6498.729, 1, 1\n6553.617, 1, 1\n')
+    luci.strict_reference = True
+    _, _, _, vel_grid3, vel_unc3, _ = luci.skyline_calibration(str(tmp_path / 'L'), n_grid, bin_size=bin_size)
+    assert np.abs(vel_grid3 - vel_grid).max() < 0.5 and (vel_unc3 > 0).all()

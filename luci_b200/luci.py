@@ -28,7 +28,7 @@ from . import dist as ldist
 from . import engine
 from ._capi import FitConfig, argmin_abs
 from .constants import LINE_DICT, snr_windows
-from .fitsio import read_fits, save_fits, write_fits
+from .fitsio import read_fits, save_fits, wcs_to_header, write_fits
 
 
 SKYLINE_V0 = 80.0          # km/s: the reference's initial guess for the sky-line velocity (LuciFit.py:859)
@@ -188,7 +188,7 @@ class Luci():
                     header_to_use[key] = header_to_use[key] * f
         if output_name is None:
             output_name = self.output_dir + '/' + self.object_name + '_deep.fits'
-        write_fits(output_name, self.deep_image, header_to_use)
+        write_fits(output_name, self.deep_image, wcs_to_header(header_to_use))
 
     def bin_cube(self, cube_final, header, binning, x_min, x_max, y_min, y_max):
         """``LuciBase.py:840-842`` / ``LuciUtility.py:319-355``: b x b nansum (no division)."""
@@ -225,7 +225,7 @@ class Luci():
         snr = engine.snr_map(region2d, method, flo, fhi, nlo, nhi)
         SNR = snr.view(nxr, nyr).t().contiguous().cpu().numpy()
         os.makedirs(self.output_dir + '/SNR', exist_ok=True)
-        write_fits(self.output_dir + '/SNR/' + self.object_name + '_SNR.fits', SNR, self.header)
+        write_fits(self.output_dir + '/SNR/' + self.object_name + '_SNR.fits', SNR, wcs_to_header(self.header))
         masks = []
         for snr_val in [1, 3, 5, 10]:
             mask = ma.masked_where(SNR >= snr_val, SNR)
@@ -250,14 +250,19 @@ class Luci():
         if int(n_stoch) < 1:
             raise ValueError('n_stoch must be >= 1')
 
-    def _cutout_header(self, header, x_min, y_min):
-        """What ``Cutout2D(...).wcs.to_header()`` changes for a rectangular cut-out: the reference pixel."""
-        h = dict(header) if header else {}
-        if 'CRPIX1' in h:
-            h['CRPIX1'] = h['CRPIX1'] - x_min
-        if 'CRPIX2' in h:
-            h['CRPIX2'] = h['CRPIX2'] - y_min
-        return h
+    def _cutout_header(self, header, x_min, y_min, x_max=None, y_max=None, full_shape=None):
+        """The header ``Cutout2D(deep, position, size, wcs=WCS(header)).wcs.to_header()`` gives the reference's maps
+        (``LuciBase.py:511-513``): WCSLIB's canonical card set (``fitsio.wcs_to_header``) with the reference pixel moved
+        to the cut-out.  ``strict_reference`` reproduces ``Cutout2D``'s reading of ``size`` as ``(ny, nx)``, which
+        displaces the origin of a non-square region (``fitsio.cutout_origin``); otherwise the fitted rectangle's own
+        origin is used."""
+        from .fitsio import cutout_origin
+        if x_max is None or y_max is None:
+            origin = (float(x_min), float(y_min))
+        else:
+            nx_f, ny_f = full_shape if full_shape is not None else self.cube_final.shape[:2]
+            origin = cutout_origin(x_min, x_max, y_min, y_max, nx_f, ny_f, strict_reference=self.strict_reference)
+        return wcs_to_header(header, origin)
 
     def _fit_maps(self, cube3d, lines, fit_function, vel_rel, sigma_rel, x_min, x_max, y_min, y_max, mask, bkg,
                   bkg_scale, uncertainty_bool, nii_cons, spec_min, spec_max, obj_redshift, prior_values, n_stoch=1,
@@ -556,7 +561,8 @@ class Luci():
         if self._is_writer():
             save_fits(self.output_dir, self.object_name, lines, m['amplitudes'], m['fluxes'], m['flux_errors'],
                       m['velocities'], m['sigmas'], m['vels_errors'], m['sigmas_errors'], m['chi2'], m['continuum'],
-                      m['continuum_error'], self._cutout_header(header, x_min, y_min), binning, fit_function=fit_function)
+                      m['continuum_error'], self._cutout_header(header, x_min, y_min, x_max, y_max), binning,
+                      fit_function=fit_function)
         self.last_fit_maps = m
         return m['velocities'], m['sigmas'], m['fluxes'], m['amplitudes']
 
@@ -612,7 +618,7 @@ class Luci():
         if self._is_writer():
             save_fits(self.output_dir, self.object_name, lines, m['amplitudes'], m['fluxes'], m['flux_errors'],
                       m['velocities'], m['sigmas'], m['vels_errors'], m['sigmas_errors'], m['chi2'], m['continuum'],
-                      m['continuum_error'], self._cutout_header(header, x_min, y_min), binning)
+                      m['continuum_error'], self._cutout_header(header, x_min, y_min, x_max, y_max), binning)
         self.last_fit_maps = m
         return m['velocities'], m['sigmas'], m['fluxes'], m['chi2'], mask
 
@@ -838,7 +844,7 @@ class Luci():
         # the sky-line branch inverts the Hessian itself (LuciFit.py:873-876), the regular fit half of it (:718): its
         # 1-sigma errors are smaller by sqrt(2)
         vel_uncertainty_grid = (q['vels_errors'][:, 0].astype(np.float64) / np.sqrt(2.0)).reshape(n_grid, n_grid)
-        write_fits(self.output_dir + '/velocity_correction.fits', vel_grid, self.header)
+        write_fits(self.output_dir + '/velocity_correction.fits', vel_grid, wcs_to_header(self.header))
         from .host_ops import plot_vector
         fit_vector = plot_vector(cfg, res['fit_sol'][-1].cpu().numpy().astype(np.float64), float(theta[-1]), dev)
         self.last_fit_summary = engine.status_summary(res['status'])

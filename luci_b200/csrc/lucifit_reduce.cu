@@ -364,6 +364,216 @@ lf_snr2_kernel(const float* __restrict__ cube, long long n_spaxel, int nz, int n
     }
 }
 
+// ---- SNR method 2, register form (spectra of up to 32 NR samples) ----------------------------------------------
+// The clip of LuciBase.py:1146-1152 needs, ten times over, the median / mean / std of the samples inside a shrinking value
+// interval and finally their minimum.  The spectrum is sorted ONCE, in registers: element e of the padded spectrum lives in
+// lane e / NR, register e % NR, so the 40 compare-exchange stages of the bitonic network whose partner distance is below NR
+// are plain FMNMX pairs on the lane's own registers and only the 15 stages that cross lanes use shuffles (2.2 k warp
+// instructions for 1024 keys; the shared-memory sort of lf_snr2_kernel spends ~9 k plus a barrier per stage).  The sorted
+// keys then go to shared memory once (row stride NR + 1: conflict-free), and every clip iteration works on ranks: the
+// survivors are a contiguous rank range [a, a + m), their float64 moments come from per-lane prefix sums plus the two
+// partial lanes at the ends of the range, the new range from two ballot searches (lane heads, then one lane's row).
+template <int NR>
+__device__ __forceinline__ void lf_regsort(float (&v)[NR], int lane)
+{
+    // flip-merge form of the bitonic sorter (all comparators ascending): block size k: compare e with its mirror
+    // e ^ (k - 1), then half-cleaners at distances k/4 ... 1
+#pragma unroll
+    for (int k = 2; k <= NR; k <<= 1) {
+#pragma unroll
+        for (int r = 0; r < NR; ++r) {
+            const int p = r ^ (k - 1);
+            if (r < p) { const float lo = fminf(v[r], v[p]), hi = fmaxf(v[r], v[p]); v[r] = lo; v[p] = hi; }
+        }
+#pragma unroll
+        for (int j = k >> 2; j > 0; j >>= 1)
+#pragma unroll
+            for (int r = 0; r < NR; ++r)
+                if ((r & j) == 0) { const float lo = fminf(v[r], v[r | j]), hi = fmaxf(v[r], v[r | j]); v[r] = lo; v[r | j] = hi; }
+    }
+#pragma unroll 1
+    for (int m = 2; m <= 32; m <<= 1) {                      // blocks of m lanes (k = m NR keys)
+        {
+            const bool lower = (lane & (m >> 1)) == 0;
+            float t[NR];
+#pragma unroll
+            for (int r = 0; r < NR; ++r) t[r] = __shfl_xor_sync(0xffffffffu, v[NR - 1 - r], m - 1);
+#pragma unroll
+            for (int r = 0; r < NR; ++r) v[r] = lower ? fminf(v[r], t[r]) : fmaxf(v[r], t[r]);
+        }
+#pragma unroll 1
+        for (int jl = m >> 2; jl > 0; jl >>= 1) {
+            const bool lower = (lane & jl) == 0;
+#pragma unroll
+            for (int r = 0; r < NR; ++r) {
+                const float p = __shfl_xor_sync(0xffffffffu, v[r], jl);
+                v[r] = lower ? fminf(v[r], p) : fmaxf(v[r], p);
+            }
+        }
+#pragma unroll
+        for (int j = NR >> 1; j > 0; j >>= 1)
+#pragma unroll
+            for (int r = 0; r < NR; ++r)
+                if ((r & j) == 0) { const float lo = fminf(v[r], v[r | j]), hi = fmaxf(v[r], v[r | j]); v[r] = lo; v[r | j] = hi; }
+    }
+}
+
+__device__ __forceinline__ double lf_warp_sum_d(double x)
+{
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) x += __shfl_xor_sync(0xffffffffu, x, o);
+    return x;
+}
+
+template <int NR> struct LfSnr2Smem { enum { PER_WARP = 2 * 34 * 8 + 4 * 32 * (NR + 1) + 4 * 32 * NR }; };
+
+template <int NR>
+__global__ void __launch_bounds__(RED_WARPS * 32)
+lf_snr2_reg_kernel(const float* __restrict__ cube, long long n_spaxel, int nz, long long n_live, int flo, int fhi,
+                   int nlo, int nhi, float* __restrict__ snr, float* __restrict__ deep)
+{
+    constexpr int ROW = NR + 1;
+    extern __shared__ __align__(16) unsigned char smem_snr2[];      // per warp: pre[2][34] doubles | sv[32 ROW] | nxt[32 NR]
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    unsigned char* mine = smem_snr2 + (size_t)warp * LfSnr2Smem<NR>::PER_WARP;
+    double* pre1 = reinterpret_cast<double*>(mine);
+    double* pre2 = pre1 + 34;
+    float* sv = reinterpret_cast<float*>(pre2 + 34);
+    float* nxt = sv + 32 * ROW;
+    const long long stride = (long long)gridDim.x * RED_WARPS;
+    // The sort and the clip of one spectrum keep a warp busy for ~10 k cycles without touching memory: the NEXT spectrum of
+    // the warp is fetched meanwhile with cp.async into a per-warp staging row, so its DRAM latency is never waited for.
+    auto prefetch = [&](long long sp) {
+        if (sp < n_spaxel) {
+            const float* row = cube + sp * (long long)nz;
+#pragma unroll
+            for (int i = 0; i < NR; ++i) {
+                const int z = lane + 32 * i;
+                if (z < nz) {
+                    const unsigned dst = (unsigned)__cvta_generic_to_shared(nxt + z);
+                    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" :: "r"(dst), "l"(row + z) : "memory");
+                }
+            }
+        }
+        asm volatile("cp.async.commit_group;" ::: "memory");
+    };
+    prefetch((long long)blockIdx.x * RED_WARPS + warp);
+    for (long long s = (long long)blockIdx.x * RED_WARPS + warp; s < n_spaxel; s += stride) {
+        float v[NR];
+        float sum = 0.f, fsum = 0.f; double n1 = 0.0, n2 = 0.0; int ncnt = 0, m = 0;
+        float allmin = INFINITY;
+        asm volatile("cp.async.wait_group 0;" ::: "memory");
+        __syncwarp();
+#pragma unroll
+        for (int i = 0; i < NR; ++i) {                       // sample z = lane + 32 i (any order sorts)
+            const int z = lane + 32 * i;
+            v[i] = z < nz ? nxt[z] : NAN;
+        }
+        __syncwarp();
+        prefetch(s + stride);
+#pragma unroll
+        for (int i = 0; i < NR; ++i) {
+            const int z = lane + 32 * i;
+            const float x = v[i];
+            const bool nn = x == x;
+            const bool fin = nn && fabsf(x) != INFINITY;
+            m += fin;
+            sum += nn ? x : 0.0f;
+            allmin = fminf(allmin, x);                       // (fminf drops a NaN)
+            fsum += (nn && z >= flo && z < fhi) ? x : 0.0f;
+            if (nn && z >= nlo && z < nhi) { n1 += x; n2 += (double)x * x; ++ncnt; }
+            v[i] = fin ? x : INFINITY;                       // non-finite samples sort to the end
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            sum += __shfl_xor_sync(0xffffffffu, sum, o); fsum += __shfl_xor_sync(0xffffffffu, fsum, o);
+            allmin = fminf(allmin, __shfl_xor_sync(0xffffffffu, allmin, o));
+        }
+        n1 = lf_warp_sum_d(n1); n2 = lf_warp_sum_d(n2);
+        ncnt = __reduce_add_sync(0xffffffffu, ncnt); m = __reduce_add_sync(0xffffffffu, m);
+        lf_regsort<NR>(v, lane);
+        // sorted keys -> shared memory (rank e at sv[e + e / NR]); per-lane float64 moments about the first median
+        __syncwarp();
+#pragma unroll
+        for (int r = 0; r < NR; ++r) sv[lane * ROW + r] = v[r];
+        __syncwarp();
+        auto key = [&](int e) { return sv[e + e / NR]; };
+        const double c0 = m > 0 ? (double)key(m / 2) : 0.0;
+        {
+            double l1 = 0.0, l2 = 0.0;
+#pragma unroll
+            for (int r = 0; r < NR; ++r) {
+                const double d = (lane * NR + r < m) ? (double)v[r] - c0 : 0.0;
+                l1 += d; l2 += d * d;
+            }
+            double i1 = l1, i2 = l2;                         // inclusive scan over lanes
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const double t1 = __shfl_up_sync(0xffffffffu, i1, o), t2 = __shfl_up_sync(0xffffffffu, i2, o);
+                if (lane >= o) { i1 += t1; i2 += t2; }
+            }
+            pre1[lane + 1] = i1; pre2[lane + 1] = i2;       // pre[l] = moments of the lanes below l
+            if (lane == 0) { pre1[0] = 0.0; pre2[0] = 0.0; }
+        }
+        __syncwarp();
+        // moments of the ranks [0, e): whole lanes from the prefix, the partial lane read cooperatively
+        auto partial = [&](int e, double& p1, double& p2) {
+            const int l = e / NR, q = e - l * NR;
+            double d = 0.0;
+            if (lane < q) d = (double)sv[l * ROW + lane] - c0;     // (NR <= 32: one key per lane)
+            p1 = d; p2 = d * d;
+        };
+        int a = 0;
+        const float head = v[0];
+        for (int it = 0; it < 10 && m > 0; ++it) {
+            const double med = (m & 1) ? (double)key(a + m / 2) : 0.5 * ((double)key(a + m / 2 - 1) + (double)key(a + m / 2));
+            double a1, a2, b1, b2;
+            partial(a, a1, a2);
+            partial(a + m, b1, b2);
+            double s1 = lf_warp_sum_d(b1 - a1), s2 = lf_warp_sum_d(b2 - a2);
+            s1 += pre1[(a + m) / NR] - pre1[a / NR];
+            s2 += pre2[(a + m) / NR] - pre2[a / NR];
+            // np.nanstd about the mean (moments about c0: a shift changes nothing).  A key survives when
+            // |key - med| <= std, i.e. (key - med)^2 m^2 <= m s2 - s1^2: no square root, no division
+            const double dm = (double)m;
+            const double rhs = fmax(dm * s2 - s1 * s1, 0.0);
+            auto is_below = [&](float k) { const double d = ((double)k - med) * dm; return d < 0.0 && d * d > rhs; };
+            auto is_above = [&](float k) { const double d = ((double)k - med) * dm; return d > 0.0 && d * d > rhs; };
+            // first rank that is not below / first rank that is above (the keys are sorted: two ballot searches each)
+            int l0, h0;
+            {
+                const int nl = __popc(__ballot_sync(0xffffffffu, is_below(head)));     // lanes whose first key is below
+                if (nl == 0) l0 = 0;
+                else {
+                    const unsigned in = __ballot_sync(0xffffffffu, lane < NR && is_below(sv[(nl - 1) * ROW + (lane < NR ? lane : 0)]));
+                    l0 = (nl - 1) * NR + __popc(in);
+                }
+                const int nh = __popc(__ballot_sync(0xffffffffu, !is_above(head)));
+                if (nh == 0) h0 = 0;
+                else {
+                    const unsigned in = __ballot_sync(0xffffffffu, lane < NR && !is_above(sv[(nh - 1) * ROW + (lane < NR ? lane : 0)]));
+                    h0 = (nh - 1) * NR + __popc(in);
+                }
+            }
+            if (l0 < a) l0 = a;
+            if (h0 > a + m) h0 = a + m;
+            if (h0 < l0) h0 = l0;
+            const int removed = m - (h0 - l0);
+            a = l0; m = h0 - l0;
+            if (removed == 0) break;
+        }
+        const float cmin = m > 0 ? key(a) : allmin;                         // LuciBase.py:1151-1152
+        if (lane == 0) {
+            if (deep) deep[s] = s < n_live ? sum : 0.0f;
+            double mu = ncnt > 0 ? n1 / ncnt : 0.0;
+            double sd = ncnt > 0 ? sqrt(fmax(n2 / ncnt - mu * mu, 0.0)) : NAN;
+            double val = ((double)fsum - (double)cmin * (double)(fhi - flo)) / sd;   // :1153, 1167
+            snr[s] = val < 0.0 ? 0.0f : (float)val;
+        }
+        __syncwarp();
+    }
+}
+
 // b x b nansum binning (bin_cube_function, LUCI/LuciUtility.py:332-341): one warp per OUTPUT spaxel walks the
 // spectral axis (coalesced, no per-element index divisions), four output samples per lane in flight; the b*b input
 // rows of a bin are read exactly once.
@@ -504,6 +714,22 @@ extern "C" cudaError_t lf_run_reduce(int mode, const float* cube, long long n_sp
                                      cudaStream_t stream)
 {
     long long want = (n_spaxel + RED_WARPS - 1) / RED_WARPS;
+    if (mode == 2 && nz <= 1024 && !getenv("LUCIFIT_SNR2_SMEM_SORT")) {
+        // register sort: 16 keys per lane up to 512 samples, 32 up to 1024
+        int occ = 1;
+        const size_t smem = (size_t)RED_WARPS * (nz <= 512 ? (size_t)LfSnr2Smem<16>::PER_WARP : (size_t)LfSnr2Smem<32>::PER_WARP);
+        cudaError_t e = nz <= 512 ? cudaFuncSetAttribute(lf_snr2_reg_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)
+                                  : cudaFuncSetAttribute(lf_snr2_reg_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+        if (nz <= 512) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, lf_snr2_reg_kernel<16>, RED_WARPS * 32, smem);
+        else cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, lf_snr2_reg_kernel<32>, RED_WARPS * 32, smem);
+        if (occ < 1) return cudaErrorLaunchOutOfResources;
+        long long cap = (long long)sm_count * occ;
+        int grid = (int)(want < cap ? want : cap); if (grid < 1) grid = 1;
+        if (nz <= 512) lf_snr2_reg_kernel<16><<<grid, RED_WARPS * 32, smem, stream>>>(cube, n_spaxel, nz, n_live, flo, fhi, nlo, nhi, snr, deep);
+        else lf_snr2_reg_kernel<32><<<grid, RED_WARPS * 32, smem, stream>>>(cube, n_spaxel, nz, n_live, flo, fhi, nlo, nhi, snr, deep);
+        return cudaGetLastError();
+    }
     if (mode == 2) {
         int npad = 32;
         while (npad < nz) npad <<= 1;

@@ -54,8 +54,11 @@ def main():
     ap.add_argument('out')
     ap.add_argument('--spaxels', type=float, default=0.0)
     ap.add_argument('--note', default='')
+    ap.add_argument('--kernel', default='', help='regex: summarise only one launch of this kernel')
+    ap.add_argument('--skip', type=int, default=0, help='launches of --kernel to skip')
     a = ap.parse_args()
-    raw = list(csv.reader(io.StringIO(ncu(['-i', a.report, '--page', 'raw', '--csv']))))
+    filt = ['-k', 'regex:' + a.kernel, '-s', str(a.skip), '-c', '1'] if a.kernel else []
+    raw = list(csv.reader(io.StringIO(ncu(['-i', a.report, '--page', 'raw', '--csv'] + filt))))
     hdr, units = raw[0], raw[1]
     lines = []
     for r in raw[2:]:
@@ -64,7 +67,7 @@ def main():
             if any(re.search(k, h) for k in KEYS):
                 lines.append('  %-88s %-16s %s' % (h, units[i], r[i]))
         lines.append('')
-    src = ncu(['-i', a.report, '--page', 'source', '--csv', '--print-source', 'cuda,sass'])
+    src = ncu(['-i', a.report, '--page', 'source', '--csv', '--print-source', 'cuda,sass'] + filt)
     fmap = {}
     agg = collections.defaultdict(lambda: [0, 0])
     cur, h2, tot, kern = None, None, 0, None

@@ -179,6 +179,17 @@ template <> struct LfWarp<32> {
 };
 #endif
 
+// Which branch of w(z) the lanes of a chunk take for one sincgauss line (see lf_profile_sc).
+template <int LANES>
+LF_CORE int lf_region_hint(const LfWarp<LANES>& w, const LfLine& ln, float dx)
+{
+    const float b = dx * ln.is2s;
+    const float bb = b * b, r2 = bb + ln.a * ln.a;
+    if (w.all(bb >= 40.0f)) return LF_HINT_FAR;
+    if (ln.a >= LF_NEAR_A_MIN && w.any(r2 < LF_W_R2_CF) && w.all(r2 < LF_NEAR_R2_MAX)) return LF_HINT_NEAR;
+    return LF_HINT_LANE;
+}
+
 // ------------------------------------------------------------------------------------------- small helpers
 template <int P> struct LfSym {            // packed upper triangle, row-major
     static LF_HD constexpr int idx(int i, int j) { return i * P - (i * (i - 1)) / 2 + (j - i); }
@@ -555,6 +566,30 @@ LF_CORE void lf_wing_terms(float b, float a, float bb, float a2, float r2, float
     E2 = iv * A2;
 }
 
+// Complex w(z), z = -b + i a, from the same three-term asymptotic series (|z|^2 >= LF_W_R2_ASY), and its first two
+// Taylor coefficients from the exact identities w' = -2 z w + 2i/sqrt pi, w'' = -2 w - 2 z w' (the cancellation in them
+// costs ~1e-7 absolute, which a step |dz| <= 0.2 scales down further).  Used by the uncertainty stage: the variants of a
+// line that share a sigma differ, in the wing, by a real step dz = -dp / (sqrt2 sigma) of at most 0.5 % of |z|, so they
+// are w + dz (w' + dz w''/2) -- third-order error 2e-7 relative -- with each variant's own, exact, phase rotation.
+LF_CORE void lf_wing_w(float b, float a, float r2, float& wr, float& wi)
+{
+    const float inv = LF_RCP(r2);
+    const float ur = -b * inv, ui = -a * inv;                       // 1/z
+    const float sr = ur * ur - ui * ui, si = 2.0f * ur * ui;        // 1/z^2
+    const float tr = 0.5f + 0.75f * sr, ti = 0.75f * si;
+    const float pr = 1.0f + (sr * tr - si * ti), pi = sr * ti + si * tr;
+    const float qr = ur * pr - ui * pi, qi = ur * pi + ui * pr;
+    wr = -LF_ISQRTPI_F * qi; wi = LF_ISQRTPI_F * qr;
+}
+LF_CORE void lf_wing_w_taylor(float b, float a, float wr, float wi, float& d1r, float& d1i, float& d2r, float& d2i)
+{
+    const float x = -b, y = a;
+    d1r = -2.0f * (x * wr - y * wi);
+    d1i = LF_2ISQRTPI_F - 2.0f * (x * wi + y * wr);
+    d2r = -wr - (x * d1r - y * d1i);                                // w''/2
+    d2i = -wi - (x * d1i + y * d1r);
+}
+
 // One pass over the fit window: chi2 = sum r^2, and (into dst[NA], per-warp memory) H = J^T J packed upper
 // followed by g = J^T r, at the parameters the line records `sl` were built for.
 template <int MODEL, int L, int NV, int NS, int LANES>
@@ -589,7 +624,6 @@ LF_CORE void lf_eval(const LfCfg& cfg, const LfWarp<LANES>& w, const float* xo, 
         for (int k = 0; k < L; ++k) {
             const LfLineX& X = sl[k];
             const float dx = lf_dx(X.ln, x);
-            bool all_far = false;
             if (MODEL == LF_GAUSSIAN) {
                 float b = dx * X.ln.is2s;
                 if (w.all(b * b > 100.0f)) { gt[k * LANES + w.lane] = 0.0f; continue; }   // exp(-100) = 0 in FP32
@@ -617,8 +651,9 @@ LF_CORE void lf_eval(const LfCfg& cfg, const LfWarp<LANES>& w, const float* xo, 
             }
             if (!wing) {
                 float gp, gs;
-                if (MODEL == LF_SINCGAUSS) all_far = w.all(lf_is_far(X.ln, dx));
-                lf_profile_sc<MODEL>(X.ln, dx, s, c, iw, all_far, g, gp, gs);
+                int hint = LF_HINT_LANE;
+                if (MODEL == LF_SINCGAUSS) hint = lf_region_hint(w, X.ln, dx);
+                lf_profile_sc<MODEL>(X.ln, dx, s, c, iw, hint, g, gp, gs);
                 const float A = X.aeff;
                 m += A * g;
                 const float tp = A * gp, ts = A * gs;
@@ -1412,7 +1447,7 @@ LF_CORE void lf_stage_out(const LfCfg& cfg, const LfWarp<LANES>& w, const float*
         for (int k = 0; k < L; ++k) {
             const LfLineX& X = sl[k];
             const float dx = lf_dx(X.ln, x);
-            bool all_far = false;
+            int hint = LF_HINT_LANE;
             float s = 0.0f, c = 1.0f;
             if (MODEL != LF_GAUSSIAN) { s = Sx * X.ck - Cx * X.sk; c = Cx * X.ck + Sx * X.sk; }
             if (MODEL == LF_SINCGAUSS) {
@@ -1424,10 +1459,10 @@ LF_CORE void lf_stage_out(const LfCfg& cfg, const LfWarp<LANES>& w, const float*
                     m += X.c_m * T;
                     continue;
                 }
-                all_far = w.all(lf_is_far(X.ln, dx));
+                hint = lf_region_hint(w, X.ln, dx);
             }
             float g, gp, gs;
-            lf_profile_sc<MODEL>(X.ln, dx, s, c, iw, all_far, g, gp, gs);
+            lf_profile_sc<MODEL>(X.ln, dx, s, c, iw, hint, g, gp, gs);
             m += X.aeff * g;
         }
         if (live) {
@@ -1598,12 +1633,12 @@ LF_CORE void lf_stage_unc(const LfCfg& cfg, const LfWarp<LANES>& w, const float*
         for (int k = 0; k < L; ++k) {
             const LfLineV& X = lines[13 * k];
             const float dx = lf_dx(X.ln, x);
-            bool far = false;
-            if (MODEL == LF_SINCGAUSS) far = w.all(lf_is_far(X.ln, dx));
+            int hint = LF_HINT_LANE;
+            if (MODEL == LF_SINCGAUSS) hint = lf_region_hint(w, X.ln, dx);
             float s = 0.0f, c = 1.0f;
             if (MODEL != LF_GAUSSIAN) { s = Sx * X.ck - Cx * X.sk; c = Cx * X.ck + Sx * X.sk; }
             float g, gp, gs;
-            lf_profile_sc<MODEL>(X.ln, dx, s, c, iw, far, g, gp, gs);
+            lf_profile_sc<MODEL>(X.ln, dx, s, c, iw, hint, g, gp, gs);
             trow[3 * k] = live ? g : 0.0f;
             m += X.aeff * g;
         }
@@ -1628,16 +1663,42 @@ LF_CORE void lf_stage_unc(const LfCfg& cfg, const LfWarp<LANES>& w, const float*
                 wing_all = w.all(!live || (bmin * bmin >= 40.0f && bmin * bmin + amin * amin >= LF_W_R2_ASY));
             }
             if (wing_all) {
-#pragma unroll 4
-                for (int v = 1; v < 13; ++v) {
-                    const LfLineV& X = lines[13 * k + v];
-                    const float dx = lf_dx(X.ln, x);
-                    const float s = Sx * X.ck - Cx * X.sk, c = Cx * X.ck + Sx * X.sk;
-                    const float b = dx * X.ln.is2s;
-                    float T, T2, E2;
-                    lf_wing_terms(b, X.ln.a, b * b, X.a2, b * b + X.a2, s, c, T, T2, E2);
-                    gvt[v * LANES + w.lane] = X.neae * T;
-                }
+                // one full evaluation of w(z) per sigma value; the shifted-centre siblings of a sigma value are a
+                // second-order Taylor step in z with their own phase rotation (lf_wing_w)
+                const LfLineV* Lk = lines + 13 * k;
+                auto rotate = [&](const LfLineV& X, float& s, float& c) { s = Sx * X.ck - Cx * X.sk; c = Cx * X.ck + Sx * X.sk; };
+                auto group = [&](int vb, int v1, int v2, int v3, int v4) {      // base variant, siblings at -/+ d [, -/+ 2d]
+                    const LfLineV& B = Lk[vb];
+                    const float b = lf_dx(B.ln, x) * B.ln.is2s;
+                    float wr, wi, d1r, d1i, d2r, d2i;
+                    lf_wing_w(b, B.ln.a, b * b + B.a2, wr, wi);
+                    lf_wing_w_taylor(b, B.ln.a, wr, wi, d1r, d1i, d2r, d2i);
+                    float s, c;
+                    if (vb != 0) { rotate(B, s, c); gvt[vb * LANES + w.lane] = B.neae * (c * wr + s * wi); }
+                    const int sib[4] = {v1, v2, v3, v4};
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) {
+                        const int v = sib[q];
+                        if (v < 0) continue;
+                        const float dz = -lf_var_dp(v) * B.ln.is2s;          // dx_v = dx + dp_v: z_v = z - dp_v / (sqrt2 sigma)
+                        const float X_ = wr + dz * (d1r + dz * d2r), Y_ = wi + dz * (d1i + dz * d2i);
+                        rotate(Lk[v], s, c);
+                        gvt[v * LANES + w.lane] = B.neae * (c * X_ + s * Y_);
+                    }
+                };
+                auto single = [&](int v) {
+                    const LfLineV& X = Lk[v];
+                    const float b = lf_dx(X.ln, x) * X.ln.is2s;
+                    float wr, wi, s, c;
+                    lf_wing_w(b, X.ln.a, b * b + X.a2, wr, wi);
+                    rotate(X, s, c);
+                    gvt[v * LANES + w.lane] = X.neae * (c * wr + s * wi);
+                };
+                group(0, 1, 2, 5, 6);
+                group(3, 9, 11, -1, -1);
+                group(4, 10, 12, -1, -1);
+                single(7);
+                single(8);
             } else
 #pragma unroll 1
             for (int v = 1; v < 13; ++v) {
@@ -1661,10 +1722,10 @@ LF_CORE void lf_stage_unc(const LfCfg& cfg, const LfWarp<LANES>& w, const float*
                         }
                     }
                     if (!wing) {
-                        bool far = false;
-                        if (MODEL == LF_SINCGAUSS) far = w.all(lf_is_far(X.ln, dx));
+                        int hint = LF_HINT_LANE;
+                        if (MODEL == LF_SINCGAUSS) hint = lf_region_hint(w, X.ln, dx);
                         float gp, gs;
-                        lf_profile_sc<MODEL>(X.ln, dx, s, c, iw, far, gv, gp, gs);
+                        lf_profile_sc<MODEL>(X.ln, dx, s, c, iw, hint, gv, gp, gs);
                     }
                 }
                 gvt[v * LANES + w.lane] = gv;

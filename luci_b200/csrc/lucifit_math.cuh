@@ -195,10 +195,20 @@ LF_HD void lf_line_setup(int model, float pp, float dp, float sig, float sinc_w,
 // which is algebraically the reference's Dawson expression (LuciFunctions.py:229-232) without its e^{+a^2}.
 // `s`, `c` = sin, cos(pi dx / w): the caller supplies them (the fit kernels rotate a per-sample phase table by a
 // per-line constant instead of spending two MUFU ops per line and sample); unused by the gaussian.
+// `hint` (warp-uniform, from lf_region_hint in the fit kernels): LF_HINT_LANE every lane picks its own branch of w(z);
+// LF_HINT_FAR all lanes are beyond b^2 = 40 (far branch, exp(-b^2) = 0); LF_HINT_NEAR all lanes take the Weideman
+// branch -- a chunk that holds the core of a line would otherwise execute BOTH branches (the lanes of the core and the
+// lanes 7+ samples away diverge), and the N = 16 expansion is good to 3e-7 relative out to |z| = 30 (value and d/dp to
+// 1e-7 of the peak; d/dsigma to 1e-5 of its peak for a >= 1, which is why narrower lines keep the per-lane choice).
+enum { LF_HINT_LANE = 0, LF_HINT_FAR = 1, LF_HINT_NEAR = 2 };
+#define LF_NEAR_A_MIN 1.0f
+#define LF_NEAR_R2_MAX 6400.0f
+
 template <int MODEL>
-LF_HD void lf_profile_sc(const LfLine& ln, float dx, float s, float c, float iw /* 1/w */, bool all_far,
+LF_HD void lf_profile_sc(const LfLine& ln, float dx, float s, float c, float iw /* 1/w */, int hint,
                          float& g, float& g_p, float& g_s)
 {
+    const bool all_far = hint == LF_HINT_FAR;
     if (MODEL == LF_GAUSSIAN) {
         float b = dx * ln.is2s;
         float b2 = b * b;
@@ -224,7 +234,7 @@ LF_HD void lf_profile_sc(const LfLine& ln, float dx, float s, float c, float iw 
         float b = dx * ln.is2s;                       // 2ab = pi dx / w is the angle of (s, c)
         const float a = ln.a;
         float r2 = b * b + a * a;
-        bool far = all_far || r2 >= LF_W_R2_CF;
+        bool far = all_far || (hint != LF_HINT_NEAR && r2 >= LF_W_R2_CF);
         float eb = all_far ? 0.0f : LF_EXP(-b * b);
         float gb, gal;                                // dg/db at fixed a ; dg/da at fixed 2ab
         if (far) {
@@ -259,7 +269,7 @@ LF_HD void lf_profile(const LfLine& ln, float dx, float piw /* pi/w */, float iw
 {
     float s = 0.0f, c = 1.0f;
     if (MODEL != LF_GAUSSIAN) lf_sincospi(dx * iw, s, c);
-    lf_profile_sc<MODEL>(ln, dx, s, c, iw, all_far, g, g_p, g_s);
+    lf_profile_sc<MODEL>(ln, dx, s, c, iw, all_far ? LF_HINT_FAR : LF_HINT_LANE, g, g_p, g_s);
 }
 
 // "far" test used to pick the warp-uniform wing path of the sincgauss evaluation: continued-fraction region

@@ -174,6 +174,13 @@ int lucifit_sim_cube(const lucifit_config* cfg, int64_t n_spaxel, const float* a
                      float flux_scale, float* cube /*[n][nz]*/, void* workspace, size_t workspace_bytes,
                      void* stream);
 
+/* Output maps: rows[n_rows][row_floats] (the out_rows of lucifit_fit_batch, one row per spaxel in map order) ->
+ * maps[row_floats][n_rows], the field-major layout of the 2-D maps the reference scatters its workers' lists into and
+ * hands to save_fits (LuciBase.py:531-551, LUCI/LuciUtility.py:69-85).  maps_be (optional) receives the same values with
+ * the bytes of every float reversed (big-endian, the byte order of a FITS data unit), so that the files can be written
+ * from it without touching the data on the host.  All DEVICE pointers. */
+int lucifit_pack_maps(const float* rows, int64_t n_rows, int row_floats, float* maps, uint32_t* maps_be, void* stream);
+
 /* Integrated spectra: sums[segment[i]][z] += cube[row_index[i]][z] for i < n_sel, float64 -- the spaxel loops of
  * fit_spectrum_region (LuciBase.py:1015-1023), extract_spectrum / extract_spectrum_region (:872-889, :931-941), the
  * per-bin spectra of fit_wvt (:1434-1447) and the region spectra of skyline_calibration (:1254-1256) as ONE pass.

@@ -57,6 +57,8 @@ extern "C" cudaError_t lf_run_bin(const float* cube, int ny, int nz, int b, int 
                                   float* out, int sm_count, cudaStream_t stream);
 extern "C" cudaError_t lf_run_sim(const LfSimArgs* a, int sm_count, cudaStream_t stream);
 extern "C" cudaError_t lf_run_peak(int mode, int iters, int blocks, float* out, cudaStream_t stream);
+extern "C" cudaError_t lf_run_pack_maps(const float* rows, long long n, int K, float* maps, unsigned* maps_be, int sm_count,
+                                        cudaStream_t stream);
 extern "C" cudaError_t lf_run_segsum(const float* cube, int nz, const long long* row_index, const int* segment,
                                      long long n_sel, int n_segments, int nansum, double* sums, int sm_count,
                                      cudaStream_t stream);
@@ -268,6 +270,17 @@ int lucifit_sanitize_cube(float* cube, int64_t n_values, float lo, float hi, flo
     int sm = 0; int rc = sm_count_of_current_device(&sm); if (rc) return rc;
     cudaError_t e = lf_run_sanitize(cube, n_values, lo, hi, fill, sm, (cudaStream_t)stream);
     if (e != cudaSuccess) return cuda_fail(e, "launch lf_sanitize_kernel");
+    return 0;
+}
+
+int lucifit_pack_maps(const float* rows, int64_t n_rows, int row_floats, float* maps, uint32_t* maps_be, void* stream)
+{
+    if (n_rows < 0 || row_floats < 1 || row_floats > 4096) return fail(LUCIFIT_EINVAL, "bad argument");
+    if (n_rows == 0) return 0;
+    if (!rows || !maps) return fail(LUCIFIT_EINVAL, "rows and maps are required");
+    int sm = 0; int rc = sm_count_of_current_device(&sm); if (rc) return rc;
+    cudaError_t e = lf_run_pack_maps(rows, n_rows, row_floats, maps, (unsigned*)maps_be, sm, (cudaStream_t)stream);
+    if (e != cudaSuccess) return cuda_fail(e, "launch lf_pack_maps_kernel");
     return 0;
 }
 

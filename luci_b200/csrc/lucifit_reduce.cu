@@ -924,3 +924,43 @@ extern "C" cudaError_t lf_run_segsum(const float* cube, int nz, const long long*
     lf_segsum_kernel<<<grid, LF_SEG_THREADS, 0, stream>>>(cube, nz, row_index, segment, n_sel, per, nansum, sums);
     return cudaGetLastError();
 }
+
+// ------------------------------------------------------------------------------------------------ output maps
+// rows[n][K] (what lucifit_fit_batch writes: one row per fitted spaxel, map order) -> field-major maps[K][n], the layout
+// of the 2-D maps Luci.fit_cube returns and LuciUtility.save_fits writes (LuciBase.py:531-551), and, in the same pass, a
+// second copy with the bytes of every float reversed: FITS is big-endian, so the files are then written straight from
+// that copy without a byte swap on the host.  A CTA moves 32 consecutive rows (one contiguous 32 K-float block) through
+// a padded shared-memory tile; both sides are coalesced.
+#define LF_PACK_ROWS 32
+__global__ void __launch_bounds__(256)
+lf_pack_maps_kernel(const float* __restrict__ rows, long long n, int K, float* __restrict__ maps, unsigned* __restrict__ maps_be)
+{
+    extern __shared__ float pack_tile[];                   // [LF_PACK_ROWS][K + 1]
+    const int KP = K + 1;
+    for (long long i0 = (long long)blockIdx.x * LF_PACK_ROWS; i0 < n; i0 += (long long)gridDim.x * LF_PACK_ROWS) {
+        const int nr = (int)((n - i0) < LF_PACK_ROWS ? (n - i0) : LF_PACK_ROWS);
+        const float* src = rows + i0 * K;
+        for (int e = threadIdx.x; e < nr * K; e += blockDim.x) pack_tile[(e / K) * KP + (e % K)] = __ldcs(src + e);
+        __syncthreads();
+        for (int e = threadIdx.x; e < K * LF_PACK_ROWS; e += blockDim.x) {
+            const int k = e / LF_PACK_ROWS, r = e % LF_PACK_ROWS;
+            if (r < nr) {
+                const float v = pack_tile[r * KP + k];
+                maps[(long long)k * n + i0 + r] = v;
+                if (maps_be) maps_be[(long long)k * n + i0 + r] = __byte_perm(__float_as_uint(v), 0, 0x0123);
+            }
+        }
+        __syncthreads();
+    }
+}
+
+extern "C" cudaError_t lf_run_pack_maps(const float* rows, long long n, int K, float* maps, unsigned* maps_be, int sm_count,
+                                        cudaStream_t stream)
+{
+    if (n <= 0) return cudaSuccess;
+    long long want = (n + LF_PACK_ROWS - 1) / LF_PACK_ROWS;
+    long long cap = (long long)sm_count * 8;
+    const int grid = (int)(want < cap ? want : cap);
+    lf_pack_maps_kernel<<<grid, 256, sizeof(float) * LF_PACK_ROWS * (K + 1), stream>>>(rows, n, K, maps, maps_be);
+    return cudaGetLastError();
+}

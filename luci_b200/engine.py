@@ -321,6 +321,20 @@ def bin_cube(cube3d, binning, x_min, x_max, y_min, y_max):
     return out
 
 
+def pack_maps(rows, want_be=False):
+    """``lucifit_pack_maps``: ``rows [n, K]`` -> field-major ``maps [K, n]`` (float32) and, with ``want_be``, the same
+    values byte-reversed (``[K, n]`` int32 holding big-endian floats: the data units of the FITS maps)."""
+    lib = _capi.lib()
+    require_cuda(rows, 'rows', torch.float32)
+    n, K = int(rows.shape[0]), int(rows.shape[1])
+    maps = torch.empty((K, n), dtype=torch.float32, device=rows.device)
+    be = torch.empty((K, n), dtype=torch.int32, device=rows.device) if want_be else None
+    with torch.cuda.device(rows.device):
+        check(lib.lucifit_pack_maps(_ptr(rows), n, K, _ptr(maps), _ptr(be), _stream()))
+    launch_counter['n'] += 1 if n > 0 else 0
+    return (maps, be) if want_be else maps
+
+
 def segment_sum(cube2d, row_index=None, segment=None, n_segments=1, nansum=False):
     """``lucifit_segment_sum``: float64 ``[n_segments, nz]`` sums of the rows ``row_index`` (int64, default all rows) of
     ``cube2d [n_rows, nz]`` into the segments ``segment`` (int32, default all into segment 0; negative = skip)."""

@@ -41,6 +41,25 @@ def _card(key, value, comment=None):
     return card[:80].ljust(80)
 
 
+def _header_block(shape, bitpix, header):
+    """The padded header of a primary HDU holding an array of ``shape`` (numpy order)."""
+    cards = [_card('SIMPLE', True, 'conforms to FITS standard'), _card('BITPIX', bitpix, 'array data type'),
+             _card('NAXIS', len(shape), 'number of array dimensions')]
+    for i, n in enumerate(reversed(shape)):
+        cards.append(_card('NAXIS%d' % (i + 1), n))
+    if header:
+        for k, v in header.items():
+            if str(k).upper() in _STRUCTURAL or v is None:
+                continue
+            if isinstance(v, tuple):                      # (value, comment), e.g. from wcs_to_header
+                cards.append(_card(k, v[0], v[1]))
+            else:
+                cards.append(_card(k, v))
+    cards.append('END'.ljust(80))
+    hdr = ''.join(cards).encode('ascii')
+    return hdr + b' ' * ((-len(hdr)) % _BLOCK)
+
+
 def write_fits(path, data, header=None, overwrite=True):
     data = np.asarray(data)
     if data.dtype == np.float32:
@@ -53,26 +72,23 @@ def write_fits(path, data, header=None, overwrite=True):
         raise TypeError('unsupported dtype %s' % data.dtype)
     if os.path.exists(path) and not overwrite:
         raise OSError('%s exists' % path)
-    cards = [_card('SIMPLE', True, 'conforms to FITS standard'), _card('BITPIX', bitpix, 'array data type'),
-             _card('NAXIS', data.ndim, 'number of array dimensions')]
-    for i, n in enumerate(reversed(data.shape)):
-        cards.append(_card('NAXIS%d' % (i + 1), n))
-    if header:
-        for k, v in header.items():
-            if str(k).upper() in _STRUCTURAL or v is None:
-                continue
-            if isinstance(v, tuple):                      # (value, comment), e.g. from wcs_to_header
-                cards.append(_card(k, v[0], v[1]))
-            else:
-                cards.append(_card(k, v))
-    cards.append('END'.ljust(80))
-    hdr = ''.join(cards).encode('ascii')
-    hdr += b' ' * ((-len(hdr)) % _BLOCK)
     raw = out.tobytes()
     raw += b'\0' * ((-len(raw)) % _BLOCK)
     with open(path, 'wb') as f:
-        f.write(hdr)
+        f.write(_header_block(data.shape, bitpix, header))
         f.write(raw)
+
+
+def write_fits_be(path, be_data, shape, header=None, bitpix=-32):
+    """Like :func:`write_fits` for a data unit that is ALREADY big-endian (a contiguous buffer of ``prod(shape)``
+    4-byte values, e.g. a row of ``lucifit_pack_maps``' byte-reversed output): header + the buffer as it is."""
+    view = memoryview(be_data).cast('B')
+    if len(view) != int(np.prod(shape)) * (abs(bitpix) // 8):
+        raise ValueError('buffer does not hold %s values of %d bits' % (shape, abs(bitpix)))
+    with open(path, 'wb') as f:
+        f.write(_header_block(tuple(shape), bitpix, header))
+        f.write(view)
+        f.write(b'\0' * ((-len(view)) % _BLOCK))
 
 
 # ---- what `astropy.wcs.WCS(header, naxis=2).to_header()` writes for a 2-D celestial WCS (the header of every map the
@@ -256,10 +272,9 @@ def read_fits(path):
     return data.astype(np.dtype(dt).newbyteorder('=')), header
 
 
-def save_fits(output_dir, object_name, lines, ampls_fits, flux_fits, flux_errors_fits, velocities_fits,
-              broadenings_fits, velocities_errors_fits, broadenings_errors_fits, chi2_fits, continuum_fits,
-              continuum_error_fits, header, binning=1, suffix='', fit_function=None):
-    """Same directory layout and file names as ``LUCI.LuciUtility.save_fits`` (LuciUtility.py:22-85)."""
+def map_jobs(output_dir, object_name, lines, binning=1, suffix='', fit_function=None):
+    """``(path, field, line index or None)`` of every file ``LUCI.LuciUtility.save_fits`` writes (LuciUtility.py:22-85):
+    same directory layout and file names; ``field`` is the name of the quantity in ``engine.ROW_FIELDS`` / ``ROW_SCALARS``."""
     for sub in ('Amplitudes', 'Fluxes', 'Velocity', 'Broadening'):
         os.makedirs(os.path.join(output_dir, sub), exist_ok=True)
     output_name = object_name + suffix
@@ -268,7 +283,7 @@ def save_fits(output_dir, object_name, lines, ampls_fits, flux_fits, flux_errors
     if fit_function is not None:
         output_name += "_" + fit_function
     lines_fit = []
-    jobs = []                     # (path, 2-D map): 7 L + 3 independent files
+    jobs = []                     # 7 L + 3 independent files
     for ct, line_ in enumerate(lines):
         # NOTE: the reference never appends to its `lines_fit` list (LuciUtility.py:63-68), so repeated line names
         # overwrite one another there; here the second component gets the documented `_2` suffix.
@@ -277,20 +292,46 @@ def save_fits(output_dir, object_name, lines, ampls_fits, flux_fits, flux_errors
         else:
             name = line_
         lines_fit.append(line_)
-        jobs.append((output_dir + '/Amplitudes/' + output_name + '_' + name + '_Amplitude.fits', ampls_fits[:, :, ct]))
-        jobs.append((output_dir + '/Fluxes/' + output_name + '_' + name + '_Flux.fits', flux_fits[:, :, ct]))
-        jobs.append((output_dir + '/Fluxes/' + output_name + '_' + name + '_Flux_err.fits', flux_errors_fits[:, :, ct]))
-        jobs.append((output_dir + '/Velocity/' + output_name + '_' + name + '_velocity.fits', velocities_fits[:, :, ct]))
-        jobs.append((output_dir + '/Broadening/' + output_name + '_' + name + '_broadening.fits', broadenings_fits[:, :, ct]))
-        jobs.append((output_dir + '/Velocity/' + output_name + '_' + name + '_velocity_err.fits', velocities_errors_fits[:, :, ct]))
-        jobs.append((output_dir + '/Broadening/' + output_name + '_' + name + '_broadening_err.fits', broadenings_errors_fits[:, :, ct]))
-    jobs.append((output_dir + '/' + output_name + '_Chi2.fits', chi2_fits))
-    jobs.append((output_dir + '/' + output_name + '_continuum.fits', continuum_fits))
-    jobs.append((output_dir + '/' + output_name + '_continuum_error.fits', continuum_error_fits))
-    if sum(np.asarray(m).size for _, m in jobs) < (1 << 22):
-        for path, m in jobs:
-            write_fits(path, m, header)
+        jobs.append((output_dir + '/Amplitudes/' + output_name + '_' + name + '_Amplitude.fits', 'amplitudes', ct))
+        jobs.append((output_dir + '/Fluxes/' + output_name + '_' + name + '_Flux.fits', 'fluxes', ct))
+        jobs.append((output_dir + '/Fluxes/' + output_name + '_' + name + '_Flux_err.fits', 'flux_errors', ct))
+        jobs.append((output_dir + '/Velocity/' + output_name + '_' + name + '_velocity.fits', 'velocities', ct))
+        jobs.append((output_dir + '/Broadening/' + output_name + '_' + name + '_broadening.fits', 'sigmas', ct))
+        jobs.append((output_dir + '/Velocity/' + output_name + '_' + name + '_velocity_err.fits', 'vels_errors', ct))
+        jobs.append((output_dir + '/Broadening/' + output_name + '_' + name + '_broadening_err.fits', 'sigmas_errors', ct))
+    jobs.append((output_dir + '/' + output_name + '_Chi2.fits', 'chi2', None))
+    jobs.append((output_dir + '/' + output_name + '_continuum.fits', 'continuum', None))
+    jobs.append((output_dir + '/' + output_name + '_continuum_error.fits', 'continuum_error', None))
+    return jobs
+
+
+def _run_jobs(fn, jobs, n_values):
+    if n_values < (1 << 22):
+        for job in jobs:
+            fn(job)
     else:                         # large maps: the byte swap and the file writes release the GIL
         from concurrent.futures import ThreadPoolExecutor
         with ThreadPoolExecutor(max_workers=min(8, os.cpu_count() or 1)) as pool:
-            list(pool.map(lambda job: write_fits(job[0], job[1], header), jobs))
+            list(pool.map(fn, jobs))
+
+
+def save_fits(output_dir, object_name, lines, ampls_fits, flux_fits, flux_errors_fits, velocities_fits,
+              broadenings_fits, velocities_errors_fits, broadenings_errors_fits, chi2_fits, continuum_fits,
+              continuum_error_fits, header, binning=1, suffix='', fit_function=None):
+    """Same arguments, directory layout and file names as ``LUCI.LuciUtility.save_fits`` (LuciUtility.py:22-85)."""
+    maps = {'amplitudes': ampls_fits, 'fluxes': flux_fits, 'flux_errors': flux_errors_fits, 'velocities': velocities_fits,
+            'sigmas': broadenings_fits, 'vels_errors': velocities_errors_fits, 'sigmas_errors': broadenings_errors_fits,
+            'chi2': chi2_fits, 'continuum': continuum_fits, 'continuum_error': continuum_error_fits}
+    jobs = map_jobs(output_dir, object_name, lines, binning, suffix, fit_function)
+    pick = lambda field, k: maps[field] if k is None else maps[field][:, :, k]
+    _run_jobs(lambda job: write_fits(job[0], pick(job[1], job[2]), header), jobs,
+              sum(np.asarray(pick(f, k)).size for _, f, k in jobs))
+
+
+def save_fits_be(output_dir, object_name, lines, be_maps, field_index, shape, header, binning=1, suffix='', fit_function=None):
+    """The same files from big-endian data units that already exist: ``be_maps [K, ny * nx]`` (4-byte values, every row
+    one 2-D map ``shape = (ny, nx)`` as ``lucifit_pack_maps`` lays them out) and ``field_index(field, line) -> row``.
+    Nothing is converted or copied on the host; the writes run in a thread pool."""
+    jobs = map_jobs(output_dir, object_name, lines, binning, suffix, fit_function)
+    _run_jobs(lambda job: write_fits_be(job[0], be_maps[field_index(job[1], job[2])], shape, header), jobs,
+              len(jobs) * int(np.prod(shape)))

@@ -530,3 +530,40 @@ def test_segment_sum_against_numpy():
                 np.testing.assert_allclose(got, want, rtol=1e-11, atol=1e-12, equal_nan=True)
         whole = engine.segment_sum(t(cube), nansum=True).cpu().numpy()
         np.testing.assert_allclose(whole[0], np.nansum(cube.astype(np.float64), axis=0), rtol=1e-11, atol=1e-12)
+
+
+def test_staged_big_endian_output_equals_plain_path(world):
+    """Large fits fetch their maps through pinned staging and write the FITS files from the byte-reversed copy the
+    device made (lucifit_pack_maps): same arrays, byte-identical files."""
+    import glob
+    luci, sc, out = world
+    v0, b0 = sc.priors()
+    args = (SN3, 'sincgauss', [1] * 5, [1] * 5, 0, 12, 0, 10)
+    base = os.path.join(out, 'Luci_outputs')
+    plain = luci.fit_cube(*args, prior_values=(v0, b0), uncertainty_bool=True)
+    files = sorted(glob.glob(os.path.join(base, '**', 'OBJ_sincgauss_*.fits'), recursive=True))
+    assert len(files) == 38
+    ref_bytes = {f: open(f, 'rb').read() for f in files}
+    ref_maps = {k: v.copy() for k, v in luci.last_fit_maps.items()}
+    for f in files:
+        os.remove(f)
+    luci.STAGE_MIN_VALUES = 1
+    try:
+        staged = luci.fit_cube(*args, prior_values=(v0, b0), uncertainty_bool=True)
+        assert luci._last_be is not None
+    finally:
+        del luci.STAGE_MIN_VALUES
+    for a, b in zip(plain, staged):
+        np.testing.assert_array_equal(a, b)
+    for k, v in ref_maps.items():
+        np.testing.assert_array_equal(v, luci.last_fit_maps[k], err_msg=k)
+    for f in files:
+        assert open(f, 'rb').read() == ref_bytes[f], f
+    # the returned arrays do not alias the staging buffers: a second fit leaves them alone
+    keep = staged[0].copy()
+    luci.STAGE_MIN_VALUES = 1
+    try:
+        luci.fit_cube(SN3, 'sincgauss', [1] * 5, [1] * 5, 0, 12, 0, 10, prior_values=(v0 + 3.0, b0))
+    finally:
+        del luci.STAGE_MIN_VALUES
+    np.testing.assert_array_equal(staged[0], keep)

@@ -42,18 +42,19 @@ def main():
         return r
 
     t_io = {'s': 0.0}
-    real_save = luci_mod.save_fits
+    real_save = Luci._save_maps
 
-    def timed_save(*args, **kw):
+    def timed_save(self, *args, **kw):
         t0 = time.perf_counter()
-        r = real_save(*args, **kw)
+        r = real_save(self, *args, **kw)
         t_io['s'] += time.perf_counter() - t0
         return r
 
     engine.fit_batch = timed_fit
-    luci_mod.save_fits = timed_save
+    Luci._save_maps = timed_save
     luci.create_deep_image()
-    for label, kw in (('given priors', dict(prior_values=(v0, b0))), ('device-measured priors', dict())):
+    for label, kw in (('given priors (first call: allocates the pinned staging)', dict(prior_values=(v0, b0))),
+                      ('given priors', dict(prior_values=(v0, b0))), ('device-measured priors', dict())):
         t_fit['s'] = t_io['s'] = 0.0
         torch.cuda.synchronize(); t0 = time.perf_counter()
         vel, broad, flux, ampl = luci.fit_entire_cube(SN3_LINES, 'sincgauss', [1] * 5, [1] * 5, **kw)

@@ -548,7 +548,10 @@ def run_e2e(torch, engine, ldist, cfg, cube, theta, v0, b0, dev, args, world, n_
         mine = 4 * probe.numel() * 4 / (e0.elapsed_time(e1) * 1e-3) / 1e9
         h2d_conc = ldist.sum_over_ranks(mine, dev) / world
     del probe
-    stream = engine.HostCubeStream(cfg, dev)
+    # chunk: 131 072 spaxels (441 MB) when the rank streams the whole cube; smaller shards keep >= 16 chunks in the pipeline
+    # so that its fill (first copy) and drain (last fit + copy back) stay a small part of the step
+    chunk = int(min(1 << 17, max(1 << 14, (n_e2e // 16 + 1023) // 1024 * 1024)))
+    stream = engine.HostCubeStream(cfg, dev, chunk=chunk)
     stream.run(host_cube, host_par, host_rows)                       # warm-up
     if world > 1:
         torch.distributed.barrier()

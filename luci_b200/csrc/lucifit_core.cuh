@@ -1555,7 +1555,7 @@ LF_CORE void lf_stage_unc(const LfCfg& cfg, const LfWarp<LANES>& w, const float*
 {
     typedef LfDims<MODEL, L, NV, NS> D;
     constexpr int PF = 3 * L + 1;
-    constexpr int STRIDE = PF | 1;
+    constexpr int TS = LANES + 4;                        // row stride of the D tile [PF][TS]: 16-byte rows, skewed banks
     constexpr int NE = PF * (PF + 1) / 2;
     constexpr int SLOTS = (NE + LANES - 1) / LANES;
     const int status = reinterpret_cast<const int*>(state)[LF_SO_STATUS];
@@ -1626,7 +1626,7 @@ LF_CORE void lf_stage_unc(const LfCfg& cfg, const LfWarp<LANES>& w, const float*
         }
         float Sx = 0.0f, Cx = 1.0f;
         if (MODEL != LF_GAUSSIAN && inwin) lf_phase((double)x * inv_w, Sx, Cx);
-        float* trow = tile + w.lane * STRIDE;
+        float* trow = tile + w.lane;                       // D_i of this lane's sample: trow[i * TS]
         // pass 1: model value at the solution (residual r0) and the unit profiles g0
         float m = cont;
 #pragma unroll 1
@@ -1639,7 +1639,7 @@ LF_CORE void lf_stage_unc(const LfCfg& cfg, const LfWarp<LANES>& w, const float*
             if (MODEL != LF_GAUSSIAN) { s = Sx * X.ck - Cx * X.sk; c = Cx * X.ck + Sx * X.sk; }
             float g, gp, gs;
             lf_profile_sc<MODEL>(X.ln, dx, s, c, iw, hint, g, gp, gs);
-            trow[3 * k] = live ? g : 0.0f;
+            trow[(3 * k) * TS] = live ? g : 0.0f;
             m += X.aeff * g;
         }
         const float r0 = yn - m;
@@ -1647,7 +1647,7 @@ LF_CORE void lf_stage_unc(const LfCfg& cfg, const LfWarp<LANES>& w, const float*
 #pragma unroll 1
         for (int k = 0; k < L; ++k) {
             const float Ak = lines[13 * k].aeff;
-            const float g0 = trow[3 * k];
+            const float g0 = trow[(3 * k) * TS];
             gvt[w.lane] = g0;
             // The 12 shifted variants of a line differ by at most 2 delta in centre and width, so one conservative test
             // (closest centre, widest / narrowest width) tells whether ALL of them are in the wing for this chunk.  Then
@@ -1736,8 +1736,8 @@ LF_CORE void lf_stage_unc(const LfCfg& cfg, const LfWarp<LANES>& w, const float*
             if (MODEL == LF_SINC) { gv[9] = gv[10] = gv[1]; gv[11] = gv[12] = gv[2]; }
             const float Dp = Ak * (gv[1] - gv[2]) * (0.5f / dl);
             const float Ds = Ak * (gv[3] - gv[4]) * (0.5f / dl);
-            trow[3 * k + 1] = live ? Dp : 0.0f;
-            trow[3 * k + 2] = live ? Ds : 0.0f;
+            trow[(3 * k + 1) * TS] = live ? Dp : 0.0f;
+            trow[(3 * k + 2) * TS] = live ? Ds : 0.0f;
             if (live) {
                 const float base = Ak * g0;
                 float* sk_ = sums + (5 * k) * LANES + w.lane;
@@ -1767,17 +1767,26 @@ LF_CORE void lf_stage_unc(const LfCfg& cfg, const LfWarp<LANES>& w, const float*
                 }
             }
         }
-        trow[3 * L] = live ? 1.0f : 0.0f;
+        trow[(3 * L) * TS] = live ? 1.0f : 0.0f;
         w.sync();
         // Gram matrix of the D vectors: entry e = (i, j), i <= j, owned by lane e % LANES
 #pragma unroll
         for (int s = 0; s < SLOTS; ++s) {
             if (s * LANES + w.lane < NE) {
-                const float* ti = tile + gi[s];
-                const float* tj = tile + gj[s];
+                const float* ti = tile + gi[s] * TS;
+                const float* tj = tile + gj[s] * TS;
                 float acc = 0.0f;
-#pragma unroll 8
-                for (int t = 0; t < LANES; ++t) acc += ti[t * STRIDE] * tj[t * STRIDE];
+#if defined(__CUDA_ARCH__)
+                if (LANES == 32) {                          // rows are 16-byte aligned: four samples per load
+#pragma unroll
+                    for (int q = 0; q < LANES / 4; ++q) {
+                        const float4 a = *reinterpret_cast<const float4*>(ti + 4 * q);
+                        const float4 b = *reinterpret_cast<const float4*>(tj + 4 * q);
+                        acc += a.x * b.x + a.y * b.y + a.z * b.z + a.w * b.w;
+                    }
+                } else
+#endif
+                for (int t = 0; t < LANES; ++t) acc += ti[t] * tj[t];
                 gram[s] += acc;
             }
         }
@@ -1835,13 +1844,15 @@ LF_CORE void lf_stage_unc(const LfCfg& cfg, const LfWarp<LANES>& w, const float*
         double ip = 1.0 / pv;
         for (int j = w.lane; j < PF; j += LANES) Hm[c * PF + j] = (j == c ? 1.0 : Hm[c * PF + j]) * ip;
         w.sync();
-        for (int r = 0; r < PF; ++r) {
-            if (r == c) continue;
-            double f = Hm[r * PF + c];
-            w.sync();
-            for (int j = w.lane; j < PF; j += LANES) Hm[r * PF + j] = (j == c ? 0.0 : Hm[r * PF + j]) - f * Hm[c * PF + j];
-            w.sync();
+        // eliminate column c from all other rows at once: the lanes share the PF^2 elements (not one row after the other
+        // with PF lanes busy); column c is stashed first because its elements are overwritten by their owners
+        for (int r = w.lane; r < PF; r += LANES) uv[r] = Hm[r * PF + c];
+        w.sync();
+        for (int e = w.lane; e < PF * PF; e += LANES) {
+            const int r = e / PF, j = e - r * PF;
+            if (r != c) Hm[e] = (j == c ? 0.0 : Hm[e]) - uv[r] * Hm[c * PF + j];
         }
+        w.sync();
     }
     if (!singular) {
         for (int c = PF - 1; c >= 0; --c) {

@@ -88,7 +88,7 @@ static inline void lf_make_layout(int L, int P, int nz, int nfit, int ncont, int
     }
     ly.un_apd = (int)o; o = lf_align(o + sizeof(double) * 3 * L, 16);
     ly.un_gt = (int)o; o = lf_align(o + sizeof(float) * (13 + 5 * L) * lanes, 16);
-    ly.un_tile = (int)o; o = lf_align(o + sizeof(float) * lanes * (PF | 1), 16);
+    ly.un_tile = (int)o; o = lf_align(o + sizeof(float) * PF * (lanes + 4), 16);     // D tile [PF][lanes + 4]
     ly.un_bytes = (int)o;
     // out: yw | sw | cw | lines[L] | apd[3 L]
     o = win;

@@ -955,10 +955,24 @@ LF_CORE void lf_stage_prep(const LfCfg& cfg, const LfWarp<LANES>& w, const float
     w.sync();
     // the spectrum is read once from HBM: LF_PREP_MLP independent loads per lane are issued before the first one is
     // consumed, otherwise the stage sits on DRAM latency (this loop is the only global traffic of the stage)
+    const bool plain = !cfg.bkg && !cfg.trans;          // the common case keeps the streaming loop to load / store / max / NaN count
     for (int i0 = w.lane; i0 < nz; i0 += LANES * LF_PREP_MLP) {
         float q[LF_PREP_MLP];
 #pragma unroll
         for (int j = 0; j < LF_PREP_MLP; ++j) { const int i = i0 + j * LANES; q[j] = i < nz ? gspec[i] : 0.0f; }
+        if (plain) {
+#pragma unroll
+            for (int j = 0; j < LF_PREP_MLP; ++j) {
+                const int i = i0 + j * LANES;
+                if (i < nz) {
+                    const float s = q[j];
+                    spec[i] = s;
+                    nan_ct += (s != s);
+                    smax = fmaxf(smax, s);
+                }
+            }
+            continue;
+        }
 #pragma unroll
         for (int j = 0; j < LF_PREP_MLP; ++j) {
             const int i = i0 + j * LANES;
@@ -968,13 +982,15 @@ LF_CORE void lf_stage_prep(const LfCfg& cfg, const LfWarp<LANES>& w, const float
                 spec[i] = s;
                 nan_ct += (s != s);
                 smax = fmaxf(smax, s);
-                if (i >= cfg.fit_lo && i < cfg.fit_hi) wmax = fmaxf(wmax, s);
                 float st = s;
                 if (cfg.trans) { float t = cfg.trans[i]; if (t > 0.5f) st = s / t; }
                 tmax = fmaxf(tmax, st);
             }
         }
     }
+    if (plain) tmax = smax;
+    w.sync();
+    for (int i = cfg.fit_lo + w.lane; i < cfg.fit_hi; i += LANES) wmax = fmaxf(wmax, spec[i]);   // (own writes + sync: visible)
     smax = w.max(smax); wmax = w.max(wmax); tmax = w.max(tmax);
     nan_ct = w.sum(nan_ct);
     w.sync();

@@ -454,7 +454,7 @@ LF_CORE void lf_setup_lines(const LfCfg& cfg, const LfWarp<LANES>& w, const floa
         int g = NV == 1 ? 0 : cfg.vg[k], h = NS == 1 ? 0 : cfg.sg[k];
         float v = th[D::IV + g], beta = th[D::IS + h];
         float vt = v * (1.0f / LF_C_KMS);
-        float i1v = 1.0f / (1.0f + vt);
+        float i1v = LF_SETUP_RCP(1.0f + vt);
         float p = cfg.p0[k] * i1v;
         float sig = p * beta * (1.0f / LF_C_KMS);
         LfLineX x;
@@ -470,11 +470,11 @@ LF_CORE void lf_setup_lines(const LfCfg& cfg, const LfWarp<LANES>& w, const floa
         lf_fold_wing(x);
         x.Gk = x.ln.sig; x.Ek = 0.0f;
         if (MODEL == LF_SINCGAUSS && cfg.i48 >= 0) {
-            const float iw2 = 1.0f / (LF_SQRT2_F * sinc_w);
+            const float iw2 = LF_SETUP_RCP(LF_SQRT2_F * sinc_w);
             const float u = x.ln.sig * iw2;
-            const float ierf_u = 1.0f / erff(u);
+            const float ierf_u = LF_SETUP_RCP(erff(u));
             x.Gk = x.ln.sig * ierf_u;
-            x.Ek = LF_2ISQRTPI_F * expf(-u * u) * ierf_u * iw2;
+            x.Ek = LF_2ISQRTPI_F * LF_SETUP_EXP(-u * u) * ierf_u * iw2;
         }
         sl[k] = x;
     }
@@ -500,11 +500,11 @@ LF_CORE void lf_setup_lines(const LfCfg& cfg, const LfWarp<LANES>& w, const floa
             float a83 = x83.aeff;
             int g83 = x83.vg, g48 = x48.vg, h83 = x83.sg, h48 = x48.sg;
             float R, E83 = 0.f, E48 = 0.f;
-            if (MODEL == LF_SINCGAUSS) { R = x83.Gk / (3.0f * x48.Gk); E83 = x83.Ek; E48 = x48.Ek; }
+            if (MODEL == LF_SINCGAUSS) { R = x83.Gk * LF_SETUP_RCP(3.0f * x48.Gk); E83 = x83.Ek; E48 = x48.Ek; }
             else R = lf_tie_ratio(MODEL, p83, b83, s83, p48, b48, s48, h83 == h48, sinc_w);
 #pragma unroll
             for (int g = 0; g < NV; ++g)
-                tx->cRv[g] = a83 * R * ((g == g83 ? x83.dpdv / p83 - E83 * x83.dsdv : 0.f) - (g == g48 ? x48.dpdv / p48 - E48 * x48.dsdv : 0.f));
+                tx->cRv[g] = a83 * R * ((g == g83 ? x83.dpdv * LF_SETUP_RCP(p83) - E83 * x83.dsdv : 0.f) - (g == g48 ? x48.dpdv * LF_SETUP_RCP(p48) - E48 * x48.dsdv : 0.f));
 #pragma unroll
             for (int h = 0; h < NS; ++h) {
                 float t = 0.f;

@@ -26,7 +26,13 @@ __device__ __forceinline__ float lf_mufu_rcp(float x) { float y; asm("rcp.approx
 #define LF_COS(x) __cosf(x)
 #define LF_RINT(x) rintf(x)
 #define LF_RSQRT(x) rsqrtf(x)
+// per-line constants of one model evaluation (lf_line_setup, lf_setup_lines: five lanes busy, a dozen divisions and two
+// exponentials each): the MUFU forms (1 ulp / 2 ulp) scale a whole line's profile by 1e-7 at most
+#define LF_SETUP_RCP(x) lf_mufu_rcp(x)
+#define LF_SETUP_EXP(x) lf_mufu_ex2((x) * 1.4426950408889634f)
 #else
+#define LF_SETUP_RCP(x) (1.0f / (x))
+#define LF_SETUP_EXP(x) expf(x)
 #define LF_RSQRT(x) (1.0f / sqrtf(x))
 #define LF_EXP(x) expf(x)
 #define LF_RCP(x) (1.0f / (x))
@@ -171,16 +177,16 @@ LF_HD void lf_line_setup(int model, float pp, float dp, float sig, float sinc_w,
     if (model == LF_SINCGAUSS) s = fmaxf(s, 0.02f * sinc_w * (LF_SQRT2_F / LF_PI_F));   // a >= 0.02 (cancellation guard)
     else s = fmaxf(s, 1e-6f);
     ln.sig = s;
-    ln.isig = 1.0f / s;
+    ln.isig = LF_SETUP_RCP(s);
     ln.is2s = ln.isig * (1.0f / LF_SQRT2_F);
     if (model == LF_SINCGAUSS) {
-        float a = s * (LF_PI_F / LF_SQRT2_F) / sinc_w;
+        float a = s * (LF_PI_F / LF_SQRT2_F) * LF_SETUP_RCP(sinc_w);
         float ef = erff(a);
         ln.a = a;
-        ln.ea = expf(-a * a);
-        ln.ierf = 1.0f / ef;
+        ln.ea = LF_SETUP_EXP(-a * a);
+        ln.ierf = LF_SETUP_RCP(ef);
         ln.q = LF_2ISQRTPI_F * ln.ea * ln.ierf;
-        ln.ia = 1.0f / a;
+        ln.ia = LF_SETUP_RCP(a);
     } else {
         ln.a = 0.0f; ln.ea = 0.0f; ln.ierf = 1.0f; ln.q = 0.0f; ln.ia = 0.0f;
     }

@@ -41,6 +41,9 @@ __device__ __forceinline__ float lf_mufu_rcp(float x) { float y; asm("rcp.approx
 #define LF_RINT(x) rintf(x)
 #endif
 
+#ifndef LF_PHASE_MUFU
+#define LF_PHASE_MUFU 1
+#endif
 #define LF_PI_F 3.14159265358979f
 #define LF_ISQRTPI_F 0.564189583547756f   /* 1/sqrt(pi) */
 #define LF_2ISQRTPI_F 1.128379167095513f  /* 2/sqrt(pi) */
@@ -147,7 +150,12 @@ LF_HD void lf_phase(double t, float& s, float& c)
 {
     double r = t - 2.0 * rint(0.5 * t);               // r in [-1, 1]
 #if defined(__CUDA_ARCH__)
+#if LF_PHASE_MUFU
+    const float a = LF_PI_F * (float)r;               // |a| <= pi: MUFU.SIN / MUFU.COS are good to 4e-7 absolute there
+    s = __sinf(a); c = __cosf(a);
+#else
     sincospif((float)r, &s, &c);
+#endif
 #else
     s = (float)sin(3.141592653589793 * r);
     c = (float)cos(3.141592653589793 * r);

@@ -214,6 +214,24 @@ LF_CORE int lf_nearest_axis(const double* axis, int nz, double pos)
     return (fabs(axis[lo - 1] - pos) <= fabs(axis[lo] - pos)) ? lo - 1 : lo;
 }
 
+// The same index found from a guess: the axis is close to uniform, so `guess` = fit_lo + (pos - x_ref) / (mean channel
+// width) is within a sample or two and a short walk replaces the ten dependent loads of the bisection.
+LF_CORE int lf_nearest_axis_from(const double* axis, int nz, double pos, int guess)
+{
+    int lo = guess < 0 ? 0 : (guess > nz ? nz : guess);        // -> first index with axis[i] >= pos, in [0, nz]
+    while (lo < nz && axis[lo] < pos) ++lo;
+    while (lo > 0 && axis[lo - 1] >= pos) --lo;
+    if (lo == 0) return 0;
+    if (lo == nz) return nz - 1;
+    return (fabs(axis[lo - 1] - pos) <= fabs(axis[lo] - pos)) ? lo - 1 : lo;
+}
+
+LF_CORE int lf_axis_guess(const LfCfg& cfg, double pos)
+{
+    const double g = (double)cfg.fit_lo + (pos - cfg.x_ref) * (double)cfg.ichan;
+    return (int)fmin(fmax(g, 0.0), (double)cfg.nz);
+}
+
 // Where the reference's np.argmin(|axis - target|) lands once the NaN samples have been removed from spectrum and axis
 // (LuciBase.py:358-360): the valid sample nearest to `target`, given the nearest sample `idx` of the full axis.
 template <typename IsNan>
@@ -1053,7 +1071,7 @@ LF_CORE void lf_stage_prep(const LfCfg& cfg, const LfWarp<LANES>& w, const float
         if (vel0 != vel0) vel0 = 0.0f;                 // LuciFit.py:406-409
         double lam = cfg.line_nm[k];
         double pos = 1e7 / (((double)vel0 / 299792.0) * lam + lam);
-        int ind = lf_nearest_axis(cfg.axis, nz, pos);
+        int ind = lf_nearest_axis_from(cfg.axis, nz, pos, lf_axis_guess(cfg, pos));
         float amp;
         if (ind + 5 > nz - 1) {
             amp = spec[ind];                           // IndexError branch (LuciFit.py:420-421)
@@ -1430,7 +1448,7 @@ LF_CORE void lf_stage_out(const LfCfg& cfg, const LfWarp<LANES>& w, const float*
     // LuciFit.py:799-801, 1065-1068).  The scale cancels: chi2 = sum (s_T/scale - m)^2 / (noise (N - P_full)).
     LfLineX* sl = wk.lines;
     for (int k = w.lane; k < L; k += LANES) {
-        int idx = lf_nearest_axis(cfg.axis, cfg.nz, apd[L + k]);
+        int idx = lf_nearest_axis_from(cfg.axis, cfg.nz, apd[L + k], lf_axis_guess(cfg, apd[L + k]));
         if (status & LF_ST_NAN_SAMPLES)                 // Model.plot snaps on the axis the NaN samples were removed from
             idx = lf_valid_near(cfg.axis, cfg.nz, idx, apd[L + k], [&](int j) {
                 float v = gspec[j];
@@ -1500,7 +1518,8 @@ LF_CORE void lf_stage_out(const LfCfg& cfg, const LfWarp<LANES>& w, const float*
         } else if (MODEL == LF_SINC) {
             flux = PI * sqrt(PI) * Ak * sinc_w_d;
         } else {
-            flux = (1.20671 / (PI * FWHM_COEFF)) * Ak * (SQ2PI * s / erf(s / (1.4142135623730951 * sinc_w_d)));
+            // (erf in FP32: 1e-7 of a flux that is stored as float32; the float64 routine costs ~120 instructions)
+            flux = (1.20671 / (PI * FWHM_COEFF)) * Ak * (SQ2PI * s / (double)erff((float)(s / (1.4142135623730951 * sinc_w_d))));
         }
         double lam = cfg.line_nm[k];
         double v = 299792.0 * ((1e7 / pk - lam) / lam);                         // LuciFitParameters.py:34-36

@@ -181,6 +181,10 @@ int lucifit_sim_cube(const lucifit_config* cfg, int64_t n_spaxel, const float* a
  * from it without touching the data on the host.  All DEVICE pointers. */
 int lucifit_pack_maps(const float* rows, int64_t n_rows, int row_floats, float* maps, uint32_t* maps_be, void* stream);
 
+/* median[r] = np.nanmedian(cube[r][lo:hi]) (the two middle values averaged in float64; NaN when nothing is valid): the
+ * level the absorption template is scaled by, LuciBase.py:354-356.  hi - lo <= 1024.  DEVICE pointers. */
+int lucifit_row_median(const float* cube, int64_t n_rows, int nz, int lo, int hi, float* median, void* stream);
+
 /* Integrated spectra: sums[segment[i]][z] += cube[row_index[i]][z] for i < n_sel, float64 -- the spaxel loops of
  * fit_spectrum_region (LuciBase.py:1015-1023), extract_spectrum / extract_spectrum_region (:872-889, :931-941), the
  * per-bin spectra of fit_wvt (:1434-1447) and the region spectra of skyline_calibration (:1254-1256) as ONE pass.

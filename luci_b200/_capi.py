@@ -43,7 +43,7 @@ class lucifit_config(C.Structure):
 
 EXPORTS = ['lucifit_row_floats', 'lucifit_workspace_bytes', 'lucifit_fit_batch', 'lucifit_fit_stages', 'lucifit_deep_image',
            'lucifit_snr_map', 'lucifit_bin_cube', 'lucifit_sim_cube', 'lucifit_peak_probe', 'lucifit_estimate_prior',
-           'lucifit_sanitize_cube', 'lucifit_pack_maps', 'lucifit_segment_sum', 'lucifit_peer_export', 'lucifit_peer_open', 'lucifit_peer_close', 'lucifit_last_error',
+           'lucifit_sanitize_cube', 'lucifit_row_median', 'lucifit_pack_maps', 'lucifit_segment_sum', 'lucifit_peer_export', 'lucifit_peer_open', 'lucifit_peer_close', 'lucifit_last_error',
            'lucifit_version']
 
 _lib = None
@@ -75,6 +75,8 @@ def declare(lib):
     lib.lucifit_estimate_prior.restype = C.c_int
     lib.lucifit_sanitize_cube.argtypes = [vp, i64, C.c_float, C.c_float, C.c_float, vp]
     lib.lucifit_sanitize_cube.restype = C.c_int
+    lib.lucifit_row_median.argtypes = [vp, i64, C.c_int, C.c_int, C.c_int, vp, vp]
+    lib.lucifit_row_median.restype = C.c_int
     lib.lucifit_pack_maps.argtypes = [vp, i64, C.c_int, vp, vp, vp]
     lib.lucifit_pack_maps.restype = C.c_int
     lib.lucifit_segment_sum.argtypes = [vp, C.c_int, vp, vp, i64, C.c_int, C.c_int, vp, vp]

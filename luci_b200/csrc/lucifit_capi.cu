@@ -57,6 +57,8 @@ extern "C" cudaError_t lf_run_bin(const float* cube, int ny, int nz, int b, int 
                                   float* out, int sm_count, cudaStream_t stream);
 extern "C" cudaError_t lf_run_sim(const LfSimArgs* a, int sm_count, cudaStream_t stream);
 extern "C" cudaError_t lf_run_peak(int mode, int iters, int blocks, float* out, cudaStream_t stream);
+extern "C" cudaError_t lf_run_rowmedian(const float* cube, long long n_rows, int nz, int lo, int hi, float* out, int sm_count,
+                                        cudaStream_t stream);
 extern "C" cudaError_t lf_run_pack_maps(const float* rows, long long n, int K, float* maps, unsigned* maps_be, int sm_count,
                                         cudaStream_t stream);
 extern "C" cudaError_t lf_run_segsum(const float* cube, int nz, const long long* row_index, const int* segment,
@@ -281,6 +283,18 @@ int lucifit_pack_maps(const float* rows, int64_t n_rows, int row_floats, float* 
     int sm = 0; int rc = sm_count_of_current_device(&sm); if (rc) return rc;
     cudaError_t e = lf_run_pack_maps(rows, n_rows, row_floats, maps, (unsigned*)maps_be, sm, (cudaStream_t)stream);
     if (e != cudaSuccess) return cuda_fail(e, "launch lf_pack_maps_kernel");
+    return 0;
+}
+
+int lucifit_row_median(const float* cube, int64_t n_rows, int nz, int lo, int hi, float* median, void* stream)
+{
+    if (n_rows < 0 || nz < 1 || lo < 0 || hi > nz || hi <= lo) return fail(LUCIFIT_EINVAL, "bad argument");
+    if (hi - lo > 1024) return fail(LUCIFIT_EINVAL, "row_median: windows of up to 1024 samples are supported");
+    if (n_rows == 0) return 0;
+    if (!cube || !median) return fail(LUCIFIT_EINVAL, "cube and median are required");
+    int sm = 0; int rc = sm_count_of_current_device(&sm); if (rc) return rc;
+    cudaError_t e = lf_run_rowmedian(cube, n_rows, nz, lo, hi, median, sm, (cudaStream_t)stream);
+    if (e != cudaSuccess) return cuda_fail(e, "launch lf_rowmedian_kernel");
     return 0;
 }
 

@@ -964,3 +964,51 @@ extern "C" cudaError_t lf_run_pack_maps(const float* rows, long long n, int K, f
     lf_pack_maps_kernel<<<grid, 256, sizeof(float) * LF_PACK_ROWS * (K + 1), stream>>>(rows, n, K, maps, maps_be);
     return cudaGetLastError();
 }
+
+// ------------------------------------------------------------------------------------------------ row medians
+// np.nanmedian(sky[lo:hi]) of every row (the continuum level the absorption template is scaled by, LuciBase.py:354-356):
+// the same register sort as SNR method 2, one warp per row; the two middle keys are averaged in float64.
+template <int NR>
+__global__ void __launch_bounds__(RED_WARPS * 32)
+lf_rowmedian_kernel(const float* __restrict__ cube, long long n_rows, int nz, int lo, int hi, float* __restrict__ out)
+{
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const long long stride = (long long)gridDim.x * RED_WARPS;
+    for (long long s = (long long)blockIdx.x * RED_WARPS + warp; s < n_rows; s += stride) {
+        const float* row = cube + s * (long long)nz;
+        float v[NR];
+        int m = 0;
+#pragma unroll
+        for (int i = 0; i < NR; ++i) {
+            const int z = lo + lane + 32 * i;
+            const float x = z < hi ? __ldcs(row + z) : NAN;
+            m += (x == x);
+            v[i] = (x == x) ? x : INFINITY;                  // NaN samples and padding sort to the end
+        }
+        m = __reduce_add_sync(0xffffffffu, m);
+        lf_regsort<NR>(v, lane);
+        auto key = [&](int e) {                              // rank e lives in lane e / NR, register e % NR
+            float mine = 0.0f;
+#pragma unroll
+            for (int r = 0; r < NR; ++r) if (r == (e % NR)) mine = v[r];
+            return __shfl_sync(0xffffffffu, mine, e / NR);
+        };
+        float med = NAN;
+        if (m > 0) med = (float)(0.5 * ((double)key((m - 1) / 2) + (double)key(m / 2)));
+        if (lane == 0) out[s] = med;
+    }
+}
+
+extern "C" cudaError_t lf_run_rowmedian(const float* cube, long long n_rows, int nz, int lo, int hi, float* out, int sm_count,
+                                        cudaStream_t stream)
+{
+    if (n_rows <= 0) return cudaSuccess;
+    const int len = hi - lo;
+    if (len > 1024) return cudaErrorInvalidValue;
+    long long want = (n_rows + RED_WARPS - 1) / RED_WARPS;
+    long long cap = (long long)sm_count * 4;
+    const int grid = (int)(want < cap ? want : cap);
+    if (len <= 512) lf_rowmedian_kernel<16><<<grid, RED_WARPS * 32, 0, stream>>>(cube, n_rows, nz, lo, hi, out);
+    else lf_rowmedian_kernel<32><<<grid, RED_WARPS * 32, 0, stream>>>(cube, n_rows, nz, lo, hi, out);
+    return cudaGetLastError();
+}

@@ -321,6 +321,18 @@ def bin_cube(cube3d, binning, x_min, x_max, y_min, y_max):
     return out
 
 
+def row_median(cube2d, lo, hi):
+    """``lucifit_row_median``: float32 ``[n_rows]`` = ``np.nanmedian(cube2d[r, lo:hi])`` of every row."""
+    lib = _capi.lib()
+    require_cuda(cube2d, 'cube', torch.float32)
+    n, nz = int(cube2d.shape[0]), int(cube2d.shape[1])
+    out = torch.empty((n,), dtype=torch.float32, device=cube2d.device)
+    with torch.cuda.device(cube2d.device):
+        check(lib.lucifit_row_median(_ptr(cube2d), n, nz, int(lo), int(hi), _ptr(out), _stream()))
+    launch_counter['n'] += 1 if n > 0 else 0
+    return out
+
+
 def pack_maps(rows, want_be=False):
     """``lucifit_pack_maps``: ``rows [n, K]`` -> field-major ``maps [K, n]`` (float32) and, with ``want_be``, the same
     values byte-reversed (``[K, n]`` int32 holding big-endian floats: the data units of the FITS maps)."""

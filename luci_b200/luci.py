@@ -392,10 +392,10 @@ class Luci():
                 bkg_t = None
             ab = torch.from_numpy(np.ascontiguousarray(absorp, dtype=np.float32)).to(dev)
             cut = int(nz * 0.25)
-            mid = sky[:, cut:-cut]
-            # np.nanmedian averages the two middle values: quantile 0.5 with linear interpolation (chunked: size limit)
-            med = torch.cat([torch.nanquantile(mid[i:i + 16384], 0.5, dim=1) for i in range(0, mid.shape[0], 16384)])
-            cube2d = (sky - (ab / torch.nanquantile(ab, 0.5))[None, :] * med[:, None] + med[:, None]).contiguous()
+            sky = sky.contiguous()
+            med = engine.row_median(sky, cut, nz - cut)                 # np.nanmedian(sky[cut:-cut]) per spaxel
+            ab_med = float(np.nanmedian(np.asarray(absorp, dtype=np.float64)))      # (host input: one number)
+            cube2d = (sky - (ab / ab_med)[None, :] * med[:, None] + med[:, None]).contiguous()
             index = None
         if auto_prior:
             v0, b0 = engine.estimate_prior(cfg, cube2d, theta_t, index=index, bkg=bkg_t)

@@ -98,3 +98,22 @@ def test_large_reduction_is_size_independent():
     std = cube[:, 10:60].double().std(dim=1, unbiased=False).float()
     ref = (mx - mean) / std.sqrt() / cube.abs().mean(dim=1).sqrt()
     torch.testing.assert_close(snr1, ref, rtol=2e-5, atol=0)
+
+
+def test_row_median_equals_numpy_nanmedian():
+    """lucifit_row_median (the level of the absorption template, LuciBase.py:354-356) against np.nanmedian, odd and even
+    counts, NaN samples, all-NaN rows, both register-sort sizes."""
+    from luci_b200 import engine
+    dev = torch.device('cuda', 0)
+    rng = np.random.default_rng(4)
+    for nz, lo, hi in ((841, 210, 631), (841, 0, 841), (300, 7, 8), (2000, 500, 1500)):
+        cube = rng.normal(size=(257, nz)).astype(np.float32)
+        cube[rng.integers(0, 257, 300), rng.integers(0, nz, 300)] = np.nan
+        cube[5, :] = np.nan
+        got = engine.row_median(torch.from_numpy(cube).to(dev), lo, hi).cpu().numpy()
+        with np.errstate(all='ignore'):
+            import warnings
+            with warnings.catch_warnings():
+                warnings.simplefilter('ignore')
+                want = np.nanmedian(cube[:, lo:hi].astype(np.float64), axis=1).astype(np.float32)
+        np.testing.assert_array_equal(got, want)

@@ -74,8 +74,8 @@ static inline void lf_make_layout(int L, int P, int nz, int nfit, int ncont, int
     ly.lm_cw = (int)o; o += win;
     ly.lm_lines = (int)o; o += sizeof(LfLineX) * L;
     ly.lm_tie = (int)o; o = lf_align(o + sizeof(LfTieX), 16);
-    ly.lm_gt = (int)o; o = lf_align(o + sizeof(float) * L * lanes, 16);
-    ly.lm_hb = (int)o; o = lf_align(o + sizeof(float) * (2 * NA + (size_t)P * P + 3 * P), 16);   // + secant term S[P][P] and three [P] vectors
+    ly.lm_gt = (int)o; o = lf_align(o + sizeof(float) * 2 * L * lanes, 16);                   // unit profiles + their (v, beta) partials as bf16 pairs
+    ly.lm_hb = (int)o; o = lf_align(o + sizeof(float) * (2 * (NA + 2 * (size_t)L) + (size_t)P * P + 3 * P), 16);   // [2][NA + 2 L] + secant term S[P][P] and three [P] vectors
     ly.lm_thb = (int)o; o = lf_align(o + sizeof(float) * 4 * P, 16);
     ly.lm_bytes = (int)o;
     // unc: variants[13 L] (later: hess) | apd[3 L] | gt[(13 + 5 L)][lanes] | tile[lanes][PF|1]   (no staged window:
@@ -144,7 +144,10 @@ static inline std::string lf_make_plan(const lucifit_config* c, LfPlan& pl, int 
     }
     d.refine_prior = c->no_prior_refine ? 0 : 1;
     d.max_iter = c->max_iter > 0 ? c->max_iter : 60;
-    d.ftol = c->ftol > 0 ? (float)c->ftol : 1e-8f;
+#ifndef LF_DEFAULT_FTOL
+#define LF_DEFAULT_FTOL 1e-8f
+#endif
+    d.ftol = c->ftol > 0 ? (float)c->ftol : LF_DEFAULT_FTOL;
     d.n_out = 7 * L + 5;
     pl.axis.assign(c->axis, c->axis + c->nz);
     for (int i = 1; i < c->nz; ++i)

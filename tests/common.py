@@ -242,21 +242,52 @@ def assert_fixture_parity(name, rows, status, g):
     return rep, opt, direct
 
 
+def oracle_uncertainties_at(g, i, full_norm):
+    """The reference's 1-sigma errors (LuciFit.py:713-722: delta = 0.1 four-point Hessian of its nll, sqrt|diag(-inv(H/2))|)
+    evaluated in float64 at a GIVEN normalised solution ``[A, p, sigma]*L + [c]`` of spaxel ``i`` -- what the device
+    computes in FP32 at the device's own solution."""
+    from oracle import luci_oracle as O
+    from oracle import tight as T
+    prob = T.problem_from_golden(g, i)
+    f = prob.f
+    nll = lambda th: -f.log_likelihood(th)
+    H = 0.5 * O.hessian_stencil(nll, np.asarray(full_norm, float))
+    try:
+        cov = -np.linalg.inv(H)
+    except np.linalg.LinAlgError:
+        cov = -np.linalg.pinv(H)
+    return np.sqrt(np.abs(np.diagonal(cov)))
+
+
 def assert_uncertainty_parity(name, rows, unc, g, sel):
     """1-sigma errors against the reference's (hessianComp, LuciUtility.py:409-434) on every spaxel of ``sel`` (where the
-    two fits share the optimum).  The reference's delta = 0.1 finite-difference Hessian is indefinite for some weak
-    lines (an eigenvalue of -0.2 next to 4e4 in unc_sincgauss_cfg2[11]); there its inverse amplifies the 1e-4
-    difference between two converged solutions to a few per cent -- in float64 just as on the device -- hence the
-    separate bounds on the bulk and on the worst entry."""
+    two fits share the optimum): median < 1e-4, 90th percentile < 1.5e-3.  The reference's delta = 0.1 finite-difference
+    Hessian is indefinite for some weak lines (an eigenvalue of -0.2 next to 4e4 in unc_sincgauss_cfg2[11]); there its
+    inverse amplifies the 1e-4 difference between two converged solutions to 5-20 % -- in float64 just as on the device.
+    So every spaxel whose errors differ from the reference's by more than 5 % must be EXPLAINED: the same stencil evaluated
+    in float64 at OUR solution (``oracle_uncertainties_at``) has to reproduce the device's FP32 numbers to 5 %, and such
+    spaxels may be at most 5 % of the sample."""
     q = split_rows(rows, len(g['lines']))
     rels = []
     for key in ('vels_errors', 'sigmas_errors', 'flux_errors', 'continuum_error'):
         ref, mine = g['ref_' + key][sel], q[key][sel]
         rel = (np.abs(mine - ref) / np.abs(ref)).ravel()
         rel = rel[np.isfinite(rel)]
-        assert np.median(rel) < 1e-4 and np.percentile(rel, 90) < 1.5e-3 and rel.max() < 0.1, (name, key, np.sort(rel)[-5:])
+        assert np.median(rel) < 1e-4 and np.percentile(rel, 90) < 1.5e-3 and rel.max() < 0.5, (name, key, np.sort(rel)[-5:])
         rels.append(rel)
     u, ur = unc[sel], g['ref_fit_unc'][sel]
     rel = np.abs(u - ur) / np.abs(ur)
-    assert np.median(rel) < 1e-4 and rel.max() < 0.1, (name, rel.max())
+    assert np.median(rel) < 1e-4 and rel.max() < 0.5, (name, rel.max())
+    idx = np.flatnonzero(sel)
+    amplified = [int(idx[r]) for r in np.flatnonzero((rel > 0.05).any(axis=1))]
+    assert len(amplified) <= max(1, int(0.05 * len(idx))), (name, amplified)
+    for i in amplified:
+        scale = float(g['ref_scale'][i])
+        full = rows_to_solution(q, g, i, scale)
+        want = oracle_uncertainties_at(g, i, full)
+        got = np.array(unc[i], float).copy()
+        got[0:-1:3] /= scale                       # amplitudes and continuum back to normalised units
+        got[-1] /= scale
+        dev = np.abs(got - want) / np.abs(want)
+        assert dev.max() < 5e-2, (name, i, dev.max())
     return np.concatenate(rels)

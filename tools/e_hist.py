@@ -20,7 +20,8 @@ cfg = FitConfig('sincgauss', SN3_LINES, [1] * 5, [1] * 5, sc.axis32, 'SN3', sc.d
 st = engine.fit_batch(cfg, cube, theta, v0, b0)['status'].cpu().numpy()
 ev, it = (st >> 8) & 0xff, st & 0xff
 snr = sc.snr.reshape(-1)
-print('mean E %.3f  mean it %.3f' % (ev.mean(), it.mean()))
+print('mean E %.3f  mean it %.3f  singular %.4f  bound %.4f  converged %.4f' % (ev.mean(), it.mean(), ((st >> 19) & 1).mean(), ((st >> 18) & 1).mean(), ((st >> 16) & 1).mean()))
+print('evals - iters histogram', np.bincount(np.clip(ev.astype(int) - it.astype(int), 0, 9)) / len(ev))
 print('E histogram', np.bincount(ev)[:16] / len(ev))
 for lo, hi in ((10, 21.5), (21.5, 46.4), (46.4, 100)):
     m = (snr >= lo) & (snr < hi)

@@ -1381,6 +1381,12 @@ LF_CORE void lf_stage_lm(const LfCfg& cfg, const LfWarp<LANES>& w, const float* 
                     w.sync();
                     sec_have = false;
                 } else if (finite && (double)pred <= LF_TUNE_REJ_CONV * chi2) { done = true; flags |= LF_ST_CONVERGED; }
+                if (D::CROSS && cross_on && !done) {
+                    // the rejected proposal came from the matrix with the exact cross term: this point goes on with plain
+                    // Gauss-Newton (the term only stays where it helps)
+                    lf_cross_apply<MODEL, L, NV, NS, LANES>(w, hcur, 1.0f);
+                    cross_on = false; cross_off = true;
+                }
             }
         }
         if (PHASE == 2 && learn) { lf_secant_update<P, LANES>(w, hcur, htri, th, tht, Ssec); sec_have = true; }
@@ -1439,6 +1445,21 @@ LF_CORE void lf_stage_lm(const LfCfg& cfg, const LfWarp<LANES>& w, const float* 
                 continue;
             }
             if (!ok) { lam *= 10.0f; flags |= LF_ST_SINGULAR; ++tries; continue; }
+            if (D::CROSS && cross_on) {
+                // a step of the cross-corrected model that runs a free parameter into its box (a broadening to 0, an amplitude
+                // to its floor) is where the few bad basins of that model lie: this point goes on with plain Gauss-Newton
+                bool clipped = false;
+#pragma unroll
+                for (int t = 0; t < PL; ++t) {
+                    const int j = t * LANES + w.lane;
+                    if (j < P && !((fixedmask >> j) & 1u)) { const float v = th[j] + delta[t]; clipped |= v < lo[j] || v > hi[j]; }
+                }
+                if (w.any(clipped)) {
+                    lf_cross_apply<MODEL, L, NV, NS, LANES>(w, hcur, 1.0f);
+                    cross_on = false; cross_off = true;
+                    continue;
+                }
+            }
             float rel = 0.0f;
             w.sync();
 #pragma unroll

@@ -11,7 +11,8 @@ from luci_b200.sim import SN3_LINES, SyntheticCube           # noqa: E402
 
 dev = torch.device('cuda', 0)
 model = sys.argv[1] if len(sys.argv) > 1 else 'sincgauss'
-sc = SyntheticCube(32, 2064, n_steps=841, model=model)
+nx = int(sys.argv[2]) if len(sys.argv) > 2 else 32
+sc = SyntheticCube(nx, 2064, n_steps=841, model=model)
 cube = sc.synthesize(dev).view(-1, 841)
 v0m, b0m = sc.priors()
 t = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(dev)
@@ -35,4 +36,4 @@ both = torch.cat([ra, rb])
 same = (both == r0) | (torch.isnan(both) & torch.isnan(r0))
 print('two halves: rows differing', int((~same).any(dim=1).sum()))
 vt = torch.from_numpy(sc.vel_fit_truth.reshape(-1)).to(dev)
-print('|v - truth| > 60 km/s:', int(((r0[:, 15] - vt).abs() > 60).sum()), 'of', r0.shape[0])
+print('|v - truth| > 60 km/s:', int(((r0[:, 15] - vt).abs() > 60).sum()), 'of', r0.shape[0], ' broadening at 0:', int((r0[:, 25] <= 0).sum()), ' max evals', int(((s0 >> 8) & 0xff).max()), ' singular', int(((s0 >> 19) & 1).sum()))

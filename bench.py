@@ -303,7 +303,9 @@ def main():
     mean_E = sum_evals / max(n_fit_total, 1)
     nfit = cfg.c.fit_hi - cfg.c.fit_lo
     L, P_red = 5, 7                                                # 4 free amplitudes + v + beta + continuum
-    W = mean_E * nfit * (L * F_MODEL[model] + P_red * (P_red + 3)) + mean_E * P_red ** 3 / 3.0      # lf_lm_kernel only
+    # lf_lm_kernel only: per evaluation and sample L profiles with partials (F), J^T J / J^T r of the reduced system, and the two
+    # FMAs per line of the exact (amplitude, velocity / broadening) Hessian term; per evaluation one Cholesky solve
+    W = mean_E * nfit * (L * (F_MODEL[model] + 4) + P_red * (P_red + 3)) + mean_E * P_red ** 3 / 3.0
     # the dominant kernel (lf_lm_kernel) timed alone: the same pipeline stage by stage with CUDA events around every
     # launch on the launching stream (engine.fit_batch(time_stages=True) -> lucifit_fit_stages)
     barrier()

@@ -629,8 +629,9 @@ class Luci():
                 mask[pair] = True
             return mask
         if isinstance(region, str):
-            if '.reg' in region:
-                raise NotImplementedError('ds9 .reg regions need pyregion (out of scope): pass a boolean mask or .npy')
+            if '.reg' in region:                        # LuciConvenience.reg_to_mask :49-57 (pyregion restated, regions.py)
+                from .regions import reg_to_mask
+                return reg_to_mask(region, self.header, self.cube_final.shape)
             if '.npy' in region:
                 return np.load(region)
             raise ValueError('Mask was incorrectly passed. Please use either a .reg file or a .npy file or a numpy ndarray')

@@ -338,6 +338,36 @@ def test_extract_spectrum_and_region(world):
     np.testing.assert_allclose(specr, host[1:4, 2:9].sum(axis=(0, 1)) / 21, rtol=1e-12)
 
 
+def test_ds9_region_files_through_the_api(world, tmp_path):
+    """``region='x.reg'`` (LuciBase.py:622-624, 917-919, 985-987 -> LuciConvenience.reg_to_mask): the ds9 file gives the
+    same spectrum / maps as the boolean mask it describes, in pixel and in sky coordinates (the fixture's WCS is one
+    degree per pixel around CRPIX (6, 5) = (10 deg, 20 deg))."""
+    from luci_b200.regions import reg_to_mask
+    luci, sc, out = world
+    host = luci.cube_final.cpu().numpy().astype(np.float64)
+    reg = tmp_path / 'r.reg'
+    reg.write_text('# Region file format: DS9 version 4.1\nphysical\ncircle(6.2,5.1,2.6)\n')
+    want = (np.arange(12)[:, None] - 5.2) ** 2 + (np.arange(10)[None, :] - 4.1) ** 2 <= 2.6 ** 2
+    _, spec = luci.extract_spectrum_region(str(reg), mean=True)
+    np.testing.assert_allclose(spec, host[want].sum(axis=0) / want.sum(), rtol=1e-12)
+    v0, b0 = sc.priors()
+    vel, broad, flux, chi2, m = luci.fit_region(SN3, 'sincgauss', [1] * 5, [1] * 5, str(reg), prior_values=(v0, b0))
+    assert (m == want).all()
+    velm, broadm, fluxm, chi2m, _ = luci.fit_region(SN3, 'sincgauss', [1] * 5, [1] * 5, want, prior_values=(v0, b0))
+    np.testing.assert_array_equal(vel, velm)
+    np.testing.assert_array_equal(chi2, chi2m)
+    assert (chi2[want.T] > 0).all() and (chi2[~want.T] == 0).all()
+    # the same circle in sky coordinates: centre = pixel (6.2, 5.1) of the TAN header, radius in degrees
+    from luci_b200.regions import TanWCS
+    lon, lat = TanWCS(luci.header).pix2world(6.2, 5.1)
+    reg.write_text('fk5\ncircle(%.10f,%.10f,2.6)\n' % (lon, lat))
+    sky = reg_to_mask(str(reg), luci.header, luci.cube_final.shape)
+    assert (sky ^ want).sum() <= 1                          # one-degree pixels: the local scale is not exactly CDELT
+    axis, sky_spec, d = luci.fit_spectrum_region(SN3, 'sincgauss', [1] * 5, [1] * 5, str(reg), prior_values=(float(v0.T[sky].mean()), float(b0.T[sky].mean())))
+    np.testing.assert_allclose(sky_spec, host[sky].sum(axis=0), rtol=1e-12)
+    assert d['chi2'] > 0
+
+
 @pytest.mark.parametrize('filt,lines', [('SN2', ['Hbeta', 'OIII4959', 'OIII5007']), ('SN1', ['OII3726', 'OII3729'])])
 def test_config3_sn1_sn2_gaussian_binning2(tmp_path, filt, lines):
     """BASELINE config 3: SN1 / SN2 cubes, gaussian model, binning=2 -- through fit_entire_cube with the CNN-like priors

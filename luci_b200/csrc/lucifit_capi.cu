@@ -1,12 +1,29 @@
 // lucifit_capi.cu -- the extern "C" entry points of include/lucifit.h.
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
+#include <mutex>
 #include <string>
+#include <utility>
+#include <vector>
 
 #include "lucifit_host.hpp"
 #include "lucifit_fit_kernel.cuh"
 #include "lucifit_prior.cuh"
+
+// Address ranges mapped by lucifit_peer_open (base, bytes): lucifit_fit_stages asks whether its out_rows lies in one.
+static std::mutex lf_peer_mu;
+static std::vector<std::pair<uintptr_t, size_t> > lf_peer_ranges;
+static bool lf_peer_mapped(const void* p)
+{
+    std::lock_guard<std::mutex> g(lf_peer_mu);
+    const uintptr_t a = (uintptr_t)p;
+    for (size_t i = 0; i < lf_peer_ranges.size(); ++i)
+        if (a >= lf_peer_ranges[i].first && a - lf_peer_ranges[i].first < lf_peer_ranges[i].second) return true;
+    return false;
+}
 
 static thread_local std::string g_err;
 static int fail(int code, const std::string& msg) { g_err = msg; return code; }
@@ -162,6 +179,11 @@ int lucifit_fit_stages(const lucifit_config* cfg, int stages, int64_t n_spaxel, 
     a.unc_ws = pl.dev.uncertainty ? (double*)(ws + pl.table_bytes + lf_align(slice * sizeof(float) * pl.dev.state_floats, 16)) : nullptr;
     int rc = sm_count_of_current_device(&a.sm_count);
     if (rc) return rc;
+    // rows that land in another process's / GPU's memory (a range this library mapped in lucifit_peer_open) leave the output
+    // kernel as whole coalesced stores (cudaPointerGetAttributes cannot tell: it reports an IPC mapping as local memory)
+    a.stage_rows = lf_peer_mapped(out_rows) ? 1 : 0;
+    if (const char* ev = getenv("LUCIFIT_STAGE_ROWS")) a.stage_rows = atoi(ev) != 0;          // measurement override
+    if (getenv("LUCIFIT_DEBUG")) fprintf(stderr, "lucifit: fit_stages n=%lld stage_rows=%d\n", (long long)n_spaxel, a.stage_rows);
     const size_t smem_max = (size_t)a.xo_bytes + (size_t)LF_PREP_WARPS * pl.ly.prep_bytes;
     if (smem_max > 200 * 1024) return fail(LUCIFIT_EINVAL, "spectrum too long for the shared-memory layout (nz * 8 warps > 200 KB)");
     const int K = 7 * pl.L + 5, PF = 3 * pl.L + 1;
@@ -353,12 +375,25 @@ int lucifit_peer_open(const void* handle, uint64_t offset, void** dev_ptr)
     cudaError_t e = cudaIpcOpenMemHandle(&base, h, cudaIpcMemLazyEnablePeerAccess);
     if (e != cudaSuccess) return cuda_fail(e, "cudaIpcOpenMemHandle");
     *dev_ptr = (char*)base + offset;
+    {
+        unsigned long long rb = 0; size_t size = 0;
+        lf_cuMemGetAddressRange_t range = lf_get_address_range_fn();
+        if (!range || range(&rb, &size, (unsigned long long)(uintptr_t)base) != 0) { rb = (unsigned long long)(uintptr_t)base; size = (size_t)1 << 46; }
+        std::lock_guard<std::mutex> g(lf_peer_mu);
+        lf_peer_ranges.push_back(std::make_pair((uintptr_t)rb, size));
+    }
     return 0;
 }
 
 int lucifit_peer_close(void* dev_ptr, uint64_t offset)
 {
     if (!dev_ptr) return 0;
+    {
+        std::lock_guard<std::mutex> g(lf_peer_mu);
+        const uintptr_t b = (uintptr_t)((char*)dev_ptr - offset);
+        for (size_t i = 0; i < lf_peer_ranges.size(); ++i)
+            if (lf_peer_ranges[i].first == b) { lf_peer_ranges.erase(lf_peer_ranges.begin() + i); break; }
+    }
     cudaError_t e = cudaIpcCloseMemHandle((char*)dev_ptr - offset);
     if (e != cudaSuccess) return cuda_fail(e, "cudaIpcCloseMemHandle");
     return 0;

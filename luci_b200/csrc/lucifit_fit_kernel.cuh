@@ -56,6 +56,7 @@ struct LfLaunch {
     int xo_bytes;
     cudaStream_t stream;
     int sm_count;
+    int stage_rows;              // out_rows is peer-mapped memory of another GPU: rows leave as whole coalesced stores
 };
 typedef cudaError_t (*lf_launch_fn)(const LfLaunch&, int stages);
 
@@ -152,7 +153,7 @@ lf_out_kernel(const __grid_constant__ LfLaunch a)
                                            a.state + s * (long long)a.cfg.state_floats,
                                            a.unc_ws ? a.unc_ws + s * PF : nullptr, a.out_rows + s * K, a.status + s,
                                            a.out_sol ? a.out_sol + s * PF : nullptr,
-                                           a.out_unc ? a.out_unc + s * PF : nullptr);
+                                           a.out_unc ? a.out_unc + s * PF : nullptr, a.stage_rows != 0);
     }
 }
 

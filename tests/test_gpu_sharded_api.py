@@ -26,9 +26,12 @@ def test_sharded_maps_equal_single_process_maps(tmp_path):
     worker = os.path.join(ROOT, 'tests', 'sharded_worker.py')
     env = dict(os.environ, PYTHONPATH=ROOT)
     subprocess.run([sys.executable, worker, str(tmp_path), '0'], check=True, env=env, timeout=600)
-    subprocess.run([sys.executable, '-m', 'torch.distributed.run', '--nnodes=1', '--nproc-per-node', '2',
-                    '--master-addr', '127.0.0.1', '--master-port', str(_free_port()), worker, str(tmp_path), '1'],
-                   check=True, env=env, timeout=900)
+    # (rows that go to a range mapped by lucifit_peer_open leave the output kernel through its staged, coalesced store path:
+    # this comparison is also the bit-for-bit check of that path against the direct stores of the single-process run)
+    run = subprocess.run([sys.executable, '-m', 'torch.distributed.run', '--nnodes=1', '--nproc-per-node', '2',
+                          '--master-addr', '127.0.0.1', '--master-port', str(_free_port()), worker, str(tmp_path), '1'],
+                         check=True, env=dict(env, LUCIFIT_DEBUG='1'), timeout=900, stderr=subprocess.PIPE, text=True)
+    assert 'stage_rows=1' in run.stderr and 'stage_rows=0' in run.stderr, run.stderr[-2000:]   # rank 1 staged, rank 0 direct
     one = np.load(os.path.join(tmp_path, 'maps_single_rank0.npz'))
     two = np.load(os.path.join(tmp_path, 'maps_sharded_rank0.npz'))
     assert bool(two['cube_peer']), 'rows were not written through peer memory'

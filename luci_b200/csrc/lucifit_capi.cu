@@ -184,8 +184,8 @@ int lucifit_fit_stages(const lucifit_config* cfg, int stages, int64_t n_spaxel, 
     a.stage_rows = lf_peer_mapped(out_rows) ? 1 : 0;
     if (const char* ev = getenv("LUCIFIT_STAGE_ROWS")) a.stage_rows = atoi(ev) != 0;          // measurement override
     if (getenv("LUCIFIT_DEBUG")) fprintf(stderr, "lucifit: fit_stages n=%lld stage_rows=%d\n", (long long)n_spaxel, a.stage_rows);
-    const size_t smem_max = (size_t)a.xo_bytes + (size_t)LF_PREP_WARPS * pl.ly.prep_bytes;
-    if (smem_max > 200 * 1024) return fail(LUCIFIT_EINVAL, "spectrum too long for the shared-memory layout (nz * 8 warps > 200 KB)");
+    const size_t smem_max = (size_t)a.xo_bytes + (size_t)8 * pl.ly.prep_bytes;          // the smallest CTA lf_pick_warps falls back to
+    if (smem_max > LF_SMEM_BUDGET) return fail(LUCIFIT_EINVAL, "spectrum too long for the shared-memory layout (nz * 8 warps > 200 KB)");
     const int K = 7 * pl.L + 5, PF = 3 * pl.L + 1;
     for (int64_t s0 = 0; s0 < n_spaxel; s0 += (int64_t)slice) {
         const int64_t ns = n_spaxel - s0 < (int64_t)slice ? n_spaxel - s0 : (int64_t)slice;

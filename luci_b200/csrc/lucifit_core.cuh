@@ -1574,10 +1574,10 @@ LF_CORE void lf_expand(const LfCfg& cfg, const LfWarp<LANES>& w, float sinc_w, c
 // (LuciBase.py:381-392, 406):
 //   [0,L) amplitudes | [L,2L) fluxes | [2L,3L) flux errors | [3L,4L) velocities | [4L,5L) velocity errors |
 //   [5L,6L) broadenings | [6L,7L) broadening errors | chi2 | corr | axis_step | continuum | continuum error
-template <int MODEL, int L, int NV, int NS, int LANES>
+template <int MODEL, int L, int NV, int NS, int LANES, bool STAGE_ROW = false>
 LF_CORE void lf_stage_out(const LfCfg& cfg, const LfWarp<LANES>& w, const float* xo, const float* gspec, const LfWork& wk,
                           const float* state, const double* unc /* [3L+1] normalised or null */,
-                          float* out_row, int32_t* out_status, float* out_sol, float* out_unc, bool stage_row = false)
+                          float* out_row, int32_t* out_status, float* out_sol, float* out_unc)
 {
     typedef LfDims<MODEL, L, NV, NS> D;
     const int status = reinterpret_cast<const int*>(state)[LF_SO_STATUS];
@@ -1662,13 +1662,12 @@ LF_CORE void lf_stage_out(const LfCfg& cfg, const LfWarp<LANES>& w, const float*
     S = w.sum(S);
     nvalid = w.sum(nvalid);
     const double chi2 = S / (noise * (double)(nvalid - (3 * L + 1)));
-    // stage_row (rows that land in another GPU's memory through a peer mapping, see lucifit_fit_stages): the row is assembled
+    // STAGE_ROW (rows that land in another GPU's memory through a peer mapping, see lucifit_fit_stages): the row is assembled
     // in the warp's scratch (the window is dead by now; yw | sw | cw hold >= 9L+6 floats) and leaves as whole 128-byte
     // stores of consecutive lanes -- 2 NVLink writes per row instead of 12 scattered 4..20-byte ones.  Into local memory
-    // the direct stores are faster (L2 merges them; the detour costs the output kernel 9 %).
-    w.sync();
+    // the direct stores are faster (L2 merges them), so that instance of the kernel is left exactly as it was.
     float* const dst_row = out_row;
-    if (stage_row) out_row = wk.yw;
+    if (STAGE_ROW) { w.sync(); out_row = wk.yw; }
     const double FWHM_COEFF = 2.3548200450309493;
     const double SQ2PI = 2.5066282746310002, PI = 3.141592653589793;
     for (int k = w.lane; k < L; k += LANES) {
@@ -1718,7 +1717,7 @@ LF_CORE void lf_stage_out(const LfCfg& cfg, const LfWarp<LANES>& w, const float*
         if (out_sol) out_sol[3 * L] = (float)(cont * scale);
         *out_status = status & ~LF_ST_CUT_MASK;
     }
-    if (stage_row) {
+    if (STAGE_ROW) {
         w.sync();
         for (int j = w.lane; j < 7 * L + 5; j += LANES) dst_row[j] = out_row[j];
     }

@@ -7,10 +7,10 @@
 
 // Warps per CTA.  Measured on the benchmark cube (B200, 1 M spaxels): consecutive spaxels go to consecutive warps of a
 // CTA, and larger CTAs keep neighbouring spaxels (neighbouring DRAM pages) on one SM -- the LM kernel runs 57.1 / 54.7 /
-// 52.5 ms with 4 / 8 / 16 warps per CTA at the same 16 resident warps per SM, the prep kernel 3.71 -> 3.32 ms from 8 to
-// 16, the output kernel is best at 8.
+// 52.5 ms with 4 / 8 / 16 warps per CTA at the same 16 resident warps per SM, the prep kernel 3.71 / 3.48 / 3.42 ms with
+// 8 / 16 / 32, the output kernel 6.42 / 5.84 / 5.40 ms (with the 80 registers it used to get, 8 was its best size).
 #ifndef LF_PREP_WARPS
-#define LF_PREP_WARPS 16
+#define LF_PREP_WARPS 32
 #endif
 #ifndef LF_PREP_LOCKSTEP
 #define LF_PREP_LOCKSTEP 1
@@ -34,8 +34,15 @@ template <int NA> struct LfLmBlocks {
 #endif
 template <int L> struct LfUncWarps { enum { W = L <= 6 ? LF_UNC_WARPS : (LF_UNC_WARPS < 12 ? LF_UNC_WARPS : 12) }; };
 #ifndef LF_OUT_WARPS
-#define LF_OUT_WARPS 8
+#define LF_OUT_WARPS 32
 #endif
+// The prep and output kernels take their CTA size at launch (lf_pick_warps): consecutive spaxels go to consecutive warps, so
+// a larger CTA keeps neighbouring spectra (neighbouring DRAM pages, one copy of the xo table) on one SM -- the output kernel
+// takes 6.42 / 5.84 / 5.40 ms per 2^20 spaxels with 8 / 16 / 32 warps per CTA at the same 64-register budget.  LF_*_WARPS
+// is the largest size tried; long spectra fall back to 16 or 8 warps to stay inside the shared memory of an SM.
+// (64 registers either way: 32 resident warps per SM)
+#define LF_PREP_BOUNDS __launch_bounds__(LF_PREP_WARPS * 32, 32 / LF_PREP_WARPS)
+#define LF_OUT_BOUNDS __launch_bounds__(LF_OUT_WARPS * 32, 32 / LF_OUT_WARPS)
 
 struct LfLaunch {
     LfCfg cfg;
@@ -70,19 +77,20 @@ __device__ __forceinline__ const float* lf_stage_xo(const LfLaunch& a, unsigned 
 }
 
 template <int MODEL, int L, int NG>
-__global__ void __launch_bounds__(LF_PREP_WARPS * 32)
+__global__ void LF_PREP_BOUNDS
 lf_prep_kernel(const __grid_constant__ LfLaunch a)
 {
     extern __shared__ __align__(16) unsigned char lf_smem[];
     const int warp = threadIdx.x >> 5;
     LfWork wk = lf_work_at(LF_STAGE_PREP, a.ly, lf_smem + (size_t)warp * a.ly.prep_bytes);
     LfWarp<32> w;
-    const long long stride = (long long)gridDim.x * LF_PREP_WARPS;
+    const int nwarps = blockDim.x >> 5;
+    const long long stride = (long long)gridDim.x * nwarps;
     // The stage is ~60 KB of straight-line code walked once per spaxel, with near-identical work for every spaxel: the
     // warps of a CTA start each spaxel together (one CTA barrier per round, uniform trip count) so that they fetch the
     // same instructions at about the same time instead of thrashing the instruction cache (ncu: 1.9 `no_instruction`
     // stall cycles per issued instruction without the barrier).
-    for (long long s0 = (long long)blockIdx.x * LF_PREP_WARPS; s0 < a.n; s0 += stride) {
+    for (long long s0 = (long long)blockIdx.x * nwarps; s0 < a.n; s0 += stride) {
 #if LF_PREP_LOCKSTEP
         __syncthreads();
 #endif
@@ -136,8 +144,8 @@ lf_unc_kernel(const __grid_constant__ LfLaunch a)
     }
 }
 
-template <int MODEL, int L, int NG>
-__global__ void __launch_bounds__(LF_OUT_WARPS * 32)
+template <int MODEL, int L, int NG, bool STAGE_ROW>
+__global__ void LF_OUT_BOUNDS
 lf_out_kernel(const __grid_constant__ LfLaunch a)
 {
     extern __shared__ __align__(16) unsigned char lf_smem[];
@@ -146,14 +154,15 @@ lf_out_kernel(const __grid_constant__ LfLaunch a)
     LfWork wk = lf_work_at(LF_STAGE_OUT, a.ly, lf_smem + a.xo_bytes + (size_t)warp * a.ly.out_bytes);
     LfWarp<32> w;
     constexpr int K = 7 * L + 5, PF = 3 * L + 1;
-    const long long stride = (long long)gridDim.x * LF_OUT_WARPS;
-    for (long long s = (long long)blockIdx.x * LF_OUT_WARPS + warp; s < a.n; s += stride) {
+    const int nwarps = blockDim.x >> 5;
+    const long long stride = (long long)gridDim.x * nwarps;
+    for (long long s = (long long)blockIdx.x * nwarps + warp; s < a.n; s += stride) {
         const long long row = a.index ? a.index[s] : a.index_base + s;
-        lf_stage_out<MODEL, L, NG, NG, 32>(a.cfg, w, xo_s, a.cube + row * (long long)a.cfg.nz, wk,
+        lf_stage_out<MODEL, L, NG, NG, 32, STAGE_ROW>(a.cfg, w, xo_s, a.cube + row * (long long)a.cfg.nz, wk,
                                            a.state + s * (long long)a.cfg.state_floats,
                                            a.unc_ws ? a.unc_ws + s * PF : nullptr, a.out_rows + s * K, a.status + s,
                                            a.out_sol ? a.out_sol + s * PF : nullptr,
-                                           a.out_unc ? a.out_unc + s * PF : nullptr, a.stage_rows != 0);
+                                           a.out_unc ? a.out_unc + s * PF : nullptr);
     }
 }
 
@@ -174,13 +183,23 @@ static cudaError_t lf_launch_one(K kern, const LfLaunch& a, int warps, size_t sm
     return cudaGetLastError();
 }
 
+// Largest CTA (in warps) of {max_warps, 16, 8} whose dynamic shared memory stays within LF_SMEM_BUDGET.
+#define LF_SMEM_BUDGET (200 * 1024)
+static inline int lf_pick_warps(int max_warps, size_t fixed_bytes, size_t bytes_per_warp)
+{
+    int w = max_warps;
+    while (w > 8 && fixed_bytes + (size_t)w * bytes_per_warp > (size_t)LF_SMEM_BUDGET) w >>= 1;
+    return w;
+}
+
 // Enqueues the requested stages (bit 0 prep, 1 lm, 2 unc, 3 out) for one slice, in pipeline order.
 template <int MODEL, int L, int NG>
 cudaError_t lf_launch(const LfLaunch& a, int stages)
 {
     cudaError_t e = cudaSuccess;
     if (stages & 1) {
-        e = lf_launch_one(lf_prep_kernel<MODEL, L, NG>, a, LF_PREP_WARPS, (size_t)LF_PREP_WARPS * a.ly.prep_bytes);
+        const int pw = lf_pick_warps(LF_PREP_WARPS, 0, (size_t)a.ly.prep_bytes);
+        e = lf_launch_one(lf_prep_kernel<MODEL, L, NG>, a, pw, (size_t)pw * a.ly.prep_bytes);
         if (e != cudaSuccess) return e;
     }
     if (stages & 2) {
@@ -196,7 +215,11 @@ cudaError_t lf_launch(const LfLaunch& a, int stages)
         e = lf_launch_one(lf_unc_kernel<MODEL, L, NG>, a, LfUncWarps<L>::W, (size_t)a.xo_bytes + (size_t)LfUncWarps<L>::W * a.ly.un_bytes);
         if (e != cudaSuccess) return e;
     }
-    if (stages & 8)
-        e = lf_launch_one(lf_out_kernel<MODEL, L, NG>, a, LF_OUT_WARPS, (size_t)a.xo_bytes + (size_t)LF_OUT_WARPS * a.ly.out_bytes);
+    if (stages & 8) {
+        const int ow = lf_pick_warps(LF_OUT_WARPS, (size_t)a.xo_bytes, (size_t)a.ly.out_bytes);
+        const size_t smem = (size_t)a.xo_bytes + (size_t)ow * a.ly.out_bytes;
+        e = a.stage_rows ? lf_launch_one(lf_out_kernel<MODEL, L, NG, true>, a, ow, smem)
+                         : lf_launch_one(lf_out_kernel<MODEL, L, NG, false>, a, ow, smem);
+    }
     return e;
 }

@@ -29,10 +29,13 @@ template <int NA> struct LfLmBlocks {
 // The uncertainty kernel is bound by its per-warp shared memory (13 L variant records, the variant / sum tiles):
 // one CTA per SM with as many warps as fit 227 KB -- 16 up to 6 lines, 12 beyond (96.2 / 91.9 / 89.6 / 91.3 ms per 2^20
 // spaxels with 4 / 8 / 16 / 18 warps per CTA for the 5-line sincgauss).
+// The uncertainty kernel: one CTA per SM as well; 20 warps at 96 registers (76 bytes of spills) beat 16 at 128 -- 31.6 against
+// 34.4 ms per 2^19 spaxels -- where 20 warps' scratch (11.2 KB each at L = 5) still fits the SM; the launcher steps down to
+// 16 / 12 / 8 warps when it does not (lf_unc_warps_for).
 #ifndef LF_UNC_WARPS
-#define LF_UNC_WARPS 16
+#define LF_UNC_WARPS 20
 #endif
-template <int L> struct LfUncWarps { enum { W = L <= 6 ? LF_UNC_WARPS : (LF_UNC_WARPS < 12 ? LF_UNC_WARPS : 12) }; };
+template <int L> struct LfUncWarps { enum { W = L <= 5 ? LF_UNC_WARPS : (L <= 6 ? (LF_UNC_WARPS < 16 ? LF_UNC_WARPS : 16) : (LF_UNC_WARPS < 12 ? LF_UNC_WARPS : 12)) }; };
 #ifndef LF_OUT_WARPS
 #define LF_OUT_WARPS 32
 #endif
@@ -131,7 +134,7 @@ __global__ void __launch_bounds__(LfUncWarps<L>::W * 32, 1)
 lf_unc_kernel(const __grid_constant__ LfLaunch a)
 {
     extern __shared__ __align__(16) unsigned char lf_smem[];
-    constexpr int WARPS = LfUncWarps<L>::W;
+    const int WARPS = blockDim.x >> 5;
     const float* xo_s = lf_stage_xo(a, lf_smem);
     const int warp = threadIdx.x >> 5;
     LfWork wk = lf_work_at(LF_STAGE_UNC, a.ly, lf_smem + a.xo_bytes + (size_t)warp * a.ly.un_bytes);
@@ -192,6 +195,15 @@ static inline int lf_pick_warps(int max_warps, size_t fixed_bytes, size_t bytes_
     return w;
 }
 
+// The uncertainty kernel's CTA: max_warps, else 16 / 12 / 8, whichever first fits the 227 KB of dynamic shared memory.
+static inline int lf_unc_warps_for(int max_warps, size_t fixed_bytes, size_t bytes_per_warp)
+{
+    const int cand[4] = {max_warps, 16, 12, 8};
+    for (int i = 0; i < 4; ++i)
+        if (cand[i] <= max_warps && fixed_bytes + (size_t)cand[i] * bytes_per_warp <= (size_t)227 * 1024) return cand[i];
+    return 8;
+}
+
 // Enqueues the requested stages (bit 0 prep, 1 lm, 2 unc, 3 out) for one slice, in pipeline order.
 template <int MODEL, int L, int NG>
 cudaError_t lf_launch(const LfLaunch& a, int stages)
@@ -212,7 +224,8 @@ cudaError_t lf_launch(const LfLaunch& a, int stages)
         }
     }
     if ((stages & 4) && a.unc_ws) {
-        e = lf_launch_one(lf_unc_kernel<MODEL, L, NG>, a, LfUncWarps<L>::W, (size_t)a.xo_bytes + (size_t)LfUncWarps<L>::W * a.ly.un_bytes);
+        const int uw = lf_unc_warps_for(LfUncWarps<L>::W, (size_t)a.xo_bytes, (size_t)a.ly.un_bytes);
+        e = lf_launch_one(lf_unc_kernel<MODEL, L, NG>, a, uw, (size_t)a.xo_bytes + (size_t)uw * a.ly.un_bytes);
         if (e != cudaSuccess) return e;
     }
     if (stages & 8) {

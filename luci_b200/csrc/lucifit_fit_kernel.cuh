@@ -26,12 +26,11 @@
 template <int NA> struct LfLmBlocks {
     enum { W = NA <= 44 ? LF_LM_WARPS_SMALL : NA <= 77 ? 12 : 8, V = NA <= 44 ? LF_LM_MINB_SMALL : 1 };
 };
-// The uncertainty kernel is bound by its per-warp shared memory (13 L variant records, the variant / sum tiles):
-// one CTA per SM with as many warps as fit 227 KB -- 16 up to 6 lines, 12 beyond (96.2 / 91.9 / 89.6 / 91.3 ms per 2^20
-// spaxels with 4 / 8 / 16 / 18 warps per CTA for the 5-line sincgauss).
-// The uncertainty kernel: one CTA per SM as well; 20 warps at 96 registers (76 bytes of spills) beat 16 at 128 -- 31.6 against
-// 34.4 ms per 2^19 spaxels -- where 20 warps' scratch (11.2 KB each at L = 5) still fits the SM; the launcher steps down to
-// 16 / 12 / 8 warps when it does not (lf_unc_warps_for).
+// The uncertainty kernel is bound by its per-warp shared memory (13 L variant records, the variant / sum tiles): one CTA per
+// SM with as many warps as fit 227 KB -- 20 up to 5 lines (11.2 KB each at L = 5), 16 at 6, 12 beyond.  Round 1 measured
+// 96.2 / 91.9 / 89.6 / 91.3 ms per 2^20 spaxels with 4 / 8 / 16 / 18 warps per CTA; with the leaner code of round 2, 20 warps
+// at 96 registers (76 bytes of spills) beat 16 at 128: 31.6 against 34.4 ms per 2^19 spaxels.  The launcher steps down to
+// 16 / 12 / 8 warps when the scratch of a configuration does not fit (lf_unc_warps_for).
 #ifndef LF_UNC_WARPS
 #define LF_UNC_WARPS 20
 #endif

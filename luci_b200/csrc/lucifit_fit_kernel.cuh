@@ -2,6 +2,7 @@
 // slice) and their launcher.  Each kernel keeps one small hot loop resident in the SM's instruction cache; a spaxel
 // travels between them as a state record in the caller's workspace (lucifit_core.cuh, LF_SO_*).
 #pragma once
+#include <nvtx3/nvToolsExt.h>   // header-only; the ranges cost nothing unless a profiler is attached
 #include <cuda_runtime.h>
 #include "lucifit_core.cuh"
 
@@ -208,12 +209,15 @@ template <int MODEL, int L, int NG>
 cudaError_t lf_launch(const LfLaunch& a, int stages)
 {
     cudaError_t e = cudaSuccess;
+    struct Range { explicit Range(const char* n) { nvtxRangePushA(n); } ~Range() { nvtxRangePop(); } };
     if (stages & 1) {
+        Range r("lucifit:prep");
         const int pw = lf_pick_warps(LF_PREP_WARPS, 0, (size_t)a.ly.prep_bytes);
         e = lf_launch_one(lf_prep_kernel<MODEL, L, NG>, a, pw, (size_t)pw * a.ly.prep_bytes);
         if (e != cudaSuccess) return e;
     }
     if (stages & 2) {
+        Range r("lucifit:lm");
         constexpr int LMW = LfLmBlocks<LfDims<MODEL, L, NG, NG>::NA>::W;
         e = lf_launch_one(lf_lm_kernel<MODEL, L, NG, 1>, a, LMW, (size_t)a.xo_bytes + (size_t)LMW * a.ly.lm_bytes);
         if (e != cudaSuccess) return e;
@@ -223,11 +227,13 @@ cudaError_t lf_launch(const LfLaunch& a, int stages)
         }
     }
     if ((stages & 4) && a.unc_ws) {
+        Range r("lucifit:unc");
         const int uw = lf_unc_warps_for(LfUncWarps<L>::W, (size_t)a.xo_bytes, (size_t)a.ly.un_bytes);
         e = lf_launch_one(lf_unc_kernel<MODEL, L, NG>, a, uw, (size_t)a.xo_bytes + (size_t)uw * a.ly.un_bytes);
         if (e != cudaSuccess) return e;
     }
     if (stages & 8) {
+        Range r("lucifit:out");
         const int ow = lf_pick_warps(LF_OUT_WARPS, (size_t)a.xo_bytes, (size_t)a.ly.out_bytes);
         const size_t smem = (size_t)a.xo_bytes + (size_t)ow * a.ly.out_bytes;
         e = a.stage_rows ? lf_launch_one(lf_out_kernel<MODEL, L, NG, true>, a, ow, smem)

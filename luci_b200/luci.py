@@ -31,6 +31,26 @@ from .constants import LINE_DICT, snr_windows
 from .fitsio import read_fits, save_fits, wcs_to_header, write_fits
 
 
+def _nvtx(name):
+    """Decorator: an NVTX range around a method (visible in Nsight captures next to the library's own lucifit:prep / lm /
+    unc / out ranges; the reference has only tqdm bars, LuciBase.py:530)."""
+    def wrap(fn):
+        import functools
+
+        @functools.wraps(fn)
+        def inner(*a, **k):
+            on = torch.cuda.is_available()
+            if on:
+                torch.cuda.nvtx.range_push(name)
+            try:
+                return fn(*a, **k)
+            finally:
+                if on:
+                    torch.cuda.nvtx.range_pop()
+        return inner
+    return wrap
+
+
 SKYLINE_V0 = 80.0          # km/s: the reference's initial guess for the sky-line velocity (LuciFit.py:859)
 # Component search of a multi-component fit started from ONE prior pair (all the reference's CNN can give): the same
 # line in two velocity groups starts exactly symmetric, a saddle of the objective the reference only leaves through the
@@ -172,6 +192,7 @@ class Luci():
                                                                          self.spectrum_axis_unshifted)
 
     # -------------------------------------------------------------------------------------------- reductions
+    @_nvtx('luci:create_deep_image')
     def create_deep_image(self, output_name=None, binning=None):
         """``LuciBase.py:147-215``: sum over the spectral axis, transposed to (ny, nx), written as FITS."""
         nx, ny, nz = self.cube_final.shape
@@ -205,6 +226,7 @@ class Luci():
                 hb[key] = hb[key] * binning
         self.header_binned = hb        # the reference mutates self.header in place here; that bug is not replicated
 
+    @_nvtx('luci:create_snr_map')
     def create_snr_map(self, x_min=0, x_max=2048, y_min=0, y_max=2064, method=1, n_threads=2, lines=[None],
                        binning=1, bkgType=None, pca_coefficient_array=None, pca_vectors=None, pca_mean=None):
         """``LuciBase.py:1048-1191``.  Returns the four masked arrays (SNR >= 1, 3, 5, 10) like the reference."""
@@ -266,6 +288,7 @@ class Luci():
             origin = cutout_origin(x_min, x_max, y_min, y_max, nx_f, ny_f, strict_reference=self.strict_reference)
         return wcs_to_header(header, origin)
 
+    @_nvtx('luci:fit_maps')
     def _fit_maps(self, cube3d, lines, fit_function, vel_rel, sigma_rel, x_min, x_max, y_min, y_max, mask, bkg,
                   bkg_scale, uncertainty_bool, nii_cons, spec_min, spec_max, obj_redshift, prior_values, n_stoch=1,
                   pca=None, initial_values=(False,), absorp=None):
@@ -483,6 +506,7 @@ class Luci():
             st['be'] = torch.empty((K, n), dtype=torch.int32, pin_memory=True)
         return st
 
+    @_nvtx('luci:save_maps')
     def _save_maps(self, lines, m, header, binning, shape, fit_function=None, suffix=''):
         """The FITS maps of a fit (LuciUtility.save_fits layout), from the big-endian staging copy when the fit left one."""
         if not self._is_writer():

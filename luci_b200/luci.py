@@ -646,6 +646,14 @@ class Luci():
                              self.cube_final.shape[1], bkg=bkg, binning=binning, bayes_bool=bayes_bool,
                              uncertainty_bool=uncertainty_bool, n_threads=n_threads, **kwargs)
 
+    def close(self):
+        """``LuciBase.py:1302-1309``: drop the cube (here: its device memory) and the header."""
+        self.cube_final = None
+        self.header = None
+        self.cube_binned = None
+        if torch.cuda.is_available():
+            torch.cuda.empty_cache()
+
     def _load_mask(self, region, pixel_list):
         if pixel_list is not False:
             mask = np.ones((self.cube_final.shape[0], self.cube_final.shape[1]), dtype=bool)   # LuciBase.py:637-639

@@ -338,6 +338,52 @@ def test_extract_spectrum_and_region(world):
     np.testing.assert_allclose(specr, host[1:4, 2:9].sum(axis=(0, 1)) / 21, rtol=1e-12)
 
 
+def test_config1_sinc_strip_through_fit_region_map_for_map(tmp_path):
+    """BASELINE config 1 as the reference ran it (oracle/make_golden.py::make_region_strip: a 100 x 8 LuciSim strip, five-line
+    sinc, ``fit_region`` with a 70 % mask, every y-row through the reference's own row worker, maps assembled like
+    LuciBase.py:706-718) through ``Luci.fit_region`` on the GPU, map for map:
+
+      * the maps are the rows of the same 562 spaxels fitted through the C ABI directly, zeros outside the mask like the
+        reference's;
+      * those rows meet the fixture bar (every spaxel on the optimum of the reference's objective or a lower minimum);
+      * wherever the reference's SLSQP answer sits on that optimum, the velocity / flux / chi2 MAPS agree with the
+        reference's maps within the north_star tolerances."""
+    from luci_b200 import engine
+    from luci_b200.luci import Luci
+    from tests.common import assert_fixture_parity, config_from_golden, golden_priors, split_rows
+    g = load_golden('region_sinc_strip')
+    dev = torch.device('cuda', 0)
+    lines = [str(x) for x in g['lines']]
+    hdr_dict = {'FILTER': 'SN3', 'STEP': int(g['delta_x']), 'STEPNB': int(g['n_steps']), 'ZPDINDEX': 0}
+    luci = Luci.from_arrays(g['cube3d'], hdr_dict, str(tmp_path), 'STRIP', spectrum_axis=g['axis32'], device=dev)
+    mask = np.asarray(g['mask'], bool)
+    vel, broad, flux, chi2, m = luci.fit_region(lines, 'sinc', [1] * 5, [1] * 5, mask, prior_values=(g['v0map'], g['b0map']))
+    assert vel.shape == (8, 100, 5) and chi2.shape == (8, 100)
+    for ours, ref in ((vel, g['map_velocities']), (flux, g['map_fluxes']), (chi2, g['map_chi2'])):
+        assert (ours[~mask.T] == 0).all() and (ref[~mask.T] == 0).all()
+    # the same spaxels through the C ABI, in the fixture's (y, x) order
+    cfg = config_from_golden(g)
+    v0, b0 = golden_priors(g)
+    t = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(dev)
+    res = engine.fit_batch(cfg, t(g['cube'].astype(np.float32)), t(g['theta']), t(v0), t(b0))
+    rows, st = res['rows'].cpu().numpy(), res['status'].cpu().numpy()
+    q = split_rows(rows, 5)
+    y, x = g['yx'][:, 0], g['yx'][:, 1]
+    np.testing.assert_allclose(vel[y, x], q['velocities'], rtol=1e-6, atol=1e-4)
+    np.testing.assert_allclose(flux[y, x], q['fluxes'], rtol=1e-6)
+    np.testing.assert_allclose(chi2[y, x], q['chi2'], rtol=1e-6)
+    rep, opt, direct = assert_fixture_parity('region_sinc_strip', rows, st, g)
+    assert opt['same'].mean() >= 0.99 and direct.mean() >= 0.8, (opt['same'].mean(), direct.mean())
+    # map for map against the reference where the reference found its optimum
+    yd, xd = y[direct], x[direct]
+    assert np.abs(vel[yd, xd] - g['map_velocities'][yd, xd]).max() <= 0.5
+    fr = g['map_fluxes'][yd, xd].astype(np.float64)
+    den = np.maximum(np.abs(fr), 1e-3 * np.abs(fr).max(axis=1, keepdims=True))
+    assert (np.abs(flux[yd, xd] - fr) / den).max() <= 1e-3
+    cr = g['map_chi2'][yd, xd].astype(np.float64)
+    assert ((chi2[yd, xd] - cr) / cr).max() <= 1e-4
+
+
 def test_ds9_region_files_through_the_api(world, tmp_path):
     """``region='x.reg'`` (LuciBase.py:622-624, 917-919, 985-987 -> LuciConvenience.reg_to_mask): the ds9 file gives the
     same spectrum / maps as the boolean mask it describes, in pixel and in sky coordinates (the fixture's WCS is one

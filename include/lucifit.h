@@ -203,7 +203,10 @@ int lucifit_segment_sum(const float* cube, int nz, const int64_t* row_index, con
  *                        LUCIFIT_PEER_HANDLE_BYTES bytes (a cudaIpcMemHandle_t of the enclosing allocation).
  *   lucifit_peer_open:   maps it into this process on the CURRENT device and returns the pointer.
  *   lucifit_peer_close:  unmaps (same pointer and offset as returned / given to lucifit_peer_open).
- * Completion: a rank's rows are in place when its stream has drained; the ranks then meet at a barrier. */
+ * Completion: a rank's rows are in place when its stream has drained; the ranks then meet at a barrier.
+ * The library keeps the ranges it has mapped: when out_rows of lucifit_fit_batch / lucifit_fit_stages lies inside one,
+ * the output kernel assembles each row in shared memory and writes it as whole 128-byte lines (2 NVLink writes per row
+ * instead of 12 small ones). */
 #define LUCIFIT_PEER_HANDLE_BYTES 64
 int lucifit_peer_export(const void* dev_ptr, void* handle, uint64_t* offset);
 int lucifit_peer_open(const void* handle, uint64_t offset, void** dev_ptr);
